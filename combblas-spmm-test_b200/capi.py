@@ -1,0 +1,318 @@
+"""ctypes binding of the C ABI (include/combblas_b200.h).  Plumbing for tests/ and bench.py only:
+the product's host layer is the C++ header set under include/CombBLAS/."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+F32, F64, I32, I64, U8, PATTERN = 0, 1, 2, 3, 4, 255
+PLUS_TIMES, MIN_PLUS, MAX_SEL2ND, OR_AND = 0, 1, 2, 3
+NP_OF = {F32: np.float32, F64: np.float64, I32: np.int32, I64: np.int64, U8: np.uint8}
+CODE_OF = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32, np.dtype(np.int64): I64,
+           np.dtype(np.uint8): U8, np.dtype(np.bool_): U8}
+
+# every symbol include/combblas_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_create", "cb_ctx_create_grid",
+           "cb_ctx_destroy", "cb_ctx_grid", "cb_ctx_sync", "cb_ctx_stream", "cb_last_error", "cb_status_string",
+           "cb_timer_start", "cb_timer_stop", "cb_tile_upload_csc", "cb_tile_upload_coo", "cb_tile_from_device_coo",
+           "cb_tile_free", "cb_tile_info", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
+           "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
+           "cb_spmm_summa", "cb_summa_times", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
+
+
+class CBError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"combblas_b200 status {status}: {text}")
+        self.status = status
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "lib", "libcombblas_b200.so")
+
+
+def build_library(jobs: int = 8) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (csrc/Makefile), in-tree."""
+    subprocess.check_call(["make", "-s", f"-j{jobs}", "-C", os.path.join(HERE, "csrc")])
+    return library_path()
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library.  Missing library = hard error: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise CBError(-1, f"{path} is missing: build it with build_library() / __graft_entry__.build(); "
+                              "the product has no CPU fallback")
+        L = ctypes.CDLL(path)
+        L.cb_last_error.restype = c_char_p
+        L.cb_last_error.argtypes = [c_void_p]
+        L.cb_status_string.restype = c_char_p
+        L.cb_ctx_stream.restype = c_void_p
+        L.cb_ctx_stream.argtypes = [c_void_p]
+        L.cb_launch_count.restype = c_int64
+        L.cb_launch_count.argtypes = [c_void_p]
+        L.cb_ctx_create.argtypes = [c_int, POINTER(c_void_p)]
+        L.cb_ctx_create_grid.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]
+        L.cb_ctx_destroy.argtypes = [c_void_p]
+        L.cb_ctx_sync.argtypes = [c_void_p]
+        L.cb_ctx_grid.argtypes = [c_void_p] + [POINTER(c_int)] * 5
+        L.cb_comm_unique_id.argtypes = [c_void_p]
+        L.cb_timer_start.argtypes = [c_void_p]
+        L.cb_timer_stop.argtypes = [c_void_p, POINTER(c_float)]
+        L.cb_tile_upload_csc.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int, c_int, POINTER(c_void_p)]
+        L.cb_tile_upload_coo.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                         POINTER(c_void_p)]
+        L.cb_tile_from_device_coo.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                              POINTER(c_void_p)]
+        L.cb_tile_free.argtypes = [c_void_p]
+        L.cb_tile_info.argtypes = [c_void_p, POINTER(c_int64)]
+        L.cb_tile_download_csr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+        L.cb_dense_alloc.argtypes = [c_void_p, c_int64, c_int64, c_int, POINTER(c_void_p)]
+        L.cb_dense_wrap.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]
+        L.cb_dense_free.argtypes = [c_void_p]
+        L.cb_dense_upload.argtypes = [c_void_p, c_void_p, c_int64]
+        L.cb_dense_download.argtypes = [c_void_p, c_void_p, c_int64]
+        L.cb_dense_fill.argtypes = [c_void_p, c_void_p]
+        L.cb_dense_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int),
+                                    POINTER(c_void_p)]
+        L.cb_semiring_id.argtypes = [c_int, c_int, c_void_p]
+        L.cb_spmm_local.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
+        L.cb_spmm_summa.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64]
+        L.cb_summa_times.argtypes = [c_void_p, POINTER(c_float)]
+        L.cb_spmm_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int]
+        L.cb_profile_enable.argtypes = [c_void_p, c_int]
+        L.cb_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
+        L.cb_gen_rmat_tile.argtypes = [c_void_p, c_int, c_int, c_uint64, POINTER(c_double), c_int, c_int64, c_int64,
+                                       c_int64, c_int64, c_int, c_uint64, POINTER(c_void_p)]
+        L.cb_gen_dense.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int64, c_int]
+        _lib = L
+    return _lib
+
+
+def _check(status, ctx=None):
+    if status != 0:
+        text = lib().cb_last_error(ctx) or b""
+        raise CBError(status, text.decode() or lib().cb_status_string(status).decode())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(c_void_p)
+    return c_void_p(int(a))
+
+
+def unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().cb_comm_unique_id(buf))
+    return buf.raw
+
+
+class Context:
+    """One device + its place in the pr x pc process grid (CommGrid, reference CommGrid.h:44-166)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, pr=1, pc=1, uid: bytes | None = None):
+        self.h = c_void_p()
+        if nranks == 1:
+            _check(lib().cb_ctx_create(device, byref(self.h)))
+        else:
+            buf = ctypes.create_string_buffer(uid, 128)
+            _check(lib().cb_ctx_create_grid(device, rank, nranks, pr, pc, buf, byref(self.h)))
+        self.rank, self.nranks, self.pr, self.pc = rank, nranks, pr, pc
+        self.myprocrow, self.myproccol = rank // pc, rank % pc
+
+    def close(self):
+        if self.h:
+            lib().cb_ctx_destroy(self.h)
+            self.h = c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        _check(lib().cb_ctx_sync(self.h), self.h)
+
+    @property
+    def stream(self):
+        return lib().cb_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().cb_launch_count(self.h)
+
+    def profile(self, on=True):
+        _check(lib().cb_profile_enable(self.h, int(on)), self.h)
+
+    def profile_read(self):
+        """-> ({'fill','spmm','fixup'} -> summed ms, same -> launches) since profile(True)."""
+        ms, n = (c_double * 3)(), (c_int64 * 3)()
+        _check(lib().cb_profile_read(self.h, ms, n), self.h)
+        names = ("fill", "spmm", "fixup")
+        return dict(zip(names, ms)), dict(zip(names, n))
+
+    def timer_start(self):
+        _check(lib().cb_timer_start(self.h), self.h)
+
+    def timer_stop(self) -> float:
+        ms = c_float()
+        _check(lib().cb_timer_stop(self.h, byref(ms)), self.h)
+        return ms.value
+
+    # ---- tiles
+    def tile_from_csc(self, m, n, cp, ir, numx=None, jc=None, pattern=None):
+        """Column-compressed arrays as the reference ships them (SpDCCols::GetArrays): jc=None means plain CSC."""
+        idx = np.int64 if np.asarray(cp).dtype == np.int64 else np.int32
+        cp = np.ascontiguousarray(cp, idx)
+        ir = np.ascontiguousarray(ir, idx)
+        jc_ = None if jc is None else np.ascontiguousarray(jc, idx)
+        vd, vals = _vals(numx)
+        t = c_void_p()
+        _check(lib().cb_tile_upload_csc(self.h, m, n, len(ir), 0 if jc_ is None else len(jc_), _ptr(cp), _ptr(jc_),
+                                        _ptr(ir), _ptr(vals), CODE_OF[np.dtype(idx)], vd, byref(t)), self.h)
+        return Tile(self, t)
+
+    def tile_from_coo(self, m, n, rows, cols, vals=None):
+        idx = np.int64 if np.asarray(rows).dtype == np.int64 else np.int32
+        rows = np.ascontiguousarray(rows, idx)
+        cols = np.ascontiguousarray(cols, idx)
+        vd, v = _vals(vals)
+        t = c_void_p()
+        _check(lib().cb_tile_upload_coo(self.h, m, n, len(rows), _ptr(rows), _ptr(cols), _ptr(v), CODE_OF[np.dtype(idx)],
+                                        vd, byref(t)), self.h)
+        return Tile(self, t)
+
+    def tile_from_device_coo(self, m, n, nz, d_rows, d_cols, d_vals=None, val_dtype=PATTERN):
+        t = c_void_p()
+        _check(lib().cb_tile_from_device_coo(self.h, m, n, nz, _ptr(d_rows), _ptr(d_cols), _ptr(d_vals), val_dtype,
+                                             byref(t)), self.h)
+        return Tile(self, t)
+
+    def gen_rmat_tile(self, scale, edgefactor=16, seed=0, initiator=(0.57, 0.19, 0.19, 0.05), symmetric=True,
+                      row0=0, m=None, col0=0, n=None, val_dtype=PATTERN, val_seed=1):
+        N = 1 << scale
+        m = N if m is None else m
+        n = N if n is None else n
+        init = (c_double * 4)(*initiator)
+        t = c_void_p()
+        _check(lib().cb_gen_rmat_tile(self.h, scale, edgefactor, seed, init, int(symmetric), row0, m, col0, n, val_dtype,
+                                      val_seed, byref(t)), self.h)
+        return Tile(self, t)
+
+    # ---- dense panels
+    def dense(self, rows, cols, dtype):
+        d = c_void_p()
+        code = dtype if isinstance(dtype, int) else CODE_OF[np.dtype(dtype)]
+        _check(lib().cb_dense_alloc(self.h, rows, cols, code, byref(d)), self.h)
+        return Dense(self, d, rows, cols, code)
+
+    def dense_from(self, host: np.ndarray):
+        host = np.ascontiguousarray(host)
+        if host.dtype == np.bool_:
+            host = host.view(np.uint8)
+        d = self.dense(host.shape[0], host.shape[1], host.dtype)
+        d.upload(host)
+        return d
+
+    def wrap(self, device_ptr, rows, cols, ld, dtype):
+        d = c_void_p()
+        code = dtype if isinstance(dtype, int) else CODE_OF[np.dtype(dtype)]
+        _check(lib().cb_dense_wrap(self.h, c_void_p(device_ptr), rows, cols, ld, code, byref(d)), self.h)
+        return Dense(self, d, rows, cols, code)
+
+    # ---- multiply
+    def spmm_local(self, tile, X, Y, semiring, accumulate=False):
+        _check(lib().cb_spmm_local(self.h, tile.h, X.h, Y.h, semiring, int(accumulate)), self.h)
+
+    def spmm_summa(self, tile, X, Y, semiring, gm, gn, gk):
+        _check(lib().cb_spmm_summa(self.h, tile.h, X.h, Y.h, semiring, gm, gn, gk), self.h)
+
+    def summa_times(self):
+        ms = (c_float * 4)()
+        _check(lib().cb_summa_times(self.h, ms), self.h)
+        return list(ms)
+
+    def spmm_host(self, tile, X: np.ndarray, semiring, Y: np.ndarray | None = None):
+        """Host panels in, host panel out (upload, multiply, download): the e2e path."""
+        Xc = np.ascontiguousarray(X)
+        if Xc.dtype == np.bool_:
+            Xc = Xc.view(np.uint8)
+        k = Xc.shape[1]
+        if Y is None:
+            Y = np.empty((tile.m, k), Xc.dtype)
+        _check(lib().cb_spmm_host(self.h, tile.h, _ptr(Xc), k, _ptr(Y), k, k, CODE_OF[Xc.dtype], semiring), self.h)
+        return Y
+
+
+def _vals(v):
+    if v is None:
+        return PATTERN, None
+    v = np.ascontiguousarray(v)
+    if v.dtype == np.bool_:
+        v = v.view(np.uint8)
+    return CODE_OF[v.dtype], v
+
+
+class Tile:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+        info = (c_int64 * 8)()
+        _check(lib().cb_tile_info(h, info))
+        (self.nnz, self.m, self.n, self.nzr, self.nzc, self.nchunks, self.nsplit, self.bytes) = list(info)
+
+    def free(self):
+        if self.h:
+            lib().cb_tile_free(self.h)
+            self.h = c_void_p()
+
+    def to_csr(self, val_dtype=None):
+        rowptr = np.empty(self.m + 1, np.int64)
+        col = np.empty(self.nnz, np.int64)
+        vals = None if val_dtype is None else np.empty(self.nnz, val_dtype)
+        _check(lib().cb_tile_download_csr(self.h, _ptr(rowptr), _ptr(col), _ptr(vals)), self.ctx.h)
+        return rowptr, col, vals
+
+
+class Dense:
+    def __init__(self, ctx, h, rows, cols, code):
+        self.ctx, self.h, self.rows, self.cols, self.code = ctx, h, rows, cols, code
+
+    def free(self):
+        if self.h:
+            lib().cb_dense_free(self.h)
+            self.h = c_void_p()
+
+    def info(self):
+        r, c, ld, dt, p = c_int64(), c_int64(), c_int64(), c_int(), c_void_p()
+        lib().cb_dense_info(self.h, byref(r), byref(c), byref(ld), byref(dt), byref(p))
+        return r.value, c.value, ld.value, dt.value, p.value
+
+    def upload(self, host: np.ndarray, ld=None):
+        host = np.ascontiguousarray(host) if ld is None else host
+        _check(lib().cb_dense_upload(self.h, _ptr(host), host.shape[1] if ld is None else ld), self.ctx.h)
+
+    def download(self, out: np.ndarray | None = None):
+        if out is None:
+            out = np.empty((self.rows, self.cols), NP_OF[self.code])
+        _check(lib().cb_dense_download(self.h, _ptr(out), out.shape[1] if out.ndim == 2 else self.cols), self.ctx.h)
+        return out
+
+    def fill(self, value):
+        v = np.array([value], NP_OF[self.code])
+        _check(lib().cb_dense_fill(self.h, _ptr(v)), self.ctx.h)
+
+    def generate(self, seed, row0=0, col0=0, gk=None, kind=0):
+        _check(lib().cb_gen_dense(self.h, seed, row0, col0, self.cols if gk is None else gk, kind), self.ctx.h)

@@ -1,0 +1,134 @@
+// cb_spmm_local / cb_spmm_host: validation, K3 (identity fill of empty rows) and dispatch into K2.
+#include "cb_spmm_dispatch.cuh"
+
+// K3: rows of the tile without nonzeros receive SR::id() - the dense-output convention of the reference's
+// dense SpMV (std::fill_n(localy, ysize, SR::id()), include/CombBLAS/ParFriends.h:1960-1963), restricted to
+// the rows K2 will not write so Y is written exactly once.
+__global__ void __launch_bounds__(256)
+cb_fill_rows_kernel(const int32_t* __restrict__ rows, int64_t nrows, char* __restrict__ Y, int64_t ldy_bytes,
+                    int row_bytes, uint4 pattern) {
+    const int vecs = row_bytes >> 4;
+    const int64_t total = nrows * vecs;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vecs;
+        const int v = (int)(i - r * vecs);
+        *reinterpret_cast<uint4*>(Y + (int64_t)rows[r] * ldy_bytes + v * 16) = pattern;
+    }
+}
+
+static uint4 id_pattern(int semiring, int dtype) {
+    unsigned char s[8] = {0};
+    cb_semiring_id(semiring, dtype, s);
+    unsigned char b[16];
+    const size_t es = cb_dtype_size(dtype);
+    for (size_t i = 0; i < 16; ++i) b[i] = s[i % es];
+    uint4 p;
+    memcpy(&p, b, 16);
+    return p;
+}
+
+int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const void* X, int64_t ldx, void* Y, int64_t ldy,
+                   int64_t k, int dtype, int semiring, int accumulate) {
+    const size_t es = cb_dtype_size(dtype);
+    if (!es) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm: dtype %d", dtype);
+    if (semiring == CB_PLUS_TIMES && dtype == CB_U8) semiring = CB_OR_AND;      // PlusTimesSRing<bool,bool>
+    int akind;
+    if (t->val_dtype == CB_PATTERN) akind = cbk::A_PATTERN;
+    else if (t->val_dtype == CB_U8) akind = cbk::A_BOOL;
+    else if (t->val_dtype == dtype) akind = cbk::A_SAME;
+    else return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm: tile values of dtype %d with a panel of dtype %d (promote_trait has no such pair)", t->val_dtype, dtype);
+    bool ok = false;
+    switch (semiring) {
+        case CB_PLUS_TIMES: ok = dtype != CB_U8; break;
+        case CB_OR_AND: ok = dtype == CB_U8 && akind != cbk::A_SAME; break;    // a CB_U8 tile was classified A_BOOL above
+        case CB_MIN_PLUS: ok = dtype != CB_U8 && akind == cbk::A_SAME; break;
+        case CB_MAX_SEL2ND: ok = dtype != CB_U8 && akind != cbk::A_SAME; break;
+    }
+    if (!ok) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm: semiring %d with tile dtype %d and panel dtype %d is not part of the ABI", semiring, t->val_dtype, dtype);
+    const int64_t row_bytes = (k * (int64_t)es + 15) / 16 * 16;
+    if (k <= 0 || t->m == 0) return CB_OK;
+    if (((uintptr_t)X | (uintptr_t)Y) & 15 || (ldx * es) % 16 || (ldy * es) % 16 || row_bytes > ldx * (int64_t)es || row_bytes > ldy * (int64_t)es)
+        return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm: panels must be 16-byte aligned with leading dimensions padded to 16 bytes (use cb_dense_alloc)");
+    if (row_bytes > (1 << 20)) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm: panel row of %lld bytes", (long long)row_bytes);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    if (!accumulate && t->m > t->nzr) {
+        const int64_t total = (t->m - t->nzr) * (row_bytes / 16);
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+        {
+            cb_prof_scope prof(ctx, stream, CB_PROF_FILL);
+            cb_fill_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(t->emptyrows, t->m - t->nzr, (char*)Y, ldy * (int64_t)es,
+                                                                      (int)row_bytes, id_pattern(semiring, dtype));
+        }
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+    }
+    if (t->nnz == 0) return CB_OK;
+    if (t->nsplit > 0) {
+        const size_t need = (size_t)2 * (size_t)t->nchunks * (size_t)row_bytes;
+        cb_tile* mt = const_cast<cb_tile*>(t);       // scratch only; grows to the widest panel seen
+        if (mt->carry_bytes < need) {
+            if (mt->carry) { CB_CUDA(ctx, cudaStreamSynchronize(stream)); CB_CUDA(ctx, cudaFree(mt->carry)); mt->carry = nullptr; mt->carry_bytes = 0; }
+            cudaError_t e = cudaMalloc(&mt->carry, need);
+            if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for the split-row carry buffer: %s", need, cudaGetErrorString(e));
+            mt->carry_bytes = need;
+        }
+    }
+    cbk::LaunchParams p;
+    p.ctx = ctx; p.stream = stream; p.t = t;
+    p.X = X; p.ldx_bytes = ldx * (int64_t)es;
+    p.Y = Y; p.ldy_bytes = ldy * (int64_t)es;
+    p.total_row_bytes = (int)row_bytes;
+    p.accumulate = accumulate;
+    switch (semiring) {
+        case CB_PLUS_TIMES:
+            return (dtype == CB_F32 || dtype == CB_F64) ? cb_launch_plus_times_f(dtype, akind, p) : cb_launch_plus_times_i(dtype, akind, p);
+        case CB_MIN_PLUS: return cb_launch_min_plus(dtype, p);
+        case CB_MAX_SEL2ND: return cb_launch_select_max(dtype, p);
+        case CB_OR_AND: return cb_launch_or_and(akind, p);
+    }
+    return CB_ERR_UNSUPPORTED;
+}
+
+extern "C" {
+
+int cb_spmm_local(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int semiring, int accumulate) {
+    if (!ctx || !t || !X || !Y) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_local: null argument");
+    // CheckSpGEMMCompliance (ParFriends.h:160-181): inner dimensions must agree
+    if (X->rows != t->n || Y->rows != t->m || X->cols != Y->cols)
+        return cb_fail(ctx, CB_ERR_DIMMISMATCH, "cb_spmm_local: A is %lld x %lld, X is %lld x %lld, Y is %lld x %lld",
+                       (long long)t->m, (long long)t->n, (long long)X->rows, (long long)X->cols, (long long)Y->rows, (long long)Y->cols);
+    if (X->dtype != Y->dtype) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm_local: X and Y dtypes differ");
+    if (X->ptr == Y->ptr) return cb_fail(ctx, CB_ERR_MATRIXALIAS, "cb_spmm_local: X and Y alias");
+    return cb_spmm_launch(ctx, ctx->compute, t, X->ptr, X->ld, Y->ptr, Y->ld, X->cols, X->dtype, semiring, accumulate);
+}
+
+static int ws_reserve(cb_ctx* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return CB_OK;
+    if (*p) { CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute)); CB_CUDA(ctx, cudaFree(*p)); *p = nullptr; *have = 0; }
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a host-path panel: %s", need, cudaGetErrorString(e));
+    *have = need;
+    return CB_OK;
+}
+
+int cb_spmm_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int64_t k,
+                 int dtype, int semiring) {
+    // X up, multiply, Y down - all on the compute stream; the device panels are kept in the ctx between calls.
+    const size_t es = cb_dtype_size(dtype);
+    if (!es || k <= 0 || ldx < k || ldy < k) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_host: bad dtype / k / leading dimension");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t per16 = 16 / (int64_t)es;
+    const int64_t ld = (k + per16 - 1) / per16 * per16;
+    CB_TRY(ws_reserve(ctx, &ctx->ws_x, &ctx->ws_x_bytes, (size_t)(t->n > 0 ? t->n : 1) * (size_t)ld * es));
+    CB_TRY(ws_reserve(ctx, &ctx->ws_y, &ctx->ws_y_bytes, (size_t)(t->m > 0 ? t->m : 1) * (size_t)ld * es));
+    if (ld != k) CB_CUDA(ctx, cudaMemsetAsync(ctx->ws_x, 0, (size_t)t->n * (size_t)ld * es, ctx->compute));
+    if (t->n) CB_CUDA(ctx, cudaMemcpy2DAsync(ctx->ws_x, (size_t)ld * es, X_host, (size_t)ldx * es, (size_t)k * es, (size_t)t->n, cudaMemcpyHostToDevice, ctx->compute));
+    CB_TRY(cb_spmm_launch(ctx, ctx->compute, t, ctx->ws_x, ld, ctx->ws_y, ld, k, dtype, semiring, 0));
+    if (t->m) CB_CUDA(ctx, cudaMemcpy2DAsync(Y_host, (size_t)ldy * es, ctx->ws_y, (size_t)ld * es, (size_t)k * es, (size_t)t->m, cudaMemcpyDeviceToHost, ctx->compute));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return CB_OK;
+}
+
+}  // extern "C"

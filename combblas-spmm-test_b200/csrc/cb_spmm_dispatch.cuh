@@ -1,0 +1,94 @@
+// Host-side launch of K2 (+ fix-up) for one semiring functor: picks the virtual-warp layout from the row width.
+#pragma once
+#include "cb_spmm_kernel.cuh"
+
+namespace cbk {
+
+struct LaunchParams {
+    cb_ctx* ctx;
+    cudaStream_t stream;
+    const cb_tile* t;
+    const void* X;
+    int64_t ldx_bytes;
+    void* Y;
+    int64_t ldy_bytes;
+    int total_row_bytes;      // padded to 16
+    int accumulate;
+};
+
+template <class Op, int VW, int R, int U>
+static int launch_layout(const LaunchParams& p) {
+    const cb_tile* t = p.t;
+    SpmmArgs a;
+    a.colflag = t->colflag;
+    a.vals = t->vals;
+    a.nzrows = t->nzrows;
+    a.chunk_start = t->chunk_start;
+    a.chunk_row = t->chunk_row;
+    a.nchunks = t->nchunks;
+    a.X = (const char*)p.X;
+    a.Y = (char*)p.Y;
+    a.ldx_bytes = p.ldx_bytes;
+    a.ldy_bytes = p.ldy_bytes;
+    a.slab_bytes = VW * R * 16;
+    a.row_bytes = a.slab_bytes;
+    a.total_row_bytes = p.total_row_bytes;
+    a.carry = (char*)t->carry;
+    a.carry_stride = p.total_row_bytes;
+    a.accumulate = p.accumulate;
+    constexpr int NV = 32 / VW;
+    const int64_t vws_per_block = 8 * NV;
+    dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
+    {
+        cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
+        cb_spmm_kernel<Op, VW, R, U><<<grid, 256, 0, p.stream>>>(a);
+    }
+    CB_LAUNCHED(p.ctx);
+    CB_CUDA(p.ctx, cudaGetLastError());
+    return CB_OK;
+}
+
+template <class Op>
+static int launch_op(const LaunchParams& p) {
+    const cb_tile* t = p.t;
+    if (t->nnz > 0) {
+        const int nvec = p.total_row_bytes / 16;
+        int s;
+        if (nvec <= 4) s = launch_layout<Op, 4, 1, 4>(p);
+        else if (nvec <= 8) s = launch_layout<Op, 8, 1, 8>(p);
+        else if (nvec <= 16) s = launch_layout<Op, 16, 1, 8>(p);
+        else if (nvec <= 32) s = launch_layout<Op, 32, 1, 8>(p);
+        else s = launch_layout<Op, 32, 2, 4>(p);
+        if (s != CB_OK) return s;
+        if (t->nsplit > 0) {
+            FixupArgs f;
+            f.split_row = t->split_row;
+            f.nsplit = t->nsplit;
+            f.nzrows = t->nzrows;
+            f.rowptr = t->rowptr;
+            f.chunk_len = t->chunk_len;
+            f.carry = (const char*)t->carry;
+            f.carry_stride = p.total_row_bytes;
+            f.Y = (char*)p.Y;
+            f.ldy_bytes = p.ldy_bytes;
+            f.total_row_bytes = p.total_row_bytes;
+            f.accumulate = p.accumulate;
+            {
+                cb_prof_scope prof(p.ctx, p.stream, CB_PROF_FIXUP);
+                cb_fixup_kernel<Op><<<(unsigned)((t->nsplit + 7) / 8), 256, 0, p.stream>>>(f);
+            }
+            CB_LAUNCHED(p.ctx);
+            CB_CUDA(p.ctx, cudaGetLastError());
+        }
+    }
+    return CB_OK;
+}
+
+}  // namespace cbk
+
+// per-family entry points (one translation unit each so they compile in parallel)
+int cb_launch_plus_times_f(int dtype, int akind, const cbk::LaunchParams& p);   // f32, f64
+int cb_launch_plus_times_i(int dtype, int akind, const cbk::LaunchParams& p);   // i32, i64
+int cb_launch_min_plus(int dtype, const cbk::LaunchParams& p);
+int cb_launch_select_max(int dtype, const cbk::LaunchParams& p);
+int cb_launch_or_and(int akind, const cbk::LaunchParams& p);

@@ -1,0 +1,312 @@
+// K2: local SpMM on a doubly-compressed-row tile, one virtual warp per work chunk.
+//
+//   Y[r, 0:k] (+)= (+)_p  A.val[p] (x) X[A.col[p], 0:k]          for the nonzeros p of row r
+//
+// Replaces LocalHybridSpGEMM restricted to a dense right-hand side (reference
+// include/CombBLAS/mtSpGEMM.h:213-460) and dcsc_gespmv generalised to k columns
+// (include/CombBLAS/Friends.h:63-78).  No tensor cores: this is a gather-bound contraction; the
+// design goal is bytes in flight, not flops.
+//
+// Mapping
+//   * A row of X is k*sizeof(T) bytes = nvec 16-byte vectors.  A "virtual warp" (vw) of VW lanes
+//     (VW = 4..32, power of two >= nvec/R) owns one row at a time; lane l holds R vectors.  A
+//     hardware warp therefore runs 32/VW independent vws: a 256-byte row (k=64 fp32) uses
+//     half-warps, a 128-byte row (k=32 int32) quarter... so every load instruction moves full
+//     128-byte lines regardless of k.
+//   * Work is nnz-balanced, not row-balanced: the tile builder cuts the nonzero stream into chunks
+//     of ~L nonzeros at row boundaries and cuts rows longer than L at multiples of L
+//     (cb_tile.cu).  One vw walks one chunk front to back.  Per step it loads VW (col,val) pairs
+//     with one coalesced load, then for groups of U pairs issues all U row gathers back to back
+//     (U*R 128-bit loads in flight per lane) before folding them into the accumulator in order.
+//   * The last nonzero of each row carries a flag in the top bit of its column index, so the walk
+//     never touches the row-pointer array; row ids come from the compressed nonempty-row list.
+//   * The semiring is a functor pair inlined into the loop; the first product of a row is stored,
+//     later ones are folded with add(product, acc) in ascending column order - the order of the
+//     reference's hash accumulator (mtSpGEMM.h:395-423), so unsplit rows are bit-identical for
+//     floating point as well.
+//   * Pieces of split rows go to a carry buffer (2 slots per chunk) and are combined in chunk order
+//     by cb_fixup_kernel: deterministic, no atomics.
+#pragma once
+#include "cb_common.cuh"
+
+namespace cbk {
+
+// ------------------------------------------------------------------------------ semiring functors
+// T is the register type of one element.  Booleans travel as bytes 0/1 and are processed four at
+// a time in a uint32_t (OR/AND are bitwise on 0/1 bytes).
+enum AKind { A_SAME = 0, A_PATTERN = 1, A_BOOL = 2 };
+
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }   // no FMA contraction:
+    static __device__ __forceinline__ float maxv() { return 3.402823466e+38f; }                 // multiply, then add
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double maxv() { return 1.7976931348623157e+308; }
+};
+template <> struct Arith<int32_t> {   // wrap-around like the host's two's complement arithmetic
+    static __device__ __forceinline__ int32_t add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+    static __device__ __forceinline__ int32_t mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+    static __device__ __forceinline__ int32_t maxv() { return 0x7fffffff; }
+};
+template <> struct Arith<int64_t> {
+    static __device__ __forceinline__ int64_t add(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
+    static __device__ __forceinline__ int64_t mul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+    static __device__ __forceinline__ int64_t maxv() { return 0x7fffffffffffffffLL; }
+};
+
+// PlusTimesSRing<TA,T>  (Semirings.h:212-232)
+template <typename T_, int AK>
+struct PlusTimes {
+    typedef T_ T;
+    typedef typename std::conditional<AK == A_SAME, T_, uint8_t>::type TA;
+    static constexpr int akind = AK;
+    static __device__ __forceinline__ T id() { return T(0); }
+    static __device__ __forceinline__ T add(T a, T b) { return Arith<T>::add(a, b); }
+    static __device__ __forceinline__ T mul(TA a, T x) {
+        if (AK == A_PATTERN) return x;                                   // static_cast<T>(true) * x
+        if (AK == A_BOOL) return Arith<T>::mul((T)(a != 0), x);          // static_cast<T>(a) * x
+        return Arith<T>::mul((T)a, x);
+    }
+};
+// MinPlusSRing<T,T>  (Semirings.h:235-255, inf_plus :40-47)
+template <typename T_>
+struct MinPlus {
+    typedef T_ T;
+    typedef T_ TA;
+    static constexpr int akind = A_SAME;
+    static __device__ __forceinline__ T id() { return Arith<T>::maxv(); }
+    static __device__ __forceinline__ T add(T a, T b) { return b < a ? b : a; }     // std::min(a, b)
+    static __device__ __forceinline__ T mul(TA a, T x) {
+        const T inf = Arith<T>::maxv();
+        return (a == inf || x == inf) ? inf : Arith<T>::add(a, x);
+    }
+};
+// SelectMaxSRing<bool,T>  (Semirings.h:191-210): multiply returns its second argument
+template <typename T_>
+struct SelectMax {
+    typedef T_ T;
+    typedef uint8_t TA;
+    static constexpr int akind = A_PATTERN;   // the stored boolean is never read
+    static __device__ __forceinline__ T id() { return T(-1); }
+    static __device__ __forceinline__ T add(T a, T b) { return a < b ? b : a; }     // std::max(a, b)
+    static __device__ __forceinline__ T mul(TA, T x) { return x; }
+};
+// PlusTimesSRing<bool,bool> (promote.h:78): + is OR, * is AND.  T = 4 packed 0/1 bytes.
+template <int AK>
+struct OrAnd {
+    typedef uint32_t T;
+    typedef uint8_t TA;
+    static constexpr int akind = AK;
+    static __device__ __forceinline__ T id() { return 0u; }
+    static __device__ __forceinline__ T add(T a, T b) { return a | b; }
+    static __device__ __forceinline__ T mul(TA a, T x) { return AK == A_PATTERN ? x : (x & (0u - (uint32_t)(a != 0))); }
+};
+
+// ------------------------------------------------------------------------------ 16-byte vectors
+template <typename T> struct alignas(16) Vec16 { T v[16 / sizeof(T)]; };
+
+template <typename T>
+__device__ __forceinline__ Vec16<T> ldg16(const void* p) {
+    // read-only path; X rows are re-used across the chip, keep them in L1/L2
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    Vec16<T> r;
+    *reinterpret_cast<uint4*>(&r) = u;
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ Vec16<T> ld16(const void* p) {
+    Vec16<T> r;
+    *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ void st16(void* p, const Vec16<T>& v) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+
+struct SpmmArgs {
+    const int32_t* __restrict__ colflag;
+    const void* __restrict__ vals;
+    const int32_t* __restrict__ nzrows;
+    const int32_t* __restrict__ chunk_start;
+    const int32_t* __restrict__ chunk_row;
+    int64_t nchunks;
+    const char* __restrict__ X;   // row-major, ldx_bytes between rows
+    char* __restrict__ Y;
+    int64_t ldx_bytes, ldy_bytes;
+    int row_bytes;                // bytes of one panel row handled per slab (<= VW*R*16)
+    int slab_bytes;               // VW*R*16: byte offset between column slabs (gridDim.y)
+    int total_row_bytes;          // k * sizeof(element)
+    char* __restrict__ carry;     // [2*nchunks] slots of carry_stride bytes
+    int64_t carry_stride;
+    int accumulate;
+};
+
+// One lane's share of a panel row: R vectors at byte offsets (vl + r*VW)*16.
+template <class Op, int R>
+struct RowFrag {
+    Vec16<typename Op::T> v[R];
+};
+
+template <class Op, int VW, int R, int U>
+__global__ void __launch_bounds__(256)
+cb_spmm_kernel(const SpmmArgs a) {
+    typedef typename Op::T T;
+    typedef typename Op::TA TA;
+    constexpr int EPL = 16 / sizeof(T);
+    constexpr int NV = 32 / VW;                       // virtual warps per warp
+    const int lane = threadIdx.x & 31;
+    const int vl = lane & (VW - 1);
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t chunk = warp * NV + (lane / VW);
+    const bool live = chunk < a.nchunks;
+
+    // this slab's columns
+    const int slab_off = blockIdx.y * a.slab_bytes;
+    const int slab_row_bytes = min(a.row_bytes, a.total_row_bytes - slab_off);
+    bool lane_on[R];
+    int off[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        off[r] = slab_off + (vl + r * VW) * 16;
+        lane_on[r] = (vl + r * VW) * 16 < slab_row_bytes;
+    }
+
+    int s = 0, e = 0, ridx = 0;
+    bool head_open = false;
+    if (live) {
+        s = a.chunk_start[chunk];
+        e = a.chunk_start[chunk + 1];
+        const int cr = a.chunk_row[chunk];
+        ridx = cr & 0x7fffffff;
+        head_open = cr < 0;
+    }
+    // every lane of the warp runs the same number of steps so the shuffles stay convergent
+    const int len = e - s;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+
+    const TA* __restrict__ vals = reinterpret_cast<const TA*>(a.vals);
+    RowFrag<Op, R> acc;
+    bool first = true;                 // no product folded into acc yet (hash table "key not registered", mtSpGEMM.h:410)
+    int row = live ? a.nzrows[ridx] : 0;
+    char* const carry_head = a.carry + (2 * chunk) * a.carry_stride;
+
+    for (int base = 0; base < maxlen; base += VW) {
+        const int p = s + base + vl;
+        int cf = 0;
+        TA av = TA();
+        if (p < e) {
+            cf = a.colflag[p];
+            if (Op::akind != A_PATTERN) av = vals[p];
+        }
+#pragma unroll
+        for (int j0 = 0; j0 < VW; j0 += U) {
+            RowFrag<Op, R> x[U];
+            int cfu[U];
+            TA avu[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cfu[u] = __shfl_sync(0xffffffffu, cf, j0 + u, VW);
+                if (Op::akind != A_PATTERN) avu[u] = (TA)__shfl_sync(0xffffffffu, av, j0 + u, VW);
+                valid[u] = (s + base + j0 + u) < e;
+                const char* xr = a.X + (int64_t)(cfu[u] & 0x7fffffff) * a.ldx_bytes;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (valid[u] && lane_on[r]) x[u].v[r] = ldg16<T>(xr + off[r]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (valid[u]) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+#pragma unroll
+                        for (int q = 0; q < EPL; ++q) {
+                            const T prod = Op::mul(Op::akind != A_PATTERN ? avu[u] : TA(), x[u].v[r].v[q]);
+                            acc.v[r].v[q] = first ? prod : Op::add(prod, acc.v[r].v[q]);
+                        }
+                    }
+                    first = false;
+                    if (cfu[u] < 0) {          // last nonzero of its row: write the row out
+                        char* dst;
+                        bool rmw = false;
+                        if (head_open) { dst = carry_head + slab_off; head_open = false; }            // piece of a split row
+                        else { dst = a.Y + (int64_t)row * a.ldy_bytes + slab_off; rmw = a.accumulate != 0; }
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (lane_on[r]) {
+                                char* d = dst + (vl + r * VW) * 16;
+                                if (rmw) {
+                                    const Vec16<T> y = ld16<T>(d);
+#pragma unroll
+                                    for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::add(y.v[q], acc.v[r].v[q]);
+                                }
+                                st16<T>(d, acc.v[r]);
+                            }
+                        }
+                        first = true;
+                        ++ridx;
+                        if (s + base + j0 + u + 1 < e) row = a.nzrows[ridx];
+                    }
+                }
+            }
+        }
+    }
+    // a row still open at the end of the chunk continues in the next chunk: park the piece
+    if (live && !first) {
+        char* dst = carry_head + (head_open ? 0 : a.carry_stride) + slab_off;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lane_on[r]) st16<T>(dst + (vl + r * VW) * 16, acc.v[r]);
+    }
+}
+
+// Combine the pieces of split rows in chunk order: Y[row] = tail[c0] (+) head[c0+1] (+) ... (+) head[c1].
+// One virtual warp of 32 lanes per split row, looping over the row's vectors.
+struct FixupArgs {
+    const int32_t* __restrict__ split_row;   // indices into nzrows
+    int64_t nsplit;
+    const int32_t* __restrict__ nzrows;
+    const int32_t* __restrict__ rowptr;
+    int chunk_len;
+    const char* __restrict__ carry;
+    int64_t carry_stride;
+    char* __restrict__ Y;
+    int64_t ldy_bytes;
+    int total_row_bytes;
+    int accumulate;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(256)
+cb_fixup_kernel(const FixupArgs a) {
+    typedef typename Op::T T;
+    constexpr int EPL = 16 / sizeof(T);
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsplit) return;
+    const int ridx = a.split_row[w];
+    const int rs = a.rowptr[ridx], re = a.rowptr[ridx + 1];
+    const int c0 = rs / a.chunk_len, c1 = (re - 1) / a.chunk_len;
+    char* yrow = a.Y + (int64_t)a.nzrows[ridx] * a.ldy_bytes;
+    for (int b = lane * 16; b < a.total_row_bytes; b += 32 * 16) {
+        Vec16<T> acc = ld16<T>(a.carry + (2 * (int64_t)c0 + 1) * a.carry_stride + b);
+        for (int c = c0 + 1; c <= c1; ++c) {
+            const Vec16<T> h = ld16<T>(a.carry + (2 * (int64_t)c) * a.carry_stride + b);
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) acc.v[q] = Op::add(h.v[q], acc.v[q]);
+        }
+        if (a.accumulate) {
+            const Vec16<T> y = ld16<T>(yrow + b);
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) acc.v[q] = Op::add(y.v[q], acc.v[q]);
+        }
+        st16<T>(yrow + b, acc);
+    }
+}
+
+}  // namespace cbk

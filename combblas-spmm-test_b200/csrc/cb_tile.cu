@@ -1,0 +1,387 @@
+// K1: build the device tile (doubly compressed rows + nnz-balanced work partition) from the
+// reference's column-compressed wire format or from COO triples.
+//
+// Replaces, on the device, what the reference does on the host when a tile is materialised:
+// SpDCCols(const SpTuples&, bool) / the threaded tuple ctor (include/CombBLAS/SpDCCols.cpp:108-184,
+// :197-304) and Transpose (:853-868).  Sorting uses CUB's device radix sort (set-up, not the hot loop).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+#include "cb_common.cuh"
+
+namespace {
+
+
+struct ToI64 { __host__ __device__ int64_t operator()(uint8_t v) const { return (int64_t)v; } };
+
+__host__ __device__ inline int bits_for(int64_t v) { int b = 1; while (b < 63 && (int64_t(1) << b) < v) ++b; return b; }
+
+template <typename IT>
+__global__ void expand_csc_kernel(const IT* __restrict__ cp, const IT* __restrict__ jc, const IT* __restrict__ ir,
+                                  int64_t ncp /* entries in cp minus 1 */, int64_t nz, uint64_t* __restrict__ keys) {
+    // one thread per nonzero: find its compressed column by binary search in cp, emit key = row<<32 | col
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = ncp;           // largest c with cp[c] <= p
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if ((int64_t)cp[mid] <= p) lo = mid; else hi = mid; }
+        const uint64_t col = jc ? (uint64_t)jc[lo] : (uint64_t)lo;
+        keys[p] = ((uint64_t)ir[p] << 32) | col;
+    }
+}
+
+template <typename IT>
+__global__ void coo_keys_kernel(const IT* __restrict__ rows, const IT* __restrict__ cols, int64_t nz, uint64_t* __restrict__ keys) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x)
+        keys[p] = ((uint64_t)rows[p] << 32) | (uint64_t)cols[p];
+}
+
+__global__ void iota_kernel(uint32_t* p, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+// per sorted nonzero: column index with the end-of-row flag, row-start flag, column presence
+__global__ void finish_entries_kernel(const uint64_t* __restrict__ keys, int64_t nz, int32_t* __restrict__ colflag,
+                                      uint8_t* __restrict__ rowstart, uint8_t* __restrict__ colseen) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t kcur = keys[p];
+        const uint32_t row = (uint32_t)(kcur >> 32), col = (uint32_t)kcur;
+        const bool last = (p == nz - 1) || ((uint32_t)(keys[p + 1] >> 32) != row);
+        const bool first = (p == 0) || ((uint32_t)(keys[p - 1] >> 32) != row);
+        colflag[p] = (int32_t)(col | (last ? 0x80000000u : 0u));
+        rowstart[p] = first ? 1 : 0;
+        colseen[col] = 1;
+    }
+}
+
+__global__ void row_ids_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ rowptr, int64_t nzr, int64_t nz,
+                               int32_t* __restrict__ nzrows, int32_t* __restrict__ rowptr_end) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nzr; i += (int64_t)gridDim.x * blockDim.x)
+        nzrows[i] = (int32_t)(keys[rowptr[i]] >> 32);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *rowptr_end = (int32_t)nz;
+}
+
+template <typename V>
+__global__ void gather_vals_kernel(const V* __restrict__ in, const uint32_t* __restrict__ perm, int64_t nz, V* __restrict__ out) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) out[p] = in[perm[p]];
+}
+
+// rows without nonzeros, ascending: row r is empty iff it is not in nzrows; its slot is r - (#nonempty rows below r)
+__global__ void empty_rows_kernel(const int32_t* __restrict__ nzrows, int64_t nzr, int64_t m, int32_t* __restrict__ emptyrows) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nzr;           // first index with nzrows[idx] >= r
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (nzrows[mid] < r) lo = mid + 1; else hi = mid; }
+        if (lo == nzr || nzrows[lo] != r) emptyrows[r - lo] = (int32_t)r;
+    }
+}
+
+// Work partition.  Chunk g nominally starts at nonzero g*L.  If that nonzero lies in a row of at most L nonzeros the
+// start is moved back to the row's first nonzero (short rows are never cut); otherwise the long row is cut right there.
+__global__ void chunk_kernel(const int32_t* __restrict__ rowptr, int64_t nzr, int64_t nz, int32_t L, int64_t nchunks,
+                             int32_t* __restrict__ chunk_start, int32_t* __restrict__ chunk_row) {
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g <= nchunks; g += (int64_t)gridDim.x * blockDim.x) {
+        if (g == nchunks) { chunk_start[g] = (int32_t)nz; continue; }
+        const int64_t pos = g * L;
+        int64_t lo = 0, hi = nzr;           // largest ridx with rowptr[ridx] <= pos
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rowptr[mid] <= pos) lo = mid; else hi = mid; }
+        const int32_t rs = rowptr[lo], re = rowptr[lo + 1];
+        if (re - rs > L) {
+            chunk_start[g] = (int32_t)pos;
+            chunk_row[g] = (int32_t)((uint32_t)lo | (pos > rs ? 0x80000000u : 0u));
+        } else {
+            chunk_start[g] = rs;
+            chunk_row[g] = (int32_t)lo;
+        }
+    }
+}
+
+__global__ void split_rows_kernel(const int32_t* __restrict__ rowptr, int64_t nzr, int32_t L, int32_t* __restrict__ out,
+                                  unsigned long long* __restrict__ count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nzr; i += (int64_t)gridDim.x * blockDim.x)
+        if (rowptr[i + 1] - rowptr[i] > L) {
+            const unsigned long long slot = atomicAdd(count, 1ULL);
+            if (out) out[slot] = (int32_t)i;
+        }
+}
+
+inline int grid_for(int64_t n, int sm) {
+    int64_t b = (n + 255) / 256;
+    int64_t cap = (int64_t)sm * 32;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int pick_chunk_len(int64_t nnz) {
+    // enough chunks for ~4 waves of resident virtual warps on 148 SMs, but long enough that the carry traffic of
+    // split rows (2 panel rows per chunk) stays ~1/L of the gather traffic
+    int64_t L = nnz / 32768;
+    int p = 32;
+    while (p * 2 <= L && p < 512) p *= 2;
+    return p;
+}
+
+// keys (row<<32|col) on the device, unsorted -> tile.  `vals` (device, nz elements of val_dtype) may be NULL.
+}  // namespace
+
+// keys (row<<32|col) on the device -> tile.  `d_vals` (device, nz elements of val_dtype, in the order of d_keys) may be
+// NULL.  presorted: keys are already ascending and unique (the generators sort while deduplicating).
+int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint64_t* d_keys, const void* d_vals,
+                            int val_dtype, bool presorted, cb_scratch& sc, cb_tile** out) {
+    const int sm = ctx->sm_count;
+    cudaStream_t st = ctx->compute;
+    cb_tile* t = new cb_tile();
+    t->ctx = ctx; t->m = m; t->n = n; t->nnz = nz; t->val_dtype = val_dtype;
+    *out = nullptr;
+    auto fail = [&](int s) { cb_tile_free(t); return s; };
+#define T_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cb_fail(ctx, e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return fail(e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA); } } while (0)
+    const size_t vs = cb_dtype_size(val_dtype);
+    T_CUDA(cudaMalloc((void**)&t->emptyrows, sizeof(int32_t) * (size_t)(m > 0 ? m : 1)));
+    if (nz == 0) {
+        if (m > 0) { empty_rows_kernel<<<grid_for(m, sm), 256, 0, st>>>(nullptr, 0, m, t->emptyrows); CB_LAUNCHED(ctx); }
+        T_CUDA(cudaStreamSynchronize(st));
+        t->bytes = sizeof(int32_t) * (size_t)m;
+        *out = t;
+        return CB_OK;
+    }
+    // 1. stable radix sort by (row, col)
+    uint64_t* keys_sorted = d_keys; uint32_t *perm = nullptr, *perm_sorted = nullptr;
+    const int end_bit = 32 + bits_for(m);
+    size_t tmp_bytes = 0;
+    void* tmp = nullptr;
+    if (presorted) {
+        // nothing to do
+    } else if (d_vals) {
+        T_CUDA(sc.alloc(&keys_sorted, (size_t)nz));
+        T_CUDA(sc.alloc(&perm, (size_t)nz));
+        T_CUDA(sc.alloc(&perm_sorted, (size_t)nz));
+        iota_kernel<<<grid_for(nz, sm), 256, 0, st>>>(perm, nz); CB_LAUNCHED(ctx);
+        T_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, keys_sorted, perm, perm_sorted, (int)nz, 0, end_bit, st));
+        T_CUDA(sc.alloc((char**)&tmp, tmp_bytes));
+        T_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, keys_sorted, perm, perm_sorted, (int)nz, 0, end_bit, st));
+    } else {
+        T_CUDA(sc.alloc(&keys_sorted, (size_t)nz));
+        T_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, keys_sorted, (int)nz, 0, end_bit, st));
+        T_CUDA(sc.alloc((char**)&tmp, tmp_bytes));
+        T_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, d_keys, keys_sorted, (int)nz, 0, end_bit, st));
+    }
+    ctx->launches += 4;
+    // 2. per-nonzero arrays
+    uint8_t *rowstart, *colseen;
+    T_CUDA(cudaMalloc((void**)&t->colflag, sizeof(int32_t) * (size_t)nz));
+    T_CUDA(sc.alloc(&rowstart, (size_t)nz));
+    T_CUDA(sc.alloc(&colseen, (size_t)(n > 0 ? n : 1)));
+    T_CUDA(cudaMemsetAsync(colseen, 0, (size_t)(n > 0 ? n : 1), st));
+    finish_entries_kernel<<<grid_for(nz, sm), 256, 0, st>>>(keys_sorted, nz, t->colflag, rowstart, colseen); CB_LAUNCHED(ctx);
+    if (d_vals && presorted) {
+        T_CUDA(cudaMalloc(&t->vals, vs * (size_t)nz));
+        T_CUDA(cudaMemcpyAsync(t->vals, d_vals, vs * (size_t)nz, cudaMemcpyDeviceToDevice, st));
+    } else if (d_vals) {
+        T_CUDA(cudaMalloc(&t->vals, vs * (size_t)nz));
+        switch (vs) {
+            case 1: gather_vals_kernel<uint8_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint8_t*)d_vals, perm_sorted, nz, (uint8_t*)t->vals); break;
+            case 4: gather_vals_kernel<uint32_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint32_t*)d_vals, perm_sorted, nz, (uint32_t*)t->vals); break;
+            default: gather_vals_kernel<uint64_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint64_t*)d_vals, perm_sorted, nz, (uint64_t*)t->vals); break;
+        }
+        CB_LAUNCHED(ctx);
+    }
+    // 3. nonempty rows: positions of row starts
+    int64_t* d_counts;                 // [0] = nzr, [1] = nzc
+    T_CUDA(sc.alloc(&d_counts, 2));
+    int32_t* starts_tmp;
+    T_CUDA(sc.alloc(&starts_tmp, (size_t)nz));
+    {
+        size_t b = 0;
+        thrust::counting_iterator<int32_t> iota(0);
+        T_CUDA(cub::DeviceSelect::Flagged(nullptr, b, iota, rowstart, starts_tmp, d_counts, (int)nz, st));
+        void* tmp2; T_CUDA(sc.alloc((char**)&tmp2, b));
+        T_CUDA(cub::DeviceSelect::Flagged(tmp2, b, iota, rowstart, starts_tmp, d_counts, (int)nz, st));
+        size_t b2 = 0;
+        auto seen64 = thrust::make_transform_iterator((const uint8_t*)colseen, ToI64());
+        T_CUDA(cub::DeviceReduce::Sum(nullptr, b2, seen64, d_counts + 1, (int)n, st));
+        void* tmp3; T_CUDA(sc.alloc((char**)&tmp3, b2));
+        T_CUDA(cub::DeviceReduce::Sum(tmp3, b2, seen64, d_counts + 1, (int)n, st));
+        ctx->launches += 3;
+    }
+    int64_t h_counts[2];
+    T_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
+    T_CUDA(cudaStreamSynchronize(st));
+    t->nzr = h_counts[0];
+    t->nzc = h_counts[1];
+    T_CUDA(cudaMalloc((void**)&t->rowptr, sizeof(int32_t) * (size_t)(t->nzr + 1)));
+    T_CUDA(cudaMalloc((void**)&t->nzrows, sizeof(int32_t) * (size_t)t->nzr));
+    T_CUDA(cudaMemcpyAsync(t->rowptr, starts_tmp, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToDevice, st));
+    row_ids_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(keys_sorted, t->rowptr, t->nzr, nz, t->nzrows, t->rowptr + t->nzr); CB_LAUNCHED(ctx);
+    if (m > t->nzr) { empty_rows_kernel<<<grid_for(m, sm), 256, 0, st>>>(t->nzrows, t->nzr, m, t->emptyrows); CB_LAUNCHED(ctx); }
+    // 4. work partition
+    t->chunk_len = pick_chunk_len(nz);
+    t->nchunks = (nz + t->chunk_len - 1) / t->chunk_len;
+    T_CUDA(cudaMalloc((void**)&t->chunk_start, sizeof(int32_t) * (size_t)(t->nchunks + 1)));
+    T_CUDA(cudaMalloc((void**)&t->chunk_row, sizeof(int32_t) * (size_t)t->nchunks));
+    chunk_kernel<<<grid_for(t->nchunks + 1, sm), 256, 0, st>>>(t->rowptr, t->nzr, nz, t->chunk_len, t->nchunks, t->chunk_start, t->chunk_row); CB_LAUNCHED(ctx);
+    unsigned long long* d_nsplit;
+    T_CUDA(sc.alloc(&d_nsplit, 1));
+    T_CUDA(cudaMemsetAsync(d_nsplit, 0, sizeof(unsigned long long), st));
+    split_rows_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(t->rowptr, t->nzr, t->chunk_len, nullptr, d_nsplit); CB_LAUNCHED(ctx);
+    unsigned long long h_nsplit = 0;
+    T_CUDA(cudaMemcpyAsync(&h_nsplit, d_nsplit, sizeof h_nsplit, cudaMemcpyDeviceToHost, st));
+    T_CUDA(cudaStreamSynchronize(st));
+    t->nsplit = (int64_t)h_nsplit;
+    if (t->nsplit) {
+        T_CUDA(cudaMalloc((void**)&t->split_row, sizeof(int32_t) * (size_t)t->nsplit));
+        T_CUDA(cudaMemsetAsync(d_nsplit, 0, sizeof(unsigned long long), st));
+        split_rows_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(t->rowptr, t->nzr, t->chunk_len, t->split_row, d_nsplit); CB_LAUNCHED(ctx);
+    }
+    T_CUDA(cudaStreamSynchronize(st));
+    t->bytes = (size_t)nz * (4 + vs) + (size_t)(2 * t->nzr + 1) * 4 + (size_t)(m - t->nzr) * 4 + (size_t)(2 * t->nchunks + 1) * 4 + (size_t)t->nsplit * 4;
+    *out = t;
+    return CB_OK;
+#undef T_CUDA
+}
+
+namespace {
+
+template <typename T> __global__ void widen_kernel(const T* in, int64_t n, int64_t* out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
+}
+
+__global__ void keys_to_csr_kernel(const int32_t* __restrict__ colflag, int64_t nz, int64_t* __restrict__ colidx) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nz; i += (int64_t)gridDim.x * blockDim.x) colidx[i] = colflag[i] & 0x7fffffff;
+}
+
+int check_sizes(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int idx_dtype, int val_dtype, const void* vals) {
+    if (!ctx) return cb_fail(nullptr, CB_ERR_INVALIDPARAMS, "null ctx");
+    if (m < 0 || n < 0 || nz < 0) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "negative tile dimension");
+    if (idx_dtype != CB_I32 && idx_dtype != CB_I64) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "index dtype must be CB_I32 or CB_I64");
+    if (val_dtype != CB_PATTERN && !cb_dtype_size(val_dtype)) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "value dtype %d", val_dtype);
+    if ((val_dtype == CB_PATTERN) != (vals == nullptr)) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "CB_PATTERN tiles carry no value array and every other dtype needs one");
+    if (m >= (int64_t(1) << 31) || n >= (int64_t(1) << 31) || nz >= (int64_t(1) << 31))
+        return cb_fail(ctx, CB_ERR_TOO_LARGE, "tile %lld x %lld with %lld nonzeros: local arrays are limited to 2^31-1 elements", (long long)m, (long long)n, (long long)nz);
+    return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_tile_upload_csc(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int64_t nzc, const void* cp, const void* jc,
+                       const void* ir, const void* numx, int idx_dtype, int val_dtype, cb_tile** out) {
+    *out = nullptr;
+    CB_TRY(check_sizes(ctx, m, n, nz, idx_dtype, val_dtype, numx));
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_scratch sc;
+    const size_t is = cb_dtype_size(idx_dtype), vs = cb_dtype_size(val_dtype);
+    const int64_t ncp = jc ? nzc : n;
+    cudaStream_t st = ctx->compute;
+    void *d_cp = nullptr, *d_jc = nullptr, *d_ir = nullptr, *d_vals = nullptr;
+    uint64_t* d_keys = nullptr;
+    CB_CUDA(ctx, sc.alloc((char**)&d_cp, is * (size_t)(ncp + 1)));
+    CB_CUDA(ctx, sc.alloc((char**)&d_ir, is * (size_t)nz));
+    CB_CUDA(ctx, sc.alloc(&d_keys, (size_t)nz));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_cp, cp, is * (size_t)(ncp + 1), cudaMemcpyHostToDevice, st));
+    if (nz) CB_CUDA(ctx, cudaMemcpyAsync(d_ir, ir, is * (size_t)nz, cudaMemcpyHostToDevice, st));
+    if (jc) {
+        CB_CUDA(ctx, sc.alloc((char**)&d_jc, is * (size_t)nzc));
+        if (nzc) CB_CUDA(ctx, cudaMemcpyAsync(d_jc, jc, is * (size_t)nzc, cudaMemcpyHostToDevice, st));
+    }
+    if (numx && nz) {
+        CB_CUDA(ctx, sc.alloc((char**)&d_vals, vs * (size_t)nz));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_vals, numx, vs * (size_t)nz, cudaMemcpyHostToDevice, st));
+    }
+    if (nz) {
+        if (idx_dtype == CB_I32) expand_csc_kernel<int32_t><<<grid_for(nz, ctx->sm_count), 256, 0, st>>>((const int32_t*)d_cp, (const int32_t*)d_jc, (const int32_t*)d_ir, ncp, nz, d_keys);
+        else expand_csc_kernel<int64_t><<<grid_for(nz, ctx->sm_count), 256, 0, st>>>((const int64_t*)d_cp, (const int64_t*)d_jc, (const int64_t*)d_ir, ncp, nz, d_keys);
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+    }
+    return cb_tile_build_from_keys(ctx, m, n, nz, d_keys, nz ? d_vals : nullptr, val_dtype, false, sc, out);
+}
+
+int cb_tile_upload_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const void* rows, const void* cols, const void* vals,
+                       int idx_dtype, int val_dtype, cb_tile** out) {
+    *out = nullptr;
+    CB_TRY(check_sizes(ctx, m, n, nz, idx_dtype, val_dtype, vals));
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_scratch sc;
+    const size_t is = cb_dtype_size(idx_dtype), vs = cb_dtype_size(val_dtype);
+    cudaStream_t st = ctx->compute;
+    void *d_r = nullptr, *d_c = nullptr, *d_vals = nullptr;
+    uint64_t* d_keys = nullptr;
+    CB_CUDA(ctx, sc.alloc((char**)&d_r, is * (size_t)nz));
+    CB_CUDA(ctx, sc.alloc((char**)&d_c, is * (size_t)nz));
+    CB_CUDA(ctx, sc.alloc(&d_keys, (size_t)nz));
+    if (nz) {
+        CB_CUDA(ctx, cudaMemcpyAsync(d_r, rows, is * (size_t)nz, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_c, cols, is * (size_t)nz, cudaMemcpyHostToDevice, st));
+        if (vals) {
+            CB_CUDA(ctx, sc.alloc((char**)&d_vals, vs * (size_t)nz));
+            CB_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, vs * (size_t)nz, cudaMemcpyHostToDevice, st));
+        }
+        if (idx_dtype == CB_I32) coo_keys_kernel<int32_t><<<grid_for(nz, ctx->sm_count), 256, 0, st>>>((const int32_t*)d_r, (const int32_t*)d_c, nz, d_keys);
+        else coo_keys_kernel<int64_t><<<grid_for(nz, ctx->sm_count), 256, 0, st>>>((const int64_t*)d_r, (const int64_t*)d_c, nz, d_keys);
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+    }
+    return cb_tile_build_from_keys(ctx, m, n, nz, d_keys, d_vals, val_dtype, false, sc, out);
+}
+
+int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const int64_t* d_rows, const int64_t* d_cols,
+                            const void* d_vals, int val_dtype, cb_tile** out) {
+    *out = nullptr;
+    CB_TRY(check_sizes(ctx, m, n, nz, CB_I64, val_dtype, d_vals));
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_scratch sc;
+    uint64_t* d_keys = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_keys, (size_t)nz));
+    if (nz) {
+        coo_keys_kernel<int64_t><<<grid_for(nz, ctx->sm_count), 256, 0, ctx->compute>>>(d_rows, d_cols, nz, d_keys);
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+    }
+    return cb_tile_build_from_keys(ctx, m, n, nz, d_keys, d_vals, val_dtype, false, sc, out);
+}
+
+int cb_tile_free(cb_tile* t) {
+    if (!t) return CB_OK;
+    if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->compute); cudaStreamSynchronize(t->ctx->comm); }
+    cudaFree(t->colflag); cudaFree(t->vals); cudaFree(t->nzrows); cudaFree(t->rowptr); cudaFree(t->emptyrows);
+    cudaFree(t->chunk_start); cudaFree(t->chunk_row); cudaFree(t->split_row); cudaFree(t->split_first); cudaFree(t->split_last);
+    cudaFree(t->carry);
+    delete t;
+    return CB_OK;
+}
+
+int cb_tile_info(const cb_tile* t, int64_t info[8]) {
+    info[0] = t->nnz; info[1] = t->m; info[2] = t->n; info[3] = t->nzr; info[4] = t->nzc;
+    info[5] = t->nchunks; info[6] = t->nsplit; info[7] = (int64_t)t->bytes;
+    return CB_OK;
+}
+
+int cb_tile_download_csr(cb_tile* t, int64_t* rowptr, int64_t* colidx, void* vals) {
+    cb_ctx* ctx = t->ctx;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    if (rowptr) {
+        std::vector<int32_t> rp((size_t)t->nzr + 1, 0), rows((size_t)t->nzr);
+        if (t->nzr) {
+            CB_CUDA(ctx, cudaMemcpyAsync(rp.data(), t->rowptr, sizeof(int32_t) * (size_t)(t->nzr + 1), cudaMemcpyDeviceToHost, st));
+            CB_CUDA(ctx, cudaMemcpyAsync(rows.data(), t->nzrows, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        for (int64_t r = 0; r <= t->m; ++r) rowptr[r] = 0;
+        for (int64_t i = 0; i < t->nzr; ++i) rowptr[rows[(size_t)i] + 1] = rp[(size_t)i + 1] - rp[(size_t)i];
+        for (int64_t r = 0; r < t->m; ++r) rowptr[r + 1] += rowptr[r];
+    }
+    if (colidx && t->nnz) {
+        cb_scratch sc;
+        int64_t* d;
+        CB_CUDA(ctx, sc.alloc(&d, (size_t)t->nnz));
+        keys_to_csr_kernel<<<grid_for(t->nnz, ctx->sm_count), 256, 0, st>>>(t->colflag, t->nnz, d);
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaMemcpyAsync(colidx, d, sizeof(int64_t) * (size_t)t->nnz, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (vals && t->vals && t->nnz) {
+        CB_CUDA(ctx, cudaMemcpyAsync(vals, t->vals, cb_dtype_size(t->val_dtype) * (size_t)t->nnz, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+/* combblas_b200.h - C ABI of the B200-native SpMM path (libcombblas_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of Combinatorial BLAS: the 2D-distributed
+ * sparse x tall-skinny-dense multiply  Y = A (x).(+) X  under a semiring.  The templated
+ * C++ host layer (combblas-spmm-test_b200/include/CombBLAS/) keeps the reference's
+ * SpParMat / CommGrid / semiring surface and lowers onto these calls; nothing but plain
+ * pointers, sizes and enums crosses this line.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 (CB_OK) or a cb_status code; cb_last_error() gives the text.
+ *     Codes 3001..3007 are the reference's MPI_Abort codes (include/CombBLAS/SpDefs.h:72-78).
+ *   - a ctx owns one CUDA device, one compute stream and one communication stream; it is used
+ *     by one host thread at a time (the reference funnels all MPI calls through the master
+ *     thread, ReleaseTests/GenWriteMatrix.cpp:65-77).
+ *   - host arrays are borrowed for the duration of the call only; every *_upload/_alloc handle
+ *     is released by the matching *_free (the reference's raw new/delete ownership,
+ *     include/CombBLAS/SpParMat.cpp:110-113).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     CB_ERR_NO_DEVICE.
+ */
+#ifndef COMBBLAS_B200_H
+#define COMBBLAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+typedef struct cb_ctx cb_ctx;     /* device + streams + (optional) pr x pc process grid */
+typedef struct cb_tile cb_tile;   /* device-resident local sparse tile (doubly compressed rows) */
+typedef struct cb_dense cb_dense; /* device-resident dense panel, row-major */
+
+/* element types.  CB_U8 carries C++ bool (one byte, 0/1).  CB_PATTERN as a tile value type means
+ * "no value array, every stored entry is true/1" (what SpDCCols<IT,bool> holds after a pattern read). */
+typedef enum { CB_F32 = 0, CB_F64 = 1, CB_I32 = 2, CB_I64 = 3, CB_U8 = 4, CB_PATTERN = 255 } cb_dtype;
+
+/* semirings of include/CombBLAS/Semirings.h that cross the ABI as opcodes:
+ *   CB_PLUS_TIMES  PlusTimesSRing<T1,T2>  :212-232   id 0, add +, multiply (T)a*(T)b
+ *   CB_MIN_PLUS    MinPlusSRing<T,T>      :235-255   id numeric max, add min, multiply inf_plus (:40-47)
+ *   CB_MAX_SEL2ND  SelectMaxSRing<bool,T> :191-210   id -1, add max, multiply(a,x)=x
+ *   CB_OR_AND      PlusTimesSRing<bool,bool> (promote.h:78): add OR, multiply AND, id false */
+typedef enum { CB_PLUS_TIMES = 0, CB_MIN_PLUS = 1, CB_MAX_SEL2ND = 2, CB_OR_AND = 3 } cb_semiring;
+
+typedef enum {
+    CB_OK = 0,
+    CB_ERR_NO_DEVICE = 1,     /* no CUDA device / driver: the product has no CPU path */
+    CB_ERR_CUDA = 2,
+    CB_ERR_NCCL = 3,
+    CB_ERR_UNSUPPORTED = 4,   /* semiring/dtype combination outside the ABI (compile-time error in the C++ layer) */
+    CB_ERR_ALLOC = 5,
+    CB_ERR_TOO_LARGE = 6,     /* a tile array has >= 2^31 elements (the reference's MPI int counts, SpParHelper.cpp:595) */
+    CB_ERR_GRIDMISMATCH = 3001,
+    CB_ERR_DIMMISMATCH = 3002,
+    CB_ERR_NOTSQUARE = 3003,
+    CB_ERR_NOFILE = 3004,
+    CB_ERR_MATRIXALIAS = 3005,
+    CB_ERR_INVALIDPARAMS = 3007
+} cb_status;
+
+/* ------------------------------------------------------------------ context / process grid
+ * Replaces CommGrid(MPI_Comm, nrowproc, ncolproc), include/CombBLAS/CommGrid.h:47 and
+ * src/CommGrid.cpp:37-75: rank -> (myprocrow = rank / pc, myproccol = rank % pc), a row
+ * communicator (same myprocrow) and a column communicator (same myproccol).  One process per GPU;
+ * the 128-byte NCCL unique id is produced by rank 0 with cb_comm_unique_id() and handed to the
+ * other ranks by whatever launcher the host has (torch.distributed store, files, MPI). */
+int cb_abi_version(void);
+int cb_device_count(int* count);
+int cb_comm_unique_id(void* id128);
+int cb_ctx_create(int device, cb_ctx** ctx);                                   /* 1 x 1 grid */
+int cb_ctx_create_grid(int device, int rank, int nranks, int pr, int pc, const void* id128, cb_ctx** ctx);
+int cb_ctx_destroy(cb_ctx* ctx);
+int cb_ctx_grid(const cb_ctx* ctx, int* rank, int* pr, int* pc, int* myprocrow, int* myproccol);
+int cb_ctx_sync(cb_ctx* ctx);                                                  /* wait for both streams */
+void* cb_ctx_stream(cb_ctx* ctx);                                              /* cudaStream_t of the compute stream */
+const char* cb_last_error(const cb_ctx* ctx);                                  /* ctx may be NULL: last error of this thread */
+const char* cb_status_string(int status);
+
+/* device timers on the compute stream (replaces the MPI_Wtime brackets of ReleaseTests/MultTiming.cpp:58-92) */
+int cb_timer_start(cb_ctx* ctx);
+int cb_timer_stop(cb_ctx* ctx, float* milliseconds);    /* synchronises on the stop event */
+
+/* ------------------------------------------------------------------ local sparse tile
+ * Replaces the tile wire format Arr<IT,NT> = {cp, jc, ir | numx} with essentials {nnz, m, n, nzc}
+ * (include/CombBLAS/SpDCCols.cpp:787-795,826-846; dcsc.h:124-131; CSC twin csc.h:71-75) and the
+ * column->row transposition the reference would do with SpDCCols(const SpTuples&, bool)
+ * (SpDCCols.cpp:108-184).  Input: column compressed, rows ascending inside a column.
+ *   jc == NULL : plain CSC, cp has n+1 entries and nzc is ignored
+ *   idx_dtype  : CB_I32 or CB_I64 (type of cp/jc/ir)
+ *   val_dtype  : type of numx, or CB_PATTERN with numx == NULL
+ * The tile is converted on the device into doubly compressed rows with a work partition. */
+int cb_tile_upload_csc(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int64_t nzc, const void* cp, const void* jc,
+                       const void* ir, const void* numx, int idx_dtype, int val_dtype, cb_tile** tile);
+/* same from unsorted local COO triples (what SpTuples holds, include/CombBLAS/SpTuples.h:64-);
+ * duplicates must already be merged. */
+int cb_tile_upload_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const void* rows, const void* cols,
+                       const void* vals, int idx_dtype, int val_dtype, cb_tile** tile);
+/* same from COO triples that already live on the device (int64 indices); used by the generators */
+int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const int64_t* d_rows, const int64_t* d_cols,
+                            const void* d_vals, int val_dtype, cb_tile** tile);
+int cb_tile_free(cb_tile* tile);
+/* {nnz, m, n, nonempty rows, nonempty columns, work chunks, split rows, bytes resident} */
+int cb_tile_info(const cb_tile* tile, int64_t info[8]);
+/* copy the device tile back as CSR (rowptr[m+1], colidx[nnz], vals) for inspection/tests; any pointer may be NULL */
+int cb_tile_download_csr(cb_tile* tile, int64_t* rowptr, int64_t* colidx, void* vals);
+
+/* ------------------------------------------------------------------ dense panel
+ * Replaces DenseParMat<IT,NT>'s local block (include/CombBLAS/DenseParMat.h:49-128; the reference
+ * allocates NT** with one new[] per row, SpHelper.h:241-247) by one contiguous row-major device
+ * allocation whose leading dimension is padded to 16 bytes. */
+int cb_dense_alloc(cb_ctx* ctx, int64_t rows, int64_t cols, int dtype, cb_dense** d);
+int cb_dense_wrap(cb_ctx* ctx, void* device_ptr, int64_t rows, int64_t cols, int64_t ld, int dtype, cb_dense** d);
+int cb_dense_free(cb_dense* d);
+int cb_dense_upload(cb_dense* d, const void* host, int64_t ld_host);     /* async on the compute stream if host is pinned */
+int cb_dense_download(cb_dense* d, void* host, int64_t ld_host);         /* returns after the copy completed */
+int cb_dense_fill(cb_dense* d, const void* scalar);                      /* std::fill_n(localy, ysize, SR::id()), ParFriends.h:1960-1963 */
+int cb_dense_info(const cb_dense* d, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype, void** device_ptr);
+int cb_semiring_id(int semiring, int dtype, void* scalar_out);           /* SR::id() as a value of dtype */
+
+/* ------------------------------------------------------------------ the multiply
+ * cb_spmm_local: Y (+)= tile (x).(+) X on this GPU, enqueued on the compute stream.
+ *   accumulate == 0 : Y = product; rows of the tile without nonzeros receive SR::id()
+ *   accumulate != 0 : Y = SR::add(Y, product) on rows with nonzeros (later SUMMA stages)
+ * Replaces LocalHybridSpGEMM<SR,NTO> restricted to a dense right-hand side
+ * (include/CombBLAS/mtSpGEMM.h:213-460), dcsc_gespmv generalised to k columns
+ * (include/CombBLAS/Friends.h:63-78) and, through `accumulate`, MultiwayMerge
+ * (include/CombBLAS/MultiwayMerge.h:411-526).  X.rows == tile.n, Y.rows == tile.m, X.cols == Y.cols,
+ * dtype(Y) == dtype(X) == promote_trait<NT_A, NT_X> (promote.h:37-91). */
+int cb_spmm_local(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring, int accumulate);
+
+/* cb_spmm_summa: the whole 2D SUMMA stage loop, collective over the ctx's grid.
+ * Replaces Mult_AnXBn_Synch / _Overlap (include/CombBLAS/ParFriends.h:1004-1108, :1110-1235) with
+ * its SpParHelper::BCastMatrix / GetSetSizes transport (SpParHelper.cpp:582-601, :797-809):
+ * per stage the owner's A sub-tile travels along the process row and the owner's X panel along the
+ * process column (NCCL on the communication stream, double buffered), overlapped with
+ * cb_spmm_local of the previous stage; the Y tile is stationary.
+ *   tile : this rank's A tile, rows of block-row myprocrow x columns of block-column myproccol
+ *   X    : this rank's X tile, rows of block-row myprocrow of n  x  columns of block myproccol of k
+ *   Y    : this rank's Y tile, rows of block-row myprocrow of m  x  columns of block myproccol of k
+ *   gm, gn, gk : global dimensions (Owner rule of SpParMat.cpp:5066-5096 gives every block range)
+ * Works on any pr x pc (the reference only on square grids, src/CommGrid.cpp:164-180). */
+int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring,
+                  int64_t gm, int64_t gn, int64_t gk);
+/* per-phase device times of the last cb_spmm_summa on this rank: {total, bcast A, bcast X, local kernels} in ms */
+int cb_summa_times(cb_ctx* ctx, float ms[4]);
+
+/* one-shot convenience with HOST operands: upload X, multiply with a resident tile, download Y.
+ * This is what SpMM<SR>(A, X) of the C++ layer calls when the panels live in host memory. */
+int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy,
+                 int64_t k, int dtype, int semiring);
+
+/* number of kernels this library has launched on the ctx since creation (bench.py's gpu_launches) */
+int64_t cb_launch_count(const cb_ctx* ctx);
+/* per-kernel device timing: while enabled every K3 (identity fill) / K2 (multiply) / fix-up launch on the
+ * compute stream is bracketed by CUDA events; read returns the summed milliseconds and launch counts per
+ * kind {fill, multiply, fix-up} since enable.  Plays the role of the reference's -DTIMING accumulators
+ * (include/CombBLAS/CombBLAS.h:76-102). */
+int cb_profile_enable(cb_ctx* ctx, int on);
+int cb_profile_read(cb_ctx* ctx, double ms[3], int64_t launches[3]);
+
+/* ------------------------------------------------------------------ synthetic operands on the device
+ * Replaces the host generators DistEdgeList::GenGraph500Data (include/CombBLAS/DistEdgeList.cpp:223-)
+ * + SpParMat(const DistEdgeList&, bool) (SpParMat.cpp:3138-3254) with the recipe of
+ * ReleaseTests/GenWriteMatrix.cpp:96-131: Kronecker edges with the given initiator, vertex scramble,
+ * self loops removed, optional A += A^T, duplicates merged.  Counter based: edge e and entry (i,j)
+ * depend only on (seed, e) / (seed, i, j), never on the grid.  Only the block of the matrix that
+ * falls into rows [row0,row0+m) x cols [col0,col0+n) is kept (local indices).
+ * val_dtype: CB_PATTERN, or a dtype whose values come from the counter hash with val_seed. */
+int cb_gen_rmat_tile(cb_ctx* ctx, int scale, int edgefactor, uint64_t seed, const double initiator[4], int symmetric,
+                     int64_t row0, int64_t m, int64_t col0, int64_t n, int val_dtype, uint64_t val_seed, cb_tile** tile);
+/* X[i,j] = value(seed, (row0+i)*gk + col0+j); kind 0 = uniform (0,1) / [1,100] / Bernoulli, kind 1 = MinPlus operand
+ * with ~1% entries at numeric max */
+int cb_gen_dense(cb_dense* d, uint64_t seed, int64_t row0, int64_t col0, int64_t gk, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMBBLAS_B200_H */
