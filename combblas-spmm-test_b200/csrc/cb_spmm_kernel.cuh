@@ -64,6 +64,7 @@ struct PlusTimes {
     typedef T_ T;
     typedef typename std::conditional<AK == A_SAME, T_, uint8_t>::type TA;
     static constexpr int akind = AK;
+    static constexpr bool first_touch = false;
     static __device__ __forceinline__ T id() { return T(0); }
     static __device__ __forceinline__ T add(T a, T b) { return Arith<T>::add(a, b); }
     static __device__ __forceinline__ T mul(TA a, T x) {
@@ -78,6 +79,7 @@ struct MinPlus {
     typedef T_ T;
     typedef T_ TA;
     static constexpr int akind = A_SAME;
+    static constexpr bool first_touch = false;
     static __device__ __forceinline__ T id() { return Arith<T>::maxv(); }
     static __device__ __forceinline__ T add(T a, T b) { return b < a ? b : a; }     // std::min(a, b)
     static __device__ __forceinline__ T mul(TA a, T x) {
@@ -91,6 +93,7 @@ struct SelectMax {
     typedef T_ T;
     typedef uint8_t TA;
     static constexpr int akind = A_PATTERN;   // the stored boolean is never read
+    static constexpr bool first_touch = true;  // max(x, -1) != x for x < -1
     static __device__ __forceinline__ T id() { return T(-1); }
     static __device__ __forceinline__ T add(T a, T b) { return a < b ? b : a; }     // std::max(a, b)
     static __device__ __forceinline__ T mul(TA, T x) { return x; }
@@ -101,6 +104,7 @@ struct OrAnd {
     typedef uint32_t T;
     typedef uint8_t TA;
     static constexpr int akind = AK;
+    static constexpr bool first_touch = false;
     static __device__ __forceinline__ T id() { return 0u; }
     static __device__ __forceinline__ T add(T a, T b) { return a | b; }
     static __device__ __forceinline__ T mul(TA a, T x) { return AK == A_PATTERN ? x : (x & (0u - (uint32_t)(a != 0))); }
@@ -152,15 +156,26 @@ struct RowFrag {
     Vec16<typename Op::T> v[R];
 };
 
+// streaming (evict-first) access for data touched once: the nonzero stream of A and the rows of Y.  Keeps L2 for X.
+__device__ __forceinline__ int32_t ld_stream(const int32_t* p) { return __ldcs(p); }
+template <typename TA> __device__ __forceinline__ TA ld_stream_val(const TA* p) { return __ldcs(p); }
+template <> __device__ __forceinline__ uint8_t ld_stream_val<uint8_t>(const uint8_t* p) { return (uint8_t)__ldcs((const unsigned char*)p); }
+template <typename T>
+__device__ __forceinline__ void st16_stream(void* p, const Vec16<T>& v) {
+    __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&v));
+}
+
 template <class Op, int VW, int R, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cb_spmm_kernel(const SpmmArgs a) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     constexpr int EPL = 16 / sizeof(T);
     constexpr int NV = 32 / VW;                       // virtual warps per warp
+    constexpr bool HASVAL = Op::akind != A_PATTERN;
     const int lane = threadIdx.x & 31;
     const int vl = lane & (VW - 1);
+    const int vshift = lane & ~(VW - 1);              // first lane of this virtual warp
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t chunk = warp * NV + (lane / VW);
     const bool live = chunk < a.nchunks;
@@ -169,12 +184,11 @@ cb_spmm_kernel(const SpmmArgs a) {
     const int slab_off = blockIdx.y * a.slab_bytes;
     const int slab_row_bytes = min(a.row_bytes, a.total_row_bytes - slab_off);
     bool lane_on[R];
-    int off[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        off[r] = slab_off + (vl + r * VW) * 16;
-        lane_on[r] = (vl + r * VW) * 16 < slab_row_bytes;
-    }
+    for (int r = 0; r < R; ++r) lane_on[r] = (vl + r * VW) * 16 < slab_row_bytes;
+    const bool all_on = lane_on[R - 1];               // lanes are switched on in order
+    const char* const xbase = a.X + slab_off + vl * 16;
+    const uint32_t ldx = (uint32_t)a.ldx_bytes;
 
     int s = 0, e = 0, ridx = 0;
     bool head_open = false;
@@ -186,71 +200,104 @@ cb_spmm_kernel(const SpmmArgs a) {
         head_open = cr < 0;
     }
     // every lane of the warp runs the same number of steps so the shuffles stay convergent
-    const int len = e - s;
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const int maxlen = __reduce_max_sync(0xffffffffu, e - s);
 
     const TA* __restrict__ vals = reinterpret_cast<const TA*>(a.vals);
     RowFrag<Op, R> acc;
-    bool first = true;                 // no product folded into acc yet (hash table "key not registered", mtSpGEMM.h:410)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::id();
+    bool first = true;                 // nothing folded into acc since the last row end
     int row = live ? a.nzrows[ridx] : 0;
-    char* const carry_head = a.carry + (2 * chunk) * a.carry_stride;
+    char* const carry_head = a.carry + (2 * chunk) * a.carry_stride + slab_off;
+
+    // fold one product row into the accumulator
+    auto fold = [&](const TA av, const RowFrag<Op, R>& x) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) {
+                const T prod = Op::mul(av, x.v[r].v[q]);
+                // the reference stores the first product of an output entry and folds later ones with
+                // add(product, acc) (mtSpGEMM.h:403-414).  add(product, id) == product for every semiring here
+                // except SelectMax with values below its identity, which keeps the explicit first-touch select.
+                acc.v[r].v[q] = (Op::first_touch && first) ? prod : Op::add(prod, acc.v[r].v[q]);
+            }
+        first = false;
+    };
+    // last nonzero of a row seen: write the row out and start the next one
+    auto flush = [&](bool more) {
+        char* dst;
+        bool rmw = false;
+        if (head_open) { dst = carry_head; head_open = false; }            // piece of a split row
+        else { dst = a.Y + (int64_t)row * a.ldy_bytes + slab_off; rmw = a.accumulate != 0; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (lane_on[r]) {
+                char* d = dst + (vl + r * VW) * 16;
+                if (rmw) {
+                    const Vec16<T> y = ld16<T>(d);
+#pragma unroll
+                    for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::add(y.v[q], acc.v[r].v[q]);
+                }
+                st16_stream<T>(d, acc.v[r]);
+#pragma unroll
+                for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::id();
+            }
+        }
+        first = true;
+        ++ridx;
+        if (more) row = a.nzrows[ridx];
+    };
 
     for (int base = 0; base < maxlen; base += VW) {
-        const int p = s + base + vl;
+        const int rem = e - (s + base);                 // nonzeros this virtual warp still owns (may be <= 0)
         int cf = 0;
         TA av = TA();
-        if (p < e) {
-            cf = a.colflag[p];
-            if (Op::akind != A_PATTERN) av = vals[p];
+        if (vl < rem) {
+            cf = ld_stream(a.colflag + s + base + vl);
+            if (HASVAL) av = ld_stream_val<TA>(vals + s + base + vl);
         }
+        // end-of-row flags of this virtual warp's VW entries, one bit each
+        const uint32_t fm = (__ballot_sync(0xffffffffu, cf < 0) >> vshift) & (VW == 32 ? 0xffffffffu : ((1u << VW) - 1u));
+        const uint32_t cm = (uint32_t)cf & 0x7fffffffu;
+        const bool fullwarp = __all_sync(0xffffffffu, rem >= VW) && all_on;   // warp-uniform: no predicates needed
 #pragma unroll
         for (int j0 = 0; j0 < VW; j0 += U) {
             RowFrag<Op, R> x[U];
-            int cfu[U];
             TA avu[U];
-            bool valid[U];
+            if (fullwarp) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                cfu[u] = __shfl_sync(0xffffffffu, cf, j0 + u, VW);
-                if (Op::akind != A_PATTERN) avu[u] = (TA)__shfl_sync(0xffffffffu, av, j0 + u, VW);
-                valid[u] = (s + base + j0 + u) < e;
-                const char* xr = a.X + (int64_t)(cfu[u] & 0x7fffffff) * a.ldx_bytes;
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
+                    const char* xr = xbase + (uint64_t)c * ldx;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (valid[u] && lane_on[r]) x[u].v[r] = ldg16<T>(xr + off[r]);
+                    for (int r = 0; r < R; ++r) x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
+                    const char* xr = xbase + (uint64_t)c * ldx;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (j0 + u < rem && lane_on[r]) x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (valid[u]) {
+            for (int u = 0; u < U; ++u) avu[u] = HASVAL ? (TA)__shfl_sync(0xffffffffu, av, j0 + u, VW) : TA();
+            const uint32_t bits = (fm >> j0) & ((1u << U) - 1u);
+            if (fullwarp && bits == 0) {
+                // common case on long rows: U products, no row ends, no bounds
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
+                for (int u = 0; u < U; ++u) fold(avu[u], x[u]);
+            } else {
 #pragma unroll
-                        for (int q = 0; q < EPL; ++q) {
-                            const T prod = Op::mul(Op::akind != A_PATTERN ? avu[u] : TA(), x[u].v[r].v[q]);
-                            acc.v[r].v[q] = first ? prod : Op::add(prod, acc.v[r].v[q]);
-                        }
-                    }
-                    first = false;
-                    if (cfu[u] < 0) {          // last nonzero of its row: write the row out
-                        char* dst;
-                        bool rmw = false;
-                        if (head_open) { dst = carry_head + slab_off; head_open = false; }            // piece of a split row
-                        else { dst = a.Y + (int64_t)row * a.ldy_bytes + slab_off; rmw = a.accumulate != 0; }
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (lane_on[r]) {
-                                char* d = dst + (vl + r * VW) * 16;
-                                if (rmw) {
-                                    const Vec16<T> y = ld16<T>(d);
-#pragma unroll
-                                    for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::add(y.v[q], acc.v[r].v[q]);
-                                }
-                                st16<T>(d, acc.v[r]);
-                            }
-                        }
-                        first = true;
-                        ++ridx;
-                        if (s + base + j0 + u + 1 < e) row = a.nzrows[ridx];
+                for (int u = 0; u < U; ++u) {
+                    if (j0 + u < rem) {
+                        fold(avu[u], x[u]);
+                        if ((bits >> u) & 1u) flush(j0 + u + 1 < rem);
                     }
                 }
             }
@@ -258,7 +305,7 @@ cb_spmm_kernel(const SpmmArgs a) {
     }
     // a row still open at the end of the chunk continues in the next chunk: park the piece
     if (live && !first) {
-        char* dst = carry_head + (head_open ? 0 : a.carry_stride) + slab_off;
+        char* dst = carry_head + (head_open ? 0 : a.carry_stride);
 #pragma unroll
         for (int r = 0; r < R; ++r)
             if (lane_on[r]) st16<T>(dst + (vl + r * VW) * 16, acc.v[r]);
