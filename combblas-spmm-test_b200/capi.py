@@ -22,7 +22,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_timer_start", "cb_timer_stop", "cb_tile_upload_csc", "cb_tile_upload_coo", "cb_tile_from_device_coo",
            "cb_tile_free", "cb_tile_info", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
-           "cb_spmm_summa", "cb_summa_times", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
+           "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
 
 
 class CBError(RuntimeError):
@@ -89,6 +89,7 @@ def lib():
         L.cb_spmm_local.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
         L.cb_spmm_summa.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64]
         L.cb_summa_times.argtypes = [c_void_p, POINTER(c_float)]
+        L.cb_summa_plan.argtypes = [c_int, c_int, c_int64, POINTER(c_int64), POINTER(c_int), POINTER(c_int), POINTER(c_int)]
         L.cb_spmm_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int]
         L.cb_profile_enable.argtypes = [c_void_p, c_int]
         L.cb_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
@@ -111,6 +112,21 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(c_void_p)
     return c_void_p(int(a))
+
+
+def summa_plan(pr, pc, gn):
+    """-> (seg boundaries [ns+1], a_owner_col [ns], x_owner_row [ns]); host arithmetic only."""
+    seg = (c_int64 * (pr + pc + 1))()
+    ac, xr, ns = (c_int * (pr + pc))(), (c_int * (pr + pc))(), c_int()
+    _check(lib().cb_summa_plan(pr, pc, gn, seg, ac, xr, byref(ns)))
+    return list(seg[:ns.value + 1]), list(ac[:ns.value]), list(xr[:ns.value])
+
+
+def block_range(total, nb, b):
+    """Owner rule of the reference (SpParMat.cpp:5066-5096): floor division, last block takes the remainder."""
+    per = total // nb
+    start = b * per
+    return start, (total - start if b == nb - 1 else per)
 
 
 def unique_id() -> bytes:

@@ -35,6 +35,31 @@ struct cb_ctx {
     std::string err;
 };
 
+// Everything a receiver needs to lay out a tile that arrives as one message (the "essentials" of
+// SpDCCols::GetEssentials, SpDCCols.cpp:787-795, extended by the work partition).
+struct cb_tile_meta {
+    int64_t m, n, nnz, nzr, nzc, nchunks, nsplit;
+    int32_t chunk_len, val_dtype;
+};
+struct cb_tile_layout { size_t colflag, vals, nzrows, rowptr, emptyrows, chunk_start, chunk_row, split_row, total; };
+static inline cb_tile_layout cb_layout(const cb_tile_meta& t) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t vs = 0;
+    switch (t.val_dtype) { case CB_F32: case CB_I32: vs = 4; break; case CB_F64: case CB_I64: vs = 8; break; case CB_U8: vs = 1; break; default: vs = 0; }
+    cb_tile_layout L;
+    size_t o = 0;
+    L.colflag = o;     o = up(o + (size_t)t.nnz * 4);
+    L.vals = o;        o = up(o + (size_t)t.nnz * vs);
+    L.nzrows = o;      o = up(o + (size_t)t.nzr * 4);
+    L.rowptr = o;      o = up(o + (size_t)(t.nzr + 1) * 4);
+    L.emptyrows = o;   o = up(o + (size_t)(t.m - t.nzr) * 4);
+    L.chunk_start = o; o = up(o + (size_t)(t.nchunks + 1) * 4);
+    L.chunk_row = o;   o = up(o + (size_t)t.nchunks * 4);
+    L.split_row = o;   o = up(o + (size_t)t.nsplit * 4);
+    L.total = o ? o : 256;
+    return L;
+}
+
 // Device tile: doubly compressed rows (the row-major mirror of Dcsc, dcsc.h:124-131) plus a work partition.
 struct cb_tile {
     cb_ctx* ctx = nullptr;
@@ -42,6 +67,9 @@ struct cb_tile {
     int64_t nzr = 0;          // rows with at least one nonzero
     int64_t nzc = 0;          // columns with at least one nonzero (n_used of the traffic model)
     int val_dtype = CB_PATTERN;
+    char* slab = nullptr;     // the one allocation holding every array below (cb_tile_layout)
+    size_t slab_bytes = 0;
+    bool owns_slab = false;
     // per nonzero, row-major, ascending column inside a row
     int32_t* colflag = nullptr;   // column index | (last nonzero of its row ? 0x80000000 : 0)
     void* vals = nullptr;         // nnz values of val_dtype, or NULL for CB_PATTERN
@@ -58,13 +86,35 @@ struct cb_tile {
     // rows longer than L are cut at multiples of L; their pieces are combined by the fix-up kernel
     int64_t nsplit = 0;
     int32_t* split_row = nullptr;    // [nsplit] index into nzrows
-    int32_t* split_first = nullptr;  // [nsplit] first chunk holding a piece
-    int32_t* split_last = nullptr;   // [nsplit] last chunk holding a piece
     // scratch for partial rows, sized at first use for the widest panel seen: 2 slots (head, tail) per chunk
     void* carry = nullptr;
     size_t carry_bytes = 0;
-    size_t bytes = 0;
+    // column slices of this tile, one per SUMMA stage it roots (built at the first cb_spmm_summa, cb_summa.cu)
+    std::vector<cb_tile*> summa_parts;
+    int64_t summa_key[3] = {-1, -1, -1};   // (grid id, gn, stages) the parts were cut for
 };
+
+static inline cb_tile_meta cb_tile_get_meta(const cb_tile* t) {
+    cb_tile_meta m;
+    memset(&m, 0, sizeof m);
+    m.m = t->m; m.n = t->n; m.nnz = t->nnz; m.nzr = t->nzr; m.nzc = t->nzc; m.nchunks = t->nchunks; m.nsplit = t->nsplit;
+    m.chunk_len = t->chunk_len; m.val_dtype = t->val_dtype;
+    return m;
+}
+static inline void cb_tile_bind(cb_tile* t, const cb_tile_meta& m, char* slab) {
+    const cb_tile_layout L = cb_layout(m);
+    t->m = m.m; t->n = m.n; t->nnz = m.nnz; t->nzr = m.nzr; t->nzc = m.nzc; t->nchunks = m.nchunks; t->nsplit = m.nsplit;
+    t->chunk_len = m.chunk_len; t->val_dtype = m.val_dtype;
+    t->slab = slab;
+    t->colflag = (int32_t*)(slab + L.colflag);
+    t->vals = (m.val_dtype == CB_PATTERN || m.nnz == 0) ? nullptr : (void*)(slab + L.vals);
+    t->nzrows = (int32_t*)(slab + L.nzrows);
+    t->rowptr = (int32_t*)(slab + L.rowptr);
+    t->emptyrows = (int32_t*)(slab + L.emptyrows);
+    t->chunk_start = (int32_t*)(slab + L.chunk_start);
+    t->chunk_row = (int32_t*)(slab + L.chunk_row);
+    t->split_row = (int32_t*)(slab + L.split_row);
+}
 
 struct cb_dense {
     cb_ctx* ctx = nullptr;

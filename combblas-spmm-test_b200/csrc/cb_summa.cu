@@ -1,13 +1,425 @@
-// placeholder until the NCCL stage loop lands (next commit)
+// 2D SUMMA stage loop over a pr x pc process grid, one process per GPU, NCCL over NVLink.
+//
+// Replaces Mult_AnXBn_Synch / Mult_AnXBn_Overlap (reference include/CombBLAS/ParFriends.h:1004-1108, :1110-1235)
+// and their transport SpParHelper::BCastMatrix / GetSetSizes (SpParHelper.cpp:582-601, :797-809):
+//   * the reference ships a tile as 3-4 MPI_Bcast calls of host arrays per stage; here a tile is ONE device
+//     allocation (cb_tile_layout) and travels as one ncclBroadcast on the row communicator, the dense panel as one
+//     ncclBroadcast on the column communicator, both on the communication stream;
+//   * receive buffers are double buffered and the broadcasts of stage s+1 are enqueued before the local multiply
+//     of stage s has run, so transfer and kernel overlap (events hand buffers between the two streams);
+//   * the stage partials are never materialised: K2 accumulates into the stationary Y tile
+//     (the role of MultiwayMerge, MultiwayMerge.h:411-526);
+//   * the inner dimension is cut at the union of A's column-block and X's row-block boundaries, so any pr x pc
+//     works (the reference's ProductGrid demands a square grid, src/CommGrid.cpp:164-180).  On a square grid with
+//     divisible n this is exactly the reference's `stages = grcols` loop.
+// NCCL is loaded with dlopen at the first multi-rank context so single-GPU use has no NCCL dependency.
+#include <dlfcn.h>
+#include <algorithm>
+#include <cub/cub.cuh>
 #include "cb_common.cuh"
-int cb_nccl_init(cb_ctx* ctx, const void*) { return cb_fail(ctx, CB_ERR_NCCL, "multi-rank grids are not built yet"); }
-void cb_nccl_destroy(cb_ctx*) {}
-void cb_summa_release(cb_ctx*) {}
+
+// ------------------------------------------------------------------------------------------ NCCL, by hand
+namespace {
+
+typedef void* ncclComm_t;
+struct ncclUniqueId { char internal[128]; };
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    return api;
+}
+
+bool nccl_load() {
+    NcclApi& a = nccl();
+    if (a.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) { a.error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define SYM(field, name)                                                    \
+    *(void**)(&a.field) = dlsym(a.handle, name);                            \
+    if (!a.field) { a.error = std::string("missing symbol ") + name; a.handle = nullptr; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommSplit, "ncclCommSplit")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(AllGather, "ncclAllGather")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+}
+
+#define CB_NCCL(ctx, expr)                                                                                  \
+    do {                                                                                                    \
+        int r__ = (expr);                                                                                   \
+        if (r__ != ncclSuccess)                                                                             \
+            return cb_fail((ctx), CB_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, nccl().GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+// first index and length of block b of nb over `total` (reference Owner rule, SpParMat.cpp:5066-5096)
+inline void block_range(int64_t total, int nb, int b, int64_t* start, int64_t* len) {
+    const int64_t per = total / nb;
+    *start = (int64_t)b * per;
+    *len = (b == nb - 1) ? total - *start : per;
+}
+
+struct SummaState {
+    int64_t gn = -1, kl = -1;
+    int dtype = -1;
+    int nstages = 0;
+    std::vector<int64_t> seg;          // nstages+1 boundaries of the inner dimension
+    std::vector<int> a_root, x_root;   // rank inside the row / column communicator that owns the stage's operand
+    char* slotA[2] = {nullptr, nullptr};
+    size_t slotA_bytes = 0;
+    char* slotX[2] = {nullptr, nullptr};
+    size_t slotX_bytes = 0;
+    cb_tile* view[2] = {nullptr, nullptr};
+    cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, begin = nullptr, end = nullptr;
+    std::vector<cudaEvent_t> comm_ev;  // begin/end pairs per stage on the communication stream
+    // metas of every stage's A part as seen by this rank's row communicator, valid for `meta_tile`
+    const cb_tile* meta_tile = nullptr;
+    std::vector<cb_tile_meta> metas;
+};
+
+}  // namespace
+
+int cb_nccl_init(cb_ctx* ctx, const void* id128) {
+    if (!nccl_load()) return cb_fail(ctx, CB_ERR_NCCL, "NCCL unavailable: %s", nccl().error.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclComm_t world = nullptr, row = nullptr, col = nullptr;
+    CB_NCCL(ctx, nccl().CommInitRank(&world, ctx->nranks, id, ctx->rank));
+    // "RowWorld": same processor row, ordered by column; "ColWorld": same processor column (src/CommGrid.cpp:66-67)
+    CB_NCCL(ctx, nccl().CommSplit(world, ctx->myprocrow, ctx->myproccol, &row, nullptr));
+    CB_NCCL(ctx, nccl().CommSplit(world, ctx->myproccol, ctx->myprocrow, &col, nullptr));
+    ctx->nccl_world = world; ctx->nccl_row = row; ctx->nccl_col = col;
+    return CB_OK;
+}
+
+void cb_nccl_destroy(cb_ctx* ctx) {
+    if (!nccl().handle) return;
+    if (ctx->nccl_row) nccl().CommDestroy((ncclComm_t)ctx->nccl_row);
+    if (ctx->nccl_col) nccl().CommDestroy((ncclComm_t)ctx->nccl_col);
+    if (ctx->nccl_world) nccl().CommDestroy((ncclComm_t)ctx->nccl_world);
+    ctx->nccl_row = ctx->nccl_col = ctx->nccl_world = nullptr;
+}
+
+void cb_summa_release(cb_ctx* ctx) {
+    SummaState* s = (SummaState*)ctx->summa_state;
+    if (!s) return;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->slotA[i]); cudaFree(s->slotX[i]);
+        if (s->view[i]) { cudaFree(s->view[i]->carry); delete s->view[i]; }
+        if (s->ready[i]) cudaEventDestroy(s->ready[i]);
+        if (s->done[i]) cudaEventDestroy(s->done[i]);
+    }
+    if (s->begin) cudaEventDestroy(s->begin);
+    if (s->end) cudaEventDestroy(s->end);
+    for (cudaEvent_t e : s->comm_ev) cudaEventDestroy(e);
+    delete s;
+    ctx->summa_state = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------ column slices of a tile
+namespace {
+
+__global__ void slice_keys_kernel(const int32_t* __restrict__ colflag, const int32_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ nzrows, int64_t nzr, int64_t nz, int32_t c0, int32_t c1,
+                                  uint64_t* __restrict__ keys, uint8_t* __restrict__ keep) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t col = colflag[p] & 0x7fffffff;
+        const bool in = col >= c0 && col < c1;
+        keep[p] = in ? 1 : 0;
+        if (in) {
+            int64_t lo = 0, hi = nzr;           // largest ridx with rowptr[ridx] <= p
+            while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rowptr[mid] <= p) lo = mid; else hi = mid; }
+            keys[p] = ((uint64_t)(uint32_t)nzrows[lo] << 32) | (uint64_t)(uint32_t)(col - c0);
+        } else {
+            keys[p] = ~0ULL;
+        }
+    }
+}
+
+inline int grid_for(int64_t n, int sm) {
+    int64_t b = (n + 255) / 256, cap = (int64_t)sm * 32;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// columns [c0, c1) of `t` as a new tile with local column indices
+int slice_cols(cb_ctx* ctx, const cb_tile* t, int64_t c0, int64_t c1, cb_tile** out) {
+    cb_scratch sc;
+    cudaStream_t st = ctx->compute;
+    const int64_t nz = t->nnz;
+    uint64_t *keys = nullptr, *keys_sel = nullptr;
+    uint8_t* keep = nullptr;
+    int64_t* d_n = nullptr;
+    void* vals_sel = nullptr;
+    const size_t vs = cb_dtype_size(t->val_dtype);
+    int64_t nsel = 0;
+    CB_CUDA(ctx, sc.alloc(&keys, (size_t)nz));
+    CB_CUDA(ctx, sc.alloc(&keys_sel, (size_t)nz));
+    if (nz > 0) {
+        CB_CUDA(ctx, sc.alloc(&keep, (size_t)nz));
+        CB_CUDA(ctx, sc.alloc(&d_n, 1));
+        slice_keys_kernel<<<grid_for(nz, ctx->sm_count), 256, 0, st>>>(t->colflag, t->rowptr, t->nzrows, t->nzr, nz, (int32_t)c0, (int32_t)c1, keys, keep);
+        CB_LAUNCHED(ctx);
+        size_t b = 0;
+        CB_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, b, keys, keep, keys_sel, d_n, (int)nz, st));
+        void* tmp; CB_CUDA(ctx, sc.alloc((char**)&tmp, b));
+        CB_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, b, keys, keep, keys_sel, d_n, (int)nz, st));
+        if (t->vals) {
+            CB_CUDA(ctx, sc.alloc((char**)&vals_sel, vs * (size_t)nz));
+            size_t b2 = 0;
+            void* tmp2 = nullptr;
+            switch (vs) {
+                case 1:
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, b2, (const uint8_t*)t->vals, keep, (uint8_t*)vals_sel, d_n, (int)nz, st));
+                    CB_CUDA(ctx, sc.alloc((char**)&tmp2, b2));
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(tmp2, b2, (const uint8_t*)t->vals, keep, (uint8_t*)vals_sel, d_n, (int)nz, st));
+                    break;
+                case 4:
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, b2, (const uint32_t*)t->vals, keep, (uint32_t*)vals_sel, d_n, (int)nz, st));
+                    CB_CUDA(ctx, sc.alloc((char**)&tmp2, b2));
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(tmp2, b2, (const uint32_t*)t->vals, keep, (uint32_t*)vals_sel, d_n, (int)nz, st));
+                    break;
+                default:
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, b2, (const uint64_t*)t->vals, keep, (uint64_t*)vals_sel, d_n, (int)nz, st));
+                    CB_CUDA(ctx, sc.alloc((char**)&tmp2, b2));
+                    CB_CUDA(ctx, cub::DeviceSelect::Flagged(tmp2, b2, (const uint64_t*)t->vals, keep, (uint64_t*)vals_sel, d_n, (int)nz, st));
+            }
+        }
+        ctx->launches += 4;
+        CB_CUDA(ctx, cudaMemcpyAsync(&nsel, d_n, sizeof nsel, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return cb_tile_build_from_keys(ctx, t->m, c1 - c0, nsel, keys_sel, (t->vals && nsel) ? vals_sel : nullptr, t->val_dtype, true, sc, out);
+}
+
+}  // namespace
+
 extern "C" {
-int cb_comm_unique_id(void*) { return cb_fail(nullptr, CB_ERR_NCCL, "multi-rank grids are not built yet"); }
-int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int semiring, int64_t, int64_t, int64_t) {
-    if (ctx->nranks == 1) return cb_spmm_local(ctx, t, X, Y, semiring, 0);
-    return cb_fail(ctx, CB_ERR_NCCL, "multi-rank grids are not built yet");
+
+int cb_comm_unique_id(void* id128) {
+    if (!nccl_load()) return cb_fail(nullptr, CB_ERR_NCCL, "NCCL unavailable: %s", nccl().error.c_str());
+    ncclUniqueId id;
+    CB_NCCL(nullptr, nccl().GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return CB_OK;
 }
-int cb_summa_times(cb_ctx* ctx, float ms[4]) { for (int i = 0; i < 4; ++i) ms[i] = ctx->summa_ms[i]; return CB_OK; }
+
+// Stage plan, pure host arithmetic (exported so the host logic is testable without a GPU).
+// Cuts [0, gn) at every boundary of A's column blocks (pc of them) and of X's row blocks (pr of them).
+// seg has room for pr + pc entries; a_owner_col[s] / x_owner_row[s] say which block owns stage s.
+int cb_summa_plan(int pr, int pc, int64_t gn, int64_t* seg, int* a_owner_col, int* x_owner_row, int* nstages) {
+    if (pr < 1 || pc < 1 || gn < 0) return CB_ERR_INVALIDPARAMS;
+    std::vector<int64_t> cuts;
+    for (int b = 0; b < pc; ++b) { int64_t s, l; block_range(gn, pc, b, &s, &l); cuts.push_back(s); }
+    for (int b = 0; b < pr; ++b) { int64_t s, l; block_range(gn, pr, b, &s, &l); cuts.push_back(s); }
+    cuts.push_back(gn);
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    int ns = 0;
+    for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+        const int64_t a = cuts[i], b = cuts[i + 1];
+        if (b <= a) continue;
+        // owner of global inner index a under the floor rule: min(a / per, nb - 1), all to the last block if per == 0
+        const int64_t perc = gn / pc, perr = gn / pr;
+        const int oc = perc ? (int)std::min<int64_t>(a / perc, pc - 1) : pc - 1;
+        const int orow = perr ? (int)std::min<int64_t>(a / perr, pr - 1) : pr - 1;
+        seg[ns] = a;
+        a_owner_col[ns] = oc;
+        x_owner_row[ns] = orow;
+        ++ns;
+    }
+    seg[ns] = gn;
+    *nstages = ns;
+    return CB_OK;
 }
+
+int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring, int64_t gm, int64_t gn, int64_t gk) {
+    if (!ctx || !tile || !X || !Y) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_summa: null argument");
+    const int pr = ctx->pr, pc = ctx->pc;
+    int64_t r0, rl, c0, cl, x0, xl, k0, kl;
+    block_range(gm, pr, ctx->myprocrow, &r0, &rl);
+    block_range(gn, pc, ctx->myproccol, &c0, &cl);
+    block_range(gn, pr, ctx->myprocrow, &x0, &xl);
+    block_range(gk, pc, ctx->myproccol, &k0, &kl);
+    // CheckSpGEMMCompliance (ParFriends.h:160-181) on the local blocks
+    if (tile->m != rl || tile->n != cl || X->rows != xl || X->cols != kl || Y->rows != rl || Y->cols != kl)
+        return cb_fail(ctx, CB_ERR_DIMMISMATCH,
+                       "cb_spmm_summa rank %d (%d,%d) of %dx%d: local A %lldx%lld (want %lldx%lld), X %lldx%lld (want %lldx%lld), Y %lldx%lld (want %lldx%lld)",
+                       ctx->rank, ctx->myprocrow, ctx->myproccol, pr, pc, (long long)tile->m, (long long)tile->n, (long long)rl, (long long)cl,
+                       (long long)X->rows, (long long)X->cols, (long long)xl, (long long)kl, (long long)Y->rows, (long long)Y->cols, (long long)rl, (long long)kl);
+    if (X->dtype != Y->dtype) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm_summa: X and Y dtypes differ");
+    if (X->ptr == Y->ptr) return cb_fail(ctx, CB_ERR_MATRIXALIAS, "cb_spmm_summa: X and Y alias");
+    if (ctx->nranks == 1) return cb_spmm_local(ctx, tile, X, Y, semiring, 0);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t es = cb_dtype_size(X->dtype);
+
+    SummaState* S = (SummaState*)ctx->summa_state;
+    if (!S) {
+        S = new SummaState();
+        ctx->summa_state = S;
+        for (int i = 0; i < 2; ++i) {
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&S->ready[i], cudaEventDisableTiming));
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&S->done[i], cudaEventDisableTiming));
+            S->view[i] = new cb_tile();
+            S->view[i]->ctx = ctx;
+        }
+        CB_CUDA(ctx, cudaEventCreate(&S->begin));
+        CB_CUDA(ctx, cudaEventCreate(&S->end));
+    }
+    // ---- plan
+    if (S->gn != gn) {
+        S->seg.assign(pr + pc + 1, 0); S->a_root.assign(pr + pc, 0); S->x_root.assign(pr + pc, 0);
+        cb_summa_plan(pr, pc, gn, S->seg.data(), S->a_root.data(), S->x_root.data(), &S->nstages);
+        S->gn = gn;
+        S->meta_tile = nullptr;
+        while ((int)S->comm_ev.size() < 2 * S->nstages) { cudaEvent_t e; CB_CUDA(ctx, cudaEventCreate(&e)); S->comm_ev.push_back(e); }
+    }
+    const int ns = S->nstages;
+    // ---- my parts of A: one column slice per stage this rank roots (cached on the tile)
+    cb_tile* mt = const_cast<cb_tile*>(tile);
+    const int64_t key[3] = {(int64_t)pr * 1000 + pc, gn, ns};
+    if (mt->summa_key[0] != key[0] || mt->summa_key[1] != key[1] || mt->summa_key[2] != key[2]) {
+        for (cb_tile* p : mt->summa_parts) cb_tile_free(p);
+        mt->summa_parts.assign(ns, nullptr);
+        for (int s = 0; s < ns; ++s) {
+            if (S->a_root[s] != ctx->myproccol) continue;
+            const int64_t a = S->seg[s] - c0, b = S->seg[s + 1] - c0;
+            if (a == 0 && b == cl) continue;                       // the whole tile: no copy
+            CB_TRY(slice_cols(ctx, tile, a, b, &mt->summa_parts[s]));
+        }
+        mt->summa_key[0] = key[0]; mt->summa_key[1] = key[1]; mt->summa_key[2] = key[2];
+        S->meta_tile = nullptr;
+    }
+    auto my_part = [&](int s) -> const cb_tile* { return mt->summa_parts[s] ? mt->summa_parts[s] : tile; };
+    // ---- sizes of every stage's A part in my processor row (GetSetSizes, SpParHelper.cpp:797-809): one allgather
+    if (S->meta_tile != tile) {
+        S->metas.assign(ns, cb_tile_meta());
+        if (pc > 1) {
+            std::vector<cb_tile_meta> mine(ns);
+            memset(mine.data(), 0, sizeof(cb_tile_meta) * ns);
+            for (int s = 0; s < ns; ++s) if (S->a_root[s] == ctx->myproccol) mine[s] = cb_tile_get_meta(my_part(s));
+            cb_scratch sc;
+            char *d_send, *d_recv;
+            const size_t bytes = sizeof(cb_tile_meta) * (size_t)ns;
+            CB_CUDA(ctx, sc.alloc(&d_send, bytes));
+            CB_CUDA(ctx, sc.alloc(&d_recv, bytes * pc));
+            CB_CUDA(ctx, cudaMemcpyAsync(d_send, mine.data(), bytes, cudaMemcpyHostToDevice, ctx->comm));
+            CB_NCCL(ctx, nccl().AllGather(d_send, d_recv, bytes, ncclInt8, (ncclComm_t)ctx->nccl_row, ctx->comm));
+            std::vector<cb_tile_meta> all((size_t)ns * pc);
+            CB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_recv, bytes * pc, cudaMemcpyDeviceToHost, ctx->comm));
+            CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+            for (int s = 0; s < ns; ++s) S->metas[s] = all[(size_t)S->a_root[s] * ns + s];
+        } else {
+            for (int s = 0; s < ns; ++s) S->metas[s] = cb_tile_get_meta(my_part(s));
+        }
+        S->meta_tile = tile;
+    }
+    // ---- receive buffers
+    size_t needA = 0, needX = 0;
+    for (int s = 0; s < ns; ++s) {
+        if (S->a_root[s] != ctx->myproccol) needA = std::max(needA, cb_layout(S->metas[s]).total);
+        if (S->x_root[s] != ctx->myprocrow) needX = std::max(needX, (size_t)(S->seg[s + 1] - S->seg[s]) * (size_t)X->ld * es);
+    }
+    if (needA > S->slotA_bytes || needX > S->slotX_bytes) {
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+        for (int i = 0; i < 2; ++i) {
+            if (needA > S->slotA_bytes) {
+                cudaFree(S->slotA[i]); S->slotA[i] = nullptr;
+                if (cudaMalloc((void**)&S->slotA[i], needA) != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a SUMMA tile slot", needA);
+            }
+            if (needX > S->slotX_bytes) {
+                cudaFree(S->slotX[i]); S->slotX[i] = nullptr;
+                if (cudaMalloc((void**)&S->slotX[i], needX) != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a SUMMA panel slot", needX);
+            }
+        }
+        S->slotA_bytes = std::max(S->slotA_bytes, needA);
+        S->slotX_bytes = std::max(S->slotX_bytes, needX);
+    }
+
+    // ---- stage loop
+    CB_CUDA(ctx, cudaEventRecord(S->begin, ctx->compute));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->begin, 0));      // operands produced on the compute stream are ready
+    bool wrote = false;
+    for (int s = 0; s < ns; ++s) {
+        const int slot = s & 1;
+        const int64_t seg_a = S->seg[s], seg_len = S->seg[s + 1] - S->seg[s];
+        const bool a_mine = S->a_root[s] == ctx->myproccol, x_mine = S->x_root[s] == ctx->myprocrow;
+        const cb_tile_meta& meta = S->metas[s];
+        if (s >= 2) CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->done[slot], 0));     // slot free again
+        const cb_tile* part = a_mine ? my_part(s) : S->view[slot];
+        const char* xsrc = x_mine ? (const char*)X->ptr + (size_t)(seg_a - x0) * (size_t)X->ld * es : S->slotX[slot];
+        CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s], ctx->comm));
+        CB_NCCL(ctx, nccl().GroupStart());
+        if (pc > 1) {          // also for an empty part: the receiver needs its empty-row list for the identity fill
+            const size_t bytes = cb_layout(meta).total;
+            char* buf = a_mine ? my_part(s)->slab : S->slotA[slot];
+            CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->a_root[s], (ncclComm_t)ctx->nccl_row, ctx->comm));
+        }
+        if (pr > 1 && seg_len > 0 && kl > 0) {
+            const size_t bytes = (size_t)seg_len * (size_t)X->ld * es;
+            char* buf = const_cast<char*>(xsrc);
+            CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->x_root[s], (ncclComm_t)ctx->nccl_col, ctx->comm));
+        }
+        CB_NCCL(ctx, nccl().GroupEnd());
+        CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s + 1], ctx->comm));
+        CB_CUDA(ctx, cudaEventRecord(S->ready[slot], ctx->comm));
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, S->ready[slot], 0));
+        if (!a_mine) {
+            cb_tile* v = S->view[slot];
+            void* keep_carry = v->carry; size_t keep_bytes = v->carry_bytes;
+            cb_tile_bind(v, meta, S->slotA[slot]);
+            v->carry = keep_carry; v->carry_bytes = keep_bytes;
+        }
+        if (meta.nnz > 0 || !wrote) {
+            // a stage whose A part is empty still has to give Y its identity fill if nothing was written yet
+            CB_TRY(cb_spmm_launch(ctx, ctx->compute, part, xsrc, X->ld, Y->ptr, Y->ld, kl, X->dtype, semiring, wrote ? 1 : 0));
+            wrote = true;
+        }
+        CB_CUDA(ctx, cudaEventRecord(S->done[slot], ctx->compute));
+    }
+    CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
+    return CB_OK;
+}
+
+int cb_summa_times(cb_ctx* ctx, float ms[4]) {
+    for (int i = 0; i < 4; ++i) ms[i] = 0;
+    SummaState* S = (SummaState*)ctx->summa_state;
+    if (!S || !S->nstages) return CB_OK;
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+    CB_CUDA(ctx, cudaEventElapsedTime(&ms[0], S->begin, S->end));
+    for (int s = 0; s < S->nstages; ++s) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, S->comm_ev[2 * s], S->comm_ev[2 * s + 1]) == cudaSuccess) ms[1] += t;
+    }
+    cudaGetLastError();
+    ms[3] = (float)S->nstages;
+    return CB_OK;
+}
+
+}  // extern "C"

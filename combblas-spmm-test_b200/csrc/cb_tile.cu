@@ -38,17 +38,24 @@ __global__ void iota_kernel(uint32_t* p, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
 
-// per sorted nonzero: column index with the end-of-row flag, row-start flag, column presence
-__global__ void finish_entries_kernel(const uint64_t* __restrict__ keys, int64_t nz, int32_t* __restrict__ colflag,
-                                      uint8_t* __restrict__ rowstart, uint8_t* __restrict__ colseen) {
+// per sorted nonzero: row-start flag and column presence
+__global__ void mark_entries_kernel(const uint64_t* __restrict__ keys, int64_t nz, uint8_t* __restrict__ rowstart,
+                                    uint8_t* __restrict__ colseen) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t kcur = keys[p];
+        const uint32_t row = (uint32_t)(kcur >> 32), col = (uint32_t)kcur;
+        rowstart[p] = ((p == 0) || ((uint32_t)(keys[p - 1] >> 32) != row)) ? 1 : 0;
+        colseen[col] = 1;
+    }
+}
+
+// per sorted nonzero: column index with the end-of-row flag in the top bit
+__global__ void colflag_kernel(const uint64_t* __restrict__ keys, int64_t nz, int32_t* __restrict__ colflag) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t kcur = keys[p];
         const uint32_t row = (uint32_t)(kcur >> 32), col = (uint32_t)kcur;
         const bool last = (p == nz - 1) || ((uint32_t)(keys[p + 1] >> 32) != row);
-        const bool first = (p == 0) || ((uint32_t)(keys[p - 1] >> 32) != row);
         colflag[p] = (int32_t)(col | (last ? 0x80000000u : 0u));
-        rowstart[p] = first ? 1 : 0;
-        colseen[col] = 1;
     }
 }
 
@@ -93,13 +100,15 @@ __global__ void chunk_kernel(const int32_t* __restrict__ rowptr, int64_t nzr, in
     }
 }
 
-__global__ void split_rows_kernel(const int32_t* __restrict__ rowptr, int64_t nzr, int32_t L, int32_t* __restrict__ out,
+__global__ void split_rows_kernel(const int32_t* __restrict__ starts, int64_t nzr, int64_t nz, int32_t L, int32_t* __restrict__ out,
                                   unsigned long long* __restrict__ count) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nzr; i += (int64_t)gridDim.x * blockDim.x)
-        if (rowptr[i + 1] - rowptr[i] > L) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nzr; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t end = (i + 1 < nzr) ? starts[i + 1] : (int32_t)nz;
+        if (end - starts[i] > L) {
             const unsigned long long slot = atomicAdd(count, 1ULL);
             if (out) out[slot] = (int32_t)i;
         }
+    }
 }
 
 inline int grid_for(int64_t n, int sm) {
@@ -122,21 +131,27 @@ int pick_chunk_len(int64_t nnz) {
 
 // keys (row<<32|col) on the device -> tile.  `d_vals` (device, nz elements of val_dtype, in the order of d_keys) may be
 // NULL.  presorted: keys are already ascending and unique (the generators sort while deduplicating).
+// All arrays of the finished tile live in ONE device allocation (cb_tile_layout), so a tile travels as one message.
 int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint64_t* d_keys, const void* d_vals,
                             int val_dtype, bool presorted, cb_scratch& sc, cb_tile** out) {
     const int sm = ctx->sm_count;
     cudaStream_t st = ctx->compute;
     cb_tile* t = new cb_tile();
-    t->ctx = ctx; t->m = m; t->n = n; t->nnz = nz; t->val_dtype = val_dtype;
+    t->ctx = ctx;
     *out = nullptr;
+    cb_tile_meta meta;
+    memset(&meta, 0, sizeof meta);
+    meta.m = m; meta.n = n; meta.nnz = nz; meta.val_dtype = val_dtype; meta.chunk_len = 32;
     auto fail = [&](int s) { cb_tile_free(t); return s; };
 #define T_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cb_fail(ctx, e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return fail(e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA); } } while (0)
     const size_t vs = cb_dtype_size(val_dtype);
-    T_CUDA(cudaMalloc((void**)&t->emptyrows, sizeof(int32_t) * (size_t)(m > 0 ? m : 1)));
     if (nz == 0) {
+        const cb_tile_layout L = cb_layout(meta);
+        T_CUDA(cudaMalloc((void**)&t->slab, L.total));
+        t->slab_bytes = L.total; t->owns_slab = true;
+        cb_tile_bind(t, meta, t->slab);
         if (m > 0) { empty_rows_kernel<<<grid_for(m, sm), 256, 0, st>>>(nullptr, 0, m, t->emptyrows); CB_LAUNCHED(ctx); }
         T_CUDA(cudaStreamSynchronize(st));
-        t->bytes = sizeof(int32_t) * (size_t)m;
         *out = t;
         return CB_OK;
     }
@@ -155,33 +170,20 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
         T_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, keys_sorted, perm, perm_sorted, (int)nz, 0, end_bit, st));
         T_CUDA(sc.alloc((char**)&tmp, tmp_bytes));
         T_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, keys_sorted, perm, perm_sorted, (int)nz, 0, end_bit, st));
+        ctx->launches += 4;
     } else {
         T_CUDA(sc.alloc(&keys_sorted, (size_t)nz));
         T_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, keys_sorted, (int)nz, 0, end_bit, st));
         T_CUDA(sc.alloc((char**)&tmp, tmp_bytes));
         T_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, d_keys, keys_sorted, (int)nz, 0, end_bit, st));
+        ctx->launches += 4;
     }
-    ctx->launches += 4;
-    // 2. per-nonzero arrays
+    // 2. count nonempty rows / columns, find the row starts
     uint8_t *rowstart, *colseen;
-    T_CUDA(cudaMalloc((void**)&t->colflag, sizeof(int32_t) * (size_t)nz));
     T_CUDA(sc.alloc(&rowstart, (size_t)nz));
     T_CUDA(sc.alloc(&colseen, (size_t)(n > 0 ? n : 1)));
     T_CUDA(cudaMemsetAsync(colseen, 0, (size_t)(n > 0 ? n : 1), st));
-    finish_entries_kernel<<<grid_for(nz, sm), 256, 0, st>>>(keys_sorted, nz, t->colflag, rowstart, colseen); CB_LAUNCHED(ctx);
-    if (d_vals && presorted) {
-        T_CUDA(cudaMalloc(&t->vals, vs * (size_t)nz));
-        T_CUDA(cudaMemcpyAsync(t->vals, d_vals, vs * (size_t)nz, cudaMemcpyDeviceToDevice, st));
-    } else if (d_vals) {
-        T_CUDA(cudaMalloc(&t->vals, vs * (size_t)nz));
-        switch (vs) {
-            case 1: gather_vals_kernel<uint8_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint8_t*)d_vals, perm_sorted, nz, (uint8_t*)t->vals); break;
-            case 4: gather_vals_kernel<uint32_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint32_t*)d_vals, perm_sorted, nz, (uint32_t*)t->vals); break;
-            default: gather_vals_kernel<uint64_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint64_t*)d_vals, perm_sorted, nz, (uint64_t*)t->vals); break;
-        }
-        CB_LAUNCHED(ctx);
-    }
-    // 3. nonempty rows: positions of row starts
+    mark_entries_kernel<<<grid_for(nz, sm), 256, 0, st>>>(keys_sorted, nz, rowstart, colseen); CB_LAUNCHED(ctx);
     int64_t* d_counts;                 // [0] = nzr, [1] = nzc
     T_CUDA(sc.alloc(&d_counts, 2));
     int32_t* starts_tmp;
@@ -202,34 +204,44 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
     int64_t h_counts[2];
     T_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
     T_CUDA(cudaStreamSynchronize(st));
-    t->nzr = h_counts[0];
-    t->nzc = h_counts[1];
-    T_CUDA(cudaMalloc((void**)&t->rowptr, sizeof(int32_t) * (size_t)(t->nzr + 1)));
-    T_CUDA(cudaMalloc((void**)&t->nzrows, sizeof(int32_t) * (size_t)t->nzr));
-    T_CUDA(cudaMemcpyAsync(t->rowptr, starts_tmp, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToDevice, st));
-    row_ids_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(keys_sorted, t->rowptr, t->nzr, nz, t->nzrows, t->rowptr + t->nzr); CB_LAUNCHED(ctx);
-    if (m > t->nzr) { empty_rows_kernel<<<grid_for(m, sm), 256, 0, st>>>(t->nzrows, t->nzr, m, t->emptyrows); CB_LAUNCHED(ctx); }
-    // 4. work partition
-    t->chunk_len = pick_chunk_len(nz);
-    t->nchunks = (nz + t->chunk_len - 1) / t->chunk_len;
-    T_CUDA(cudaMalloc((void**)&t->chunk_start, sizeof(int32_t) * (size_t)(t->nchunks + 1)));
-    T_CUDA(cudaMalloc((void**)&t->chunk_row, sizeof(int32_t) * (size_t)t->nchunks));
-    chunk_kernel<<<grid_for(t->nchunks + 1, sm), 256, 0, st>>>(t->rowptr, t->nzr, nz, t->chunk_len, t->nchunks, t->chunk_start, t->chunk_row); CB_LAUNCHED(ctx);
+    meta.nzr = h_counts[0];
+    meta.nzc = h_counts[1];
+    // 3. size of the work partition
+    meta.chunk_len = pick_chunk_len(nz);
+    meta.nchunks = (nz + meta.chunk_len - 1) / meta.chunk_len;
     unsigned long long* d_nsplit;
     T_CUDA(sc.alloc(&d_nsplit, 1));
     T_CUDA(cudaMemsetAsync(d_nsplit, 0, sizeof(unsigned long long), st));
-    split_rows_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(t->rowptr, t->nzr, t->chunk_len, nullptr, d_nsplit); CB_LAUNCHED(ctx);
+    split_rows_kernel<<<grid_for(meta.nzr, sm), 256, 0, st>>>(starts_tmp, meta.nzr, nz, meta.chunk_len, nullptr, d_nsplit); CB_LAUNCHED(ctx);
     unsigned long long h_nsplit = 0;
     T_CUDA(cudaMemcpyAsync(&h_nsplit, d_nsplit, sizeof h_nsplit, cudaMemcpyDeviceToHost, st));
     T_CUDA(cudaStreamSynchronize(st));
-    t->nsplit = (int64_t)h_nsplit;
+    meta.nsplit = (int64_t)h_nsplit;
+    // 4. one allocation for the whole tile, then fill it
+    const cb_tile_layout L = cb_layout(meta);
+    T_CUDA(cudaMalloc((void**)&t->slab, L.total));
+    t->slab_bytes = L.total; t->owns_slab = true;
+    cb_tile_bind(t, meta, t->slab);
+    colflag_kernel<<<grid_for(nz, sm), 256, 0, st>>>(keys_sorted, nz, t->colflag); CB_LAUNCHED(ctx);
+    if (d_vals && presorted) {
+        T_CUDA(cudaMemcpyAsync(t->vals, d_vals, vs * (size_t)nz, cudaMemcpyDeviceToDevice, st));
+    } else if (d_vals) {
+        switch (vs) {
+            case 1: gather_vals_kernel<uint8_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint8_t*)d_vals, perm_sorted, nz, (uint8_t*)t->vals); break;
+            case 4: gather_vals_kernel<uint32_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint32_t*)d_vals, perm_sorted, nz, (uint32_t*)t->vals); break;
+            default: gather_vals_kernel<uint64_t><<<grid_for(nz, sm), 256, 0, st>>>((const uint64_t*)d_vals, perm_sorted, nz, (uint64_t*)t->vals); break;
+        }
+        CB_LAUNCHED(ctx);
+    }
+    T_CUDA(cudaMemcpyAsync(t->rowptr, starts_tmp, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToDevice, st));
+    row_ids_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(keys_sorted, t->rowptr, t->nzr, nz, t->nzrows, t->rowptr + t->nzr); CB_LAUNCHED(ctx);
+    if (m > t->nzr) { empty_rows_kernel<<<grid_for(m, sm), 256, 0, st>>>(t->nzrows, t->nzr, m, t->emptyrows); CB_LAUNCHED(ctx); }
+    chunk_kernel<<<grid_for(t->nchunks + 1, sm), 256, 0, st>>>(t->rowptr, t->nzr, nz, t->chunk_len, t->nchunks, t->chunk_start, t->chunk_row); CB_LAUNCHED(ctx);
     if (t->nsplit) {
-        T_CUDA(cudaMalloc((void**)&t->split_row, sizeof(int32_t) * (size_t)t->nsplit));
         T_CUDA(cudaMemsetAsync(d_nsplit, 0, sizeof(unsigned long long), st));
-        split_rows_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(t->rowptr, t->nzr, t->chunk_len, t->split_row, d_nsplit); CB_LAUNCHED(ctx);
+        split_rows_kernel<<<grid_for(t->nzr, sm), 256, 0, st>>>(starts_tmp, t->nzr, nz, t->chunk_len, t->split_row, d_nsplit); CB_LAUNCHED(ctx);
     }
     T_CUDA(cudaStreamSynchronize(st));
-    t->bytes = (size_t)nz * (4 + vs) + (size_t)(2 * t->nzr + 1) * 4 + (size_t)(m - t->nzr) * 4 + (size_t)(2 * t->nchunks + 1) * 4 + (size_t)t->nsplit * 4;
     *out = t;
     return CB_OK;
 #undef T_CUDA
@@ -340,16 +352,16 @@ int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const
 int cb_tile_free(cb_tile* t) {
     if (!t) return CB_OK;
     if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->compute); cudaStreamSynchronize(t->ctx->comm); }
-    cudaFree(t->colflag); cudaFree(t->vals); cudaFree(t->nzrows); cudaFree(t->rowptr); cudaFree(t->emptyrows);
-    cudaFree(t->chunk_start); cudaFree(t->chunk_row); cudaFree(t->split_row); cudaFree(t->split_first); cudaFree(t->split_last);
+    if (t->owns_slab) cudaFree(t->slab);
     cudaFree(t->carry);
+    for (cb_tile* sub : t->summa_parts) cb_tile_free(sub);
     delete t;
     return CB_OK;
 }
 
 int cb_tile_info(const cb_tile* t, int64_t info[8]) {
     info[0] = t->nnz; info[1] = t->m; info[2] = t->n; info[3] = t->nzr; info[4] = t->nzc;
-    info[5] = t->nchunks; info[6] = t->nsplit; info[7] = (int64_t)t->bytes;
+    info[5] = t->nchunks; info[6] = t->nsplit; info[7] = (int64_t)t->slab_bytes;
     return CB_OK;
 }
 

@@ -145,8 +145,15 @@ int cb_spmm_local(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
  * Works on any pr x pc (the reference only on square grids, src/CommGrid.cpp:164-180). */
 int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring,
                   int64_t gm, int64_t gn, int64_t gk);
-/* per-phase device times of the last cb_spmm_summa on this rank: {total, bcast A, bcast X, local kernels} in ms */
+/* device times of the last cb_spmm_summa on this rank: {whole stage loop on the compute stream (ms), time the
+ * communication stream spent in the stage broadcasts (ms, overlaps the kernels), reserved, number of stages} */
 int cb_summa_times(cb_ctx* ctx, float ms[4]);
+/* The stage plan cb_spmm_summa uses, as pure host arithmetic (no device needed): [0, gn) is cut at every boundary
+ * of A's pc column blocks and of X's pr row blocks (floor rule of SpParMat.cpp:5066-5096).  seg needs pr+pc+1
+ * entries, the owner arrays pr+pc.  Stage s covers inner indices [seg[s], seg[s+1]); its A part is broadcast along
+ * each processor row from grid column a_owner_col[s], its X panel along each processor column from grid row
+ * x_owner_row[s].  On a square grid with pr | gn this is the reference's `stages = grcols` loop (ParFriends.h:1036). */
+int cb_summa_plan(int pr, int pc, int64_t gn, int64_t* seg, int* a_owner_col, int* x_owner_row, int* nstages);
 
 /* one-shot convenience with HOST operands: upload X, multiply with a resident tile, download Y.
  * This is what SpMM<SR>(A, X) of the C++ layer calls when the panels live in host memory. */

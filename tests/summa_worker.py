@@ -1,0 +1,136 @@
+"""One rank of a SUMMA parity run, launched by torch.distributed.run (see tests/test_summa_*.py).
+
+  --mode cpu : host logic only.  The C library's stage plan (cb_summa_plan) and the reference's block distribution
+               drive a stage loop whose transport is gloo broadcasts on row / column process groups and whose local
+               multiply is the CPU ORACLE (this is a test of the distributed plumbing, not of the product kernel).
+  --mode gpu : the product.  Every rank builds its A tile / X tile on its GPU and calls cb_spmm_summa (NCCL).
+Rank 0 gathers the Y tiles and compares with the single-rank oracle: bit-exact for integer semirings,
+relative tolerance for floating point.  Exit code 0 = parity.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cbb200_loader  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+cb = cbb200_loader.load_package()
+
+CASES = {
+    "minplus_i32": (O.MIN_PLUS, np.int32, np.int32, "x_minplus"),
+    "pt_f64": (O.PLUS_TIMES, np.float64, np.float64, "value"),
+    "pt_f32": (O.PLUS_TIMES, np.float32, np.float32, "value"),
+    "pt_pat_i64": (O.PLUS_TIMES, None, np.int64, "value"),
+    "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"),
+    "or_and": (O.OR_AND, None, np.uint8, "value"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="cpu")
+    ap.add_argument("--pr", type=int, required=True)
+    ap.add_argument("--pc", type=int, required=True)
+    ap.add_argument("--scale", type=int, default=9)
+    ap.add_argument("--k", type=int, default=13)
+    ap.add_argument("--cases", default="minplus_i32,pt_f64")
+    ap.add_argument("--ragged", type=int, default=1, help="drop trailing rows/cols so nothing divides evenly")
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert a.pr * a.pc == world
+    if a.mode == "gpu":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    pr, pc = a.pr, a.pc
+    myrow, mycol = rank // pc, rank % pc                      # CommGrid.h:106-110
+    row_groups = [dist.new_group([r * pc + c for c in range(pc)]) for r in range(pr)]
+    col_groups = [dist.new_group([r * pc + c for r in range(pr)]) for c in range(pc)]
+
+    # global operands, identical on every rank (counter-based generators)
+    n, I, J = O.rmat_matrix(a.scale, 8, seed=3)
+    m = n
+    if a.ragged:
+        m, n = n - 5, n - 3
+        keep = (I < m) & (J < n)
+        I, J = I[keep], J[keep]
+    k = a.k
+    ctx = None
+    if a.mode == "gpu":
+        holder = [cb.capi.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(holder, src=0)
+        ctx = cb.Context(local, rank, world, pr, pc, holder[0])
+    failures = 0
+    for case in a.cases.split(","):
+        sr, adt, xdt, kind = CASES[case]
+        V = None if adt is None else O.matrix_values(I, J, n, 7, adt)
+        X = O.dense_operand(n, k, 9, xdt, kind)
+        r0, rl = cb.capi.block_range(m, pr, myrow)
+        c0, cl = cb.capi.block_range(n, pc, mycol)
+        x0, xl = cb.capi.block_range(n, pr, myrow)
+        k0, kl = cb.capi.block_range(k, pc, mycol)
+        sel = (I >= r0) & (I < r0 + rl) & (J >= c0) & (J < c0 + cl)
+        Il, Jl, Vl = I[sel] - r0, J[sel] - c0, (None if V is None else V[sel])
+        Xl = np.ascontiguousarray(X[x0:x0 + xl, k0:k0 + kl])
+        if a.mode == "gpu":
+            tile = ctx.tile_from_coo(rl, cl, Il, Jl, Vl)
+            Xd, Yd = ctx.dense_from(Xl) if kl else ctx.dense(xl, 0, xdt), ctx.dense(rl, kl, xdt)
+            for _ in range(2):                                  # twice: the second call reuses the cached plan/buffers
+                ctx.spmm_summa(tile, Xd, Yd, sr, m, n, k)
+            Yl = Yd.download() if kl else np.zeros((rl, 0), xdt)
+            for h in (tile, Xd, Yd):
+                h.free()
+        else:
+            seg, a_owner, x_owner = cb.capi.summa_plan(pr, pc, n)
+            Yl = None
+            for s in range(len(a_owner)):
+                lo, hi = seg[s], seg[s + 1]
+                # A part: columns [lo,hi) of the tile of grid column a_owner[s], broadcast along my processor row
+                if a_owner[s] == mycol:
+                    ps = (Jl >= lo - c0) & (Jl < hi - c0)
+                    obj = [(Il[ps], Jl[ps] - (lo - c0), None if Vl is None else Vl[ps])]
+                else:
+                    obj = [None]
+                dist.broadcast_object_list(obj, src=myrow * pc + a_owner[s], group=row_groups[myrow])
+                Ai, Aj, Av = obj[0]
+                # X panel: rows [lo,hi) of the tile of grid row x_owner[s], broadcast along my processor column
+                obj = [Xl[lo - x0:hi - x0] if x_owner[s] == myrow else None]
+                dist.broadcast_object_list(obj, src=x_owner[s] * pc + mycol, group=col_groups[mycol])
+                Xs = obj[0]
+                if kl == 0:
+                    continue
+                Yl = O.spmm(sr, rl, hi - lo, Ai, Aj, Av, Xs, accum_into=Yl)
+            if Yl is None:
+                Yl = np.zeros((rl, kl), xdt)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((r0, k0, Yl), gathered, dst=0)
+        if rank == 0:
+            Y = np.zeros((m, k), X.dtype if X.dtype != np.bool_ else np.uint8)
+            for (rr, kk, y) in gathered:
+                Y[rr:rr + y.shape[0], kk:kk + y.shape[1]] = y
+            ref = O.spmm(sr, m, n, I, J, V, X)
+            if np.issubdtype(ref.dtype, np.floating):
+                tol = 1e-5 if ref.dtype == np.float32 else 1e-12
+                ok = bool((np.abs(Y - ref) <= tol * np.maximum(np.abs(ref), 1e-300)).all())
+            else:
+                ok = bool(np.array_equal(Y, ref))
+            print(f"[summa {a.mode} {pr}x{pc}] {case}: {'ok' if ok else 'MISMATCH'}", flush=True)
+            failures += 0 if ok else 1
+    flag = torch.tensor([failures], device=f"cuda:{local}" if a.mode == "gpu" else "cpu")
+    dist.broadcast(flag, src=0)
+    if ctx is not None:
+        ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,35 @@
+"""The real multi-GPU SUMMA (cb_spmm_summa over NCCL) against the single-rank oracle.  Needs >= 2 GPUs on the box;
+run with `gpurun --gpus N`.  One process per GPU, launched with torch.distributed.run."""
+import pytest
+import torch
+
+from tests.test_summa_cpu import torchrun
+
+pytestmark = pytest.mark.gpu
+ALL = "minplus_i32,pt_f64,pt_f32,pt_pat_i64,selmax_i32,or_and"
+
+
+def need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("pr,pc", [(1, 2), (2, 1)])
+def test_summa_2gpu(pr, pc):
+    need(2)
+    r = torchrun(2, ["--mode", "gpu", "--pr", str(pr), "--pc", str(pc), "--cases", ALL, "--scale", "11", "--k", "24"])
+    assert r.returncode == 0 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("pr,pc", [(2, 2), (1, 4), (4, 1)])
+def test_summa_4gpu(pr, pc):
+    need(4)
+    r = torchrun(4, ["--mode", "gpu", "--pr", str(pr), "--pc", str(pc), "--cases", ALL, "--scale", "12", "--k", "33"])
+    assert r.returncode == 0 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("pr,pc", [(2, 4), (4, 2)])
+def test_summa_8gpu(pr, pc):
+    need(8)
+    r = torchrun(8, ["--mode", "gpu", "--pr", str(pr), "--pc", str(pc), "--cases", ALL, "--scale", "12", "--k", "64"])
+    assert r.returncode == 0 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
