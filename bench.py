@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--ref-cols", type=int, default=16, help="panel columns of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--grid", default=None, help="process grid as PRxPC (default: as square as possible, pr <= pc)")
+    ap.add_argument("--no-cache-a", action="store_true", help="re-broadcast the A parts every multiply like the reference does")
     args = ap.parse_args()
     if args.workload is None:
         # N=1: the configuration the metric is quoted on that fits one GPU (BASELINE configs[1]); N>1: the 2D SUMMA configs
@@ -191,8 +193,11 @@ def main():
         holder = [cb.capi.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(holder, src=0)
         uid = holder[0]
-    pr, pc = grid_shape(world)
+    pr, pc = grid_shape(world) if not args.grid else tuple(int(v) for v in args.grid.lower().split("x"))
+    assert pr * pc == world, f"grid {pr}x{pc} does not match {world} ranks"
     ctx = cb.Context(local, rank, world, pr, pc, uid)
+    if args.no_cache_a:
+        ctx.summa_cache_a(False)
 
     sr = {"plus_times": cb.PLUS_TIMES, "min_plus": cb.MIN_PLUS, "or_and": cb.OR_AND, "select_max": cb.MAX_SEL2ND}[w["sr"]]
     xdt = NPDT[w["xdt"]]
@@ -262,7 +267,8 @@ def main():
     # roofline of the dominant kernel (K2, cb_spmm_kernel) on this rank: algorithmic bytes of the local multiply
     peak, peak_src = measured_peak_gbs()
     k2_ms = prof_ms["spmm"] / max(prof_n["spmm"], 1)
-    stages = 1 if world == 1 else int(np.lcm(pr, pc))
+    stages = len(cb.capi.summa_plan(pr, pc, N)[1])
+    summa_ms = ctx.summa_times() if world > 1 else None
     b_alg_local = alg_bytes(tile.nnz, tile.m, tile.nzc, kl, s_val, s_t)      # per multiply on this rank (all stages together)
     k2_per_step = prof_n["spmm"] / args.steps if args.steps else 1
     achieved = b_alg_local / max(k2_per_step, 1) / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
@@ -329,7 +335,9 @@ def main():
             "config": {"workload": args.workload + ": " + w["desc"], "n": N, "nnz": int(nnz_total), "k": k, "semiring": w["sr"],
                        "grid": f"{pr}x{pc}", "stages": stages, "l2_policy": "inputs larger than L2 (A+X+Y per GPU >> 126 MB), no flush",
                        "generator": "counter-based Kronecker (csrc/cb_gen.cu), seed 0", "setup_s": round(t_setup, 3),
-                       "chunks": tile.nchunks, "split_rows": tile.nsplit},
+                       "chunks": tile.nchunks, "split_rows": tile.nsplit,
+                       "a_parts_cached": (world > 1 and not args.no_cache_a),
+                       "summa_last_call_ms": None if summa_ms is None else {"stage_loop": summa_ms[0], "comm_stream_busy": summa_ms[1]}},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
             "checksum_first_rows": checksum,
         }

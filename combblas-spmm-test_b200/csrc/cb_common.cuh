@@ -23,6 +23,7 @@ struct cb_ctx {
     void* nccl_row = nullptr;         // ranks with the same myprocrow ("RowWorld", src/CommGrid.cpp:66)
     void* nccl_col = nullptr;         // ranks with the same myproccol ("ColWorld", src/CommGrid.cpp:67)
     int64_t launches = 0;
+    bool summa_cache_a = true;        // keep received A parts on the device between multiplies (cb_summa_cache_a)
     // optional per-kernel device timing (bench.py's roofline): event pairs around K3 / K2 / fix-up launches
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events[3];     // [kind] -> begin,end,begin,end,...
@@ -63,6 +64,7 @@ static inline cb_tile_layout cb_layout(const cb_tile_meta& t) {
 // Device tile: doubly compressed rows (the row-major mirror of Dcsc, dcsc.h:124-131) plus a work partition.
 struct cb_tile {
     cb_ctx* ctx = nullptr;
+    uint64_t uid = 0;         // unique per built tile (0 for views onto received buffers)
     int64_t m = 0, n = 0, nnz = 0;
     int64_t nzr = 0;          // rows with at least one nonzero
     int64_t nzc = 0;          // columns with at least one nonzero (n_used of the traffic model)
@@ -92,6 +94,9 @@ struct cb_tile {
     // column slices of this tile, one per SUMMA stage it roots (built at the first cb_spmm_summa, cb_summa.cu)
     std::vector<cb_tile*> summa_parts;
     int64_t summa_key[3] = {-1, -1, -1};   // (grid id, gn, stages) the parts were cut for
+    // parts of the other ranks of my processor row, kept after the first cb_spmm_summa with this tile so that later
+    // multiplies with the same (immutable) matrix move only the dense panels (cb_summa_cache_a)
+    std::vector<cb_tile*> summa_remote;
 };
 
 static inline cb_tile_meta cb_tile_get_meta(const cb_tile* t) {

@@ -99,6 +99,7 @@ struct SummaState {
     std::vector<cudaEvent_t> comm_ev;  // begin/end pairs per stage on the communication stream
     // metas of every stage's A part as seen by this rank's row communicator, valid for `meta_tile`
     const cb_tile* meta_tile = nullptr;
+    uint64_t meta_uid = 0;
     std::vector<cb_tile_meta> metas;
 };
 
@@ -304,6 +305,8 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     const int64_t key[3] = {(int64_t)pr * 1000 + pc, gn, ns};
     if (mt->summa_key[0] != key[0] || mt->summa_key[1] != key[1] || mt->summa_key[2] != key[2]) {
         for (cb_tile* p : mt->summa_parts) cb_tile_free(p);
+        for (cb_tile* p : mt->summa_remote) cb_tile_free(p);
+        mt->summa_remote.clear();
         mt->summa_parts.assign(ns, nullptr);
         for (int s = 0; s < ns; ++s) {
             if (S->a_root[s] != ctx->myproccol) continue;
@@ -316,7 +319,7 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     }
     auto my_part = [&](int s) -> const cb_tile* { return mt->summa_parts[s] ? mt->summa_parts[s] : tile; };
     // ---- sizes of every stage's A part in my processor row (GetSetSizes, SpParHelper.cpp:797-809): one allgather
-    if (S->meta_tile != tile) {
+    if (S->meta_tile != tile || S->meta_uid != tile->uid) {
         S->metas.assign(ns, cb_tile_meta());
         if (pc > 1) {
             std::vector<cb_tile_meta> mine(ns);
@@ -337,11 +340,33 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
             for (int s = 0; s < ns; ++s) S->metas[s] = cb_tile_get_meta(my_part(s));
         }
         S->meta_tile = tile;
+        S->meta_uid = tile->uid;
+    }
+    // ---- A parts of my row neighbours: kept on the device after the first multiply with this tile (tiles are immutable)
+    const bool cache = ctx->summa_cache_a && pc > 1;
+    bool cached = cache && (int)mt->summa_remote.size() == ns;
+    if (cache && !cached) {
+        mt->summa_remote.assign(ns, nullptr);
+        for (int s = 0; s < ns; ++s) {
+            if (S->a_root[s] == ctx->myproccol) continue;
+            cb_tile* v = new cb_tile();
+            v->ctx = ctx;
+            const size_t bytes = cb_layout(S->metas[s]).total;
+            if (cudaMalloc((void**)&v->slab, bytes) != cudaSuccess) {
+                delete v;
+                for (cb_tile* p : mt->summa_remote) cb_tile_free(p);
+                mt->summa_remote.clear();
+                return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a cached SUMMA tile part", bytes);
+            }
+            v->slab_bytes = bytes; v->owns_slab = true;
+            cb_tile_bind(v, S->metas[s], v->slab);
+            mt->summa_remote[s] = v;
+        }
     }
     // ---- receive buffers
     size_t needA = 0, needX = 0;
     for (int s = 0; s < ns; ++s) {
-        if (S->a_root[s] != ctx->myproccol) needA = std::max(needA, cb_layout(S->metas[s]).total);
+        if (!cache && S->a_root[s] != ctx->myproccol) needA = std::max(needA, cb_layout(S->metas[s]).total);
         if (S->x_root[s] != ctx->myprocrow) needX = std::max(needX, (size_t)(S->seg[s + 1] - S->seg[s]) * (size_t)X->ld * es);
     }
     if (needA > S->slotA_bytes || needX > S->slotX_bytes) {
@@ -371,13 +396,13 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         const bool a_mine = S->a_root[s] == ctx->myproccol, x_mine = S->x_root[s] == ctx->myprocrow;
         const cb_tile_meta& meta = S->metas[s];
         if (s >= 2) CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->done[slot], 0));     // slot free again
-        const cb_tile* part = a_mine ? my_part(s) : S->view[slot];
+        const cb_tile* part = a_mine ? my_part(s) : (cache ? mt->summa_remote[s] : S->view[slot]);
         const char* xsrc = x_mine ? (const char*)X->ptr + (size_t)(seg_a - x0) * (size_t)X->ld * es : S->slotX[slot];
         CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s], ctx->comm));
         CB_NCCL(ctx, nccl().GroupStart());
-        if (pc > 1) {          // also for an empty part: the receiver needs its empty-row list for the identity fill
+        if (pc > 1 && !cached) {   // also for an empty part: the receiver needs its empty-row list for the identity fill
             const size_t bytes = cb_layout(meta).total;
-            char* buf = a_mine ? my_part(s)->slab : S->slotA[slot];
+            char* buf = a_mine ? my_part(s)->slab : (cache ? mt->summa_remote[s]->slab : S->slotA[slot]);
             CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->a_root[s], (ncclComm_t)ctx->nccl_row, ctx->comm));
         }
         if (pr > 1 && seg_len > 0 && kl > 0) {
@@ -389,7 +414,7 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s + 1], ctx->comm));
         CB_CUDA(ctx, cudaEventRecord(S->ready[slot], ctx->comm));
         CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, S->ready[slot], 0));
-        if (!a_mine) {
+        if (!a_mine && !cache) {
             cb_tile* v = S->view[slot];
             void* keep_carry = v->carry; size_t keep_bytes = v->carry_bytes;
             cb_tile_bind(v, meta, S->slotA[slot]);
@@ -403,6 +428,11 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         CB_CUDA(ctx, cudaEventRecord(S->done[slot], ctx->compute));
     }
     CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
+    return CB_OK;
+}
+
+int cb_summa_cache_a(cb_ctx* ctx, int on) {
+    ctx->summa_cache_a = on != 0;
     return CB_OK;
 }
 

@@ -4,6 +4,7 @@
 // Replaces, on the device, what the reference does on the host when a tile is materialised:
 // SpDCCols(const SpTuples&, bool) / the threaded tuple ctor (include/CombBLAS/SpDCCols.cpp:108-184,
 // :197-304) and Transpose (:853-868).  Sorting uses CUB's device radix sort (set-up, not the hot loop).
+#include <atomic>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -136,8 +137,10 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
                             int val_dtype, bool presorted, cb_scratch& sc, cb_tile** out) {
     const int sm = ctx->sm_count;
     cudaStream_t st = ctx->compute;
+    static std::atomic<uint64_t> next_uid{1};
     cb_tile* t = new cb_tile();
     t->ctx = ctx;
+    t->uid = next_uid.fetch_add(1);
     *out = nullptr;
     cb_tile_meta meta;
     memset(&meta, 0, sizeof meta);
@@ -355,6 +358,7 @@ int cb_tile_free(cb_tile* t) {
     if (t->owns_slab) cudaFree(t->slab);
     cudaFree(t->carry);
     for (cb_tile* sub : t->summa_parts) cb_tile_free(sub);
+    for (cb_tile* sub : t->summa_remote) cb_tile_free(sub);
     delete t;
     return CB_OK;
 }

@@ -145,6 +145,11 @@ int cb_spmm_local(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
  * Works on any pr x pc (the reference only on square grids, src/CommGrid.cpp:164-180). */
 int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring,
                   int64_t gm, int64_t gn, int64_t gk);
+/* A-part caching (default on).  Tiles are immutable, so the parts of A a rank receives from its row neighbours
+ * during the first cb_spmm_summa with a tile are kept in its HBM (one block-row of A per GPU: a few GB of 180 GB)
+ * and later multiplies with the same tile only move the dense panels.  The reference re-broadcasts A on every call
+ * (ParFriends.h:1036-1052); cb_summa_cache_a(ctx, 0) restores that behaviour (double-buffered receive slots). */
+int cb_summa_cache_a(cb_ctx* ctx, int on);
 /* device times of the last cb_spmm_summa on this rank: {whole stage loop on the compute stream (ms), time the
  * communication stream spent in the stage broadcasts (ms, overlaps the kernels), reserved, number of stages} */
 int cb_summa_times(cb_ctx* ctx, float ms[4]);
