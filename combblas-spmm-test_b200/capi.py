@@ -22,7 +22,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_timer_start", "cb_timer_stop", "cb_tile_upload_csc", "cb_tile_upload_coo", "cb_tile_from_device_coo",
            "cb_tile_free", "cb_tile_info", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
-           "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
+           "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
 
 
 class CBError(RuntimeError):
@@ -91,6 +91,7 @@ def lib():
         L.cb_summa_times.argtypes = [c_void_p, POINTER(c_float)]
         L.cb_summa_plan.argtypes = [c_int, c_int, c_int64, POINTER(c_int64), POINTER(c_int), POINTER(c_int), POINTER(c_int)]
         L.cb_summa_cache_a.argtypes = [c_void_p, c_int]
+        L.cb_comm_allreduce_i64.argtypes = [c_void_p, c_int, c_int, POINTER(c_int64), c_int]
         L.cb_spmm_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int]
         L.cb_profile_enable.argtypes = [c_void_p, c_int]
         L.cb_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]

@@ -34,6 +34,7 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -63,6 +64,7 @@ bool nccl_load() {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Broadcast, "ncclBroadcast")
     SYM(AllGather, "ncclAllGather")
+    SYM(AllReduce, "ncclAllReduce")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -428,6 +430,25 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         CB_CUDA(ctx, cudaEventRecord(S->done[slot], ctx->compute));
     }
     CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
+    return CB_OK;
+}
+
+// Small host-side reductions over the grid's communicators: what SpParMat::getnnz/getnrow/getncol do with
+// MPI_Allreduce (reference include/CombBLAS/SpParMat.cpp:773-797).  which: 0 world, 1 row, 2 column; op: 0 sum, 1 max, 2 min.
+int cb_comm_allreduce_i64(cb_ctx* ctx, int which, int op, int64_t* inout, int count) {
+    if (ctx->nranks == 1 || count <= 0) return CB_OK;
+    ncclComm_t comm = (ncclComm_t)(which == 0 ? ctx->nccl_world : which == 1 ? ctx->nccl_row : ctx->nccl_col);
+    if (!comm) return cb_fail(ctx, CB_ERR_NCCL, "cb_comm_allreduce_i64: no communicator %d", which);
+    if (op < 0 || op > 2) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_comm_allreduce_i64: op %d", op);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_scratch sc;
+    int64_t* d;
+    CB_CUDA(ctx, sc.alloc(&d, (size_t)count));
+    CB_CUDA(ctx, cudaMemcpyAsync(d, inout, sizeof(int64_t) * (size_t)count, cudaMemcpyHostToDevice, ctx->comm));
+    const int nccl_op = op == 0 ? 0 /*ncclSum*/ : op == 1 ? 2 /*ncclMax*/ : 3 /*ncclMin*/;
+    CB_NCCL(ctx, nccl().AllReduce(d, d, (size_t)count, 4 /*ncclInt64*/, nccl_op, comm, ctx->comm));
+    CB_CUDA(ctx, cudaMemcpyAsync(inout, d, sizeof(int64_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->comm));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
     return CB_OK;
 }
 

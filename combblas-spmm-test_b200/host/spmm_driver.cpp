@@ -1,0 +1,132 @@
+// spmm_driver - a driver in the style of the reference's ReleaseTests/MultTest.cpp / MultTiming.cpp, written against
+// the B200 host layer: declare the SpParMat typedefs, build a grid, read or generate A, multiply, PrintInfo, verify.
+//
+//   spmm_driver mtx  <file.mtx> <k> [ydump.bin]          fp64 PlusTimes on a Matrix Market file (BASELINE config C1)
+//   spmm_driver rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]   Kronecker matrix generated on the GPU
+//
+// Single process, or one process per GPU under a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK
+// (python -m torch.distributed.run --no-python ./spmm_driver ...).  Verification replays the multiply with the
+// host semiring functors on the local tile for the columns it owns (exact for integers, 1e-12 / 1e-5 for fp).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include "CombBLAS/CombBLAS.h"
+
+using namespace combblas;
+
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+template <class T> T hashval(uint64_t h);
+template <> double hashval<double>(uint64_t h) { return (double)(2 * (h >> 12) + 1) * 1.1102230246251565404e-16; }
+template <> float hashval<float>(uint64_t h) { return (float)(2 * (h >> 41) + 1) * 5.9604644775390625e-08f; }
+template <> int32_t hashval<int32_t>(uint64_t h) { return (int32_t)(1 + (h >> 8) % 100); }
+template <> int64_t hashval<int64_t>(uint64_t h) { return (int64_t)(1 + (h >> 8) % 100); }
+template <> bool hashval<bool>(uint64_t h) { return (h >> 63) != 0; }
+
+// X[i,j] = value(seed 42, i*k + j): the same operand the tests' oracle builds
+template <class IT, class NT>
+DenseParMat<IT, NT> MakeX(std::shared_ptr<CommGrid> grid, IT n, IT k) {
+    DenseParMat<IT, NT> X = DenseParMat<IT, NT>::Global(NT(), grid, n, k);
+    IT r0, c0;
+    X.GetPlaceInGlobalGrid(n, k, r0, c0);
+    for (IT i = 0; i < X.getlocalrows(); ++i)
+        for (IT j = 0; j < X.getlocalcols(); ++j)
+            X(i, j) = hashval<NT>(splitmix64(42ULL * 0x100000001B3ULL ^ (uint64_t)((r0 + i) * k + (c0 + j))));
+    return X;
+}
+
+// replay on the host with the semiring's own functors; only valid on a 1 x 1 grid (everything is local)
+template <class SR, class IT, class NA, class NX>
+bool VerifyLocal(const SpParMat<IT, NA, SpDCCols<IT, NA>>& A, const DenseParMat<IT, NX>& X, const DenseParMat<IT, NX>& Y, double tol) {
+    const SpDCCols<IT, NA>& t = A.seq();
+    const IT m = t.getnrow(), k = X.getlocalcols();
+    std::vector<NX> acc((size_t)m * (size_t)k, SR::id());
+    std::vector<char> touched((size_t)m * (size_t)k, 0);
+    for (size_t c = 0; c < t.jc.size(); ++c)
+        for (IT p = t.cp[c]; p < t.cp[c + 1]; ++p)
+            for (IT j = 0; j < k; ++j) {
+                const NX prod = SR::multiply((NA)t.numx[(size_t)p], (NX)X(t.jc[c], j));
+                const size_t q = (size_t)t.ir[(size_t)p] * (size_t)k + (size_t)j;
+                acc[q] = touched[q] ? SR::add(prod, acc[q]) : prod;
+                touched[q] = 1;
+            }
+    size_t bad = 0;
+    for (IT i = 0; i < m; ++i)
+        for (IT j = 0; j < k; ++j) {
+            const double a = (double)acc[(size_t)i * k + j], b = (double)Y(i, j);
+            if (tol == 0 ? a != b : std::fabs(a - b) > tol * std::max(std::fabs(a), 1e-300)) ++bad;
+        }
+    return bad == 0;
+}
+
+template <class SR, class NA, class NX>
+int RunRmat(int scale, int64_t k, int pr, int pc, double tol, bool values) {
+    typedef SpParMat<int64_t, NA, SpDCCols<int64_t, NA>> PSpMat;
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, pr, pc));
+    PSpMat A(grid);
+    A.GenGraph500(scale, 16, true, 0, values, 1);
+    A.PrintInfo();
+    DenseParMat<int64_t, NX> X = MakeX<int64_t, NX>(grid, A.getncol(), k);
+    double t0 = MPI_Wtime();
+    DenseParMat<int64_t, NX> Y = SpMM<SR>(A, X);
+    double t1 = MPI_Wtime();
+    Y = SpMM<SR>(A, X);
+    double t2 = MPI_Wtime();
+    float imb = A.LoadImbalance();
+    if (grid->GetRank() == 0)
+        std::cout << "SpMM first call " << (t1 - t0) << " s, second call " << (t2 - t1) << " s, load imbalance " << imb << std::endl;
+    if (grid->GetSize() == 1 && scale <= 16) {
+        if (VerifyLocal<SR>(A, X, Y, tol)) SpParHelper::Print("SpMM working correctly\n");
+        else { SpParHelper::Print("ERROR in SpMM, go fix it!\n"); return 1; }
+    }
+    return 0;
+}
+
+int main(int argc, char* argv[]) {
+    MPI_Init(&argc, &argv);
+    int rc = 0;
+    if (argc < 4) {
+        SpParHelper::Print("Usage: spmm_driver mtx <file.mtx> <k> [ydump.bin] | rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]\n");
+        MPI_Finalize();
+        return 2;
+    }
+    {
+        const std::string mode = argv[1];
+        if (mode == "mtx") {
+            typedef SpParMat<int64_t, double, SpDCCols<int64_t, double>> PSpMat_Double;
+            std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+            PSpMat_Double A(grid);
+            A.ParallelReadMM(argv[2], true, maximum<double>());
+            A.PrintInfo();
+            const int64_t k = std::atoll(argv[3]);
+            DenseParMat<int64_t, double> X = MakeX<int64_t, double>(grid, A.getncol(), k);
+            DenseParMat<int64_t, double> Y = SpMM<PlusTimesSRing<double, double>>(A, X);
+            if (grid->GetSize() == 1) {
+                if (VerifyLocal<PlusTimesSRing<double, double>>(A, X, Y, 1e-12)) SpParHelper::Print("SpMM working correctly\n");
+                else { SpParHelper::Print("ERROR in SpMM, go fix it!\n"); rc = 1; }
+                if (argc > 4) {
+                    FILE* f = std::fopen(argv[4], "wb");
+                    std::fwrite(Y.data(), sizeof(double), (size_t)Y.getlocalrows() * (size_t)Y.getlocalcols(), f);
+                    std::fclose(f);
+                }
+            }
+        } else {
+            const int scale = std::atoi(argv[2]);
+            const int64_t k = std::atoll(argv[3]);
+            const std::string what = argc > 4 ? argv[4] : "pt_f32";
+            const int pr = argc > 6 ? std::atoi(argv[5]) : 0, pc = argc > 6 ? std::atoi(argv[6]) : 0;
+            if (what == "pt_f32") rc = RunRmat<PlusTimesSRing<float, float>, float, float>(scale, k, pr, pc, 1e-5, true);
+            else if (what == "mp_i32") rc = RunRmat<MinPlusSRing<int32_t, int32_t>, int32_t, int32_t>(scale, k, pr, pc, 0, true);
+            else if (what == "sel_i64") rc = RunRmat<SelectMaxSRing<bool, int64_t>, bool, int64_t>(scale, k, pr, pc, 0, false);
+            else if (what == "bool") rc = RunRmat<PlusTimesSRing<bool, bool>, bool, bool>(scale, k, pr, pc, 0, false);
+            else { SpParHelper::Print("unknown semiring key\n"); rc = 2; }
+        }
+    }
+    MPI_Finalize();
+    return rc;
+}

@@ -1,0 +1,239 @@
+// SpParMat<IT,NT,DER>: 2D-distributed sparse matrix = CommGrid + one local tile, with a device-resident mirror.
+//
+// Surface and distribution follow the reference (include/CombBLAS/SpParMat.h:67-452):
+//   * block distribution with floor division, last grid row / column takes the remainder; Owner() and
+//     GetPlaceInGlobalGrid() as in SpParMat.cpp:5066-5115;
+//   * ctors (grid), (DER*, grid) [takes ownership, SpParMat.cpp:73-77], from global triples, ParallelReadMM
+//     (Matrix Market with symmetric expansion, SpHelper.h:75-91), getnrow/getncol/getnnz (SpParMat.cpp:773-797),
+//     seq()/seqptr(), PrintInfo (:2853-2875), LoadImbalance (:762-770), operator== (:2877-2884).
+// B200-first differences, all behind the same calls:
+//   * the tile is uploaded once (lazily) into HBM as doubly compressed rows and stays there (DeviceTile());
+//   * triple / file ingestion is replicated: every process sees the whole input and keeps what it owns, instead of
+//     MPI-IO + MPI_Alltoallv (one box, no network between the ranks);
+//   * GenGraph500() builds the tile directly on the GPU and never materialises it on the host.
+#ifndef CB_SPPARMAT_H
+#define CB_SPPARMAT_H
+
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include "CommGrid.h"
+#include "SpTuples.h"
+
+namespace combblas {
+
+template <class T>
+struct maximum { T operator()(const T& x, const T& y) const { return x < y ? y : x; } };
+template <class T>
+struct cb_sum { T operator()(const T& x, const T& y) const { return x + y; } };
+
+template <class IT, class NT, class DER>
+class SpParMat {
+public:
+    typedef typename DER::LocalIT LocalIT;
+    typedef typename DER::LocalNT LocalNT;
+    typedef typename cb_storage<NT>::type ST;
+
+    SpParMat() : commGrid(new CommGrid(MPI_COMM_WORLD, 0, 0)), spSeq(new DER()) {}
+    explicit SpParMat(std::shared_ptr<CommGrid> grid) : commGrid(grid), spSeq(new DER()) {}
+    SpParMat(DER* myseq, std::shared_ptr<CommGrid> grid) : commGrid(grid), spSeq(myseq) {}
+    // "matlab sparse" form (SpParMat.cpp:3066-3099) on replicated global triples
+    SpParMat(IT total_m, IT total_n, const std::vector<IT>& rows, const std::vector<IT>& cols, const std::vector<NT>& vals,
+             std::shared_ptr<CommGrid> grid, bool SumDuplicates = false)
+        : commGrid(grid), spSeq(nullptr) {
+        FromGlobalTriples(total_m, total_n, rows, cols, vals, SumDuplicates);
+    }
+    SpParMat(const SpParMat& rhs) : commGrid(rhs.commGrid), spSeq(new DER(rhs.seq())), gm(rhs.gm), gn(rhs.gn) {}
+    SpParMat& operator=(const SpParMat& rhs) {
+        if (this != &rhs) { DER* copy = new DER(rhs.seq()); Release(); commGrid = rhs.commGrid; spSeq = copy; gm = rhs.gm; gn = rhs.gn; }
+        return *this;
+    }
+    SpParMat(SpParMat&& rhs) noexcept
+        : commGrid(rhs.commGrid), spSeq(rhs.spSeq), gm(rhs.gm), gn(rhs.gn), dtile(rhs.dtile), dnnz(rhs.dnnz), devvals(rhs.devvals) {
+        rhs.spSeq = nullptr; rhs.dtile = nullptr;
+    }
+    ~SpParMat() { Release(); }
+
+    // ---- construction helpers
+    template <typename BinOp = maximum<NT>>
+    void ParallelReadMM(const std::string& filename, bool onebased, BinOp binop = BinOp()) {
+        std::ifstream in(filename);
+        if (!in) { SpParHelper::Print("COMBBLAS: Matrix-market file " + filename + " can not be found\n"); MPI_Abort(MPI_COMM_WORLD, NOFILE); }
+        std::string line;
+        std::getline(in, line);
+        std::string banner = line;
+        for (auto& ch : banner) ch = (char)std::tolower(ch);
+        const bool hasbanner = banner.compare(0, 14, "%%matrixmarket") == 0;
+        const bool pattern = hasbanner && banner.find("pattern") != std::string::npos;
+        const bool symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
+        if (hasbanner) do { std::getline(in, line); } while (!line.empty() && line[0] == '%');
+        long long tm, tn, tnz;
+        std::istringstream(line) >> tm >> tn >> tnz;
+        std::vector<IT> rows, cols;
+        std::vector<NT> vals;
+        long long ii, jj;
+        double vv = 1;
+        while (std::getline(in, line)) {
+            if (line.empty()) continue;
+            std::istringstream ls(line);
+            if (!(ls >> ii >> jj)) continue;
+            if (!pattern) ls >> vv;
+            if (onebased) { --ii; --jj; }
+            rows.push_back((IT)ii); cols.push_back((IT)jj); vals.push_back((NT)vv);
+            if (symmetric && ii != jj) { rows.push_back((IT)jj); cols.push_back((IT)ii); vals.push_back((NT)vv); }   // SpHelper.h:85-90
+        }
+        FromGlobalTriples((IT)tm, (IT)tn, rows, cols, vals, true, binop);
+    }
+
+    // Graph500-style Kronecker matrix generated on the device (GenWriteMatrix.cpp:96-131 recipe).  The local tile never
+    // exists on the host; seq() downloads it on first use.
+    void GenGraph500(int scale, int edgefactor, bool symmetric = true, uint64_t seed = 0, bool values = false, uint64_t val_seed = 1,
+                     const double* initiator = nullptr) {
+        Release();
+        spSeq = nullptr;
+        gm = gn = (IT)1 << scale;
+        IT r0, rl, c0, cl;
+        BlockRange(gm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), r0, rl);
+        BlockRange(gn, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), c0, cl);
+        const double dflt[4] = {0.57, 0.19, 0.19, 0.05};
+        const int vd = (values && !std::is_same<NT, bool>::value) ? cb_dtype_of<NT>::value : CB_PATTERN;
+        cb_ctx* ctx = commGrid->GetContext();
+        cb_check(cb_gen_rmat_tile(ctx, scale, edgefactor, seed, initiator ? initiator : dflt, symmetric ? 1 : 0, r0, rl, c0, cl, vd, val_seed, &dtile),
+                 ctx, "cb_gen_rmat_tile");
+        int64_t info[8];
+        cb_tile_info(dtile, info);
+        dnnz = info[0];
+        devvals = vd != CB_PATTERN;
+    }
+
+    // ---- queries
+    IT getnrow() const { return gm >= 0 ? gm : (IT)commGrid->SumCol(getlocalrows()); }
+    IT getncol() const { return gn >= 0 ? gn : (IT)commGrid->SumRow(getlocalcols()); }
+    IT getnnz() const { return (IT)commGrid->SumWorld(getlocalnnz()); }
+    LocalIT getlocalrows() const { return spSeq ? spSeq->getnrow() : LocalRows(); }
+    LocalIT getlocalcols() const { return spSeq ? spSeq->getncol() : LocalCols(); }
+    LocalIT getlocalnnz() const { return spSeq ? spSeq->getnnz() : (LocalIT)dnnz; }
+    std::shared_ptr<CommGrid> getcommgrid() const { return commGrid; }
+    DER& seq() const { const_cast<SpParMat*>(this)->MaterialiseHost(); return *spSeq; }
+    DER* seqptr() const { const_cast<SpParMat*>(this)->MaterialiseHost(); return spSeq; }
+
+    float LoadImbalance() const {
+        const int64_t tot = commGrid->SumWorld(getlocalnnz()), mx = commGrid->MaxWorld(getlocalnnz());
+        return tot ? (float)mx / ((float)tot / commGrid->GetSize()) : 1.0f;
+    }
+    void PrintInfo() const {
+        const IT mm = getnrow(), nn = getncol(), nz = getnnz();
+        if (commGrid->GetRank() == 0)
+            std::cout << "As a whole: " << mm << " rows and " << nn << " columns and " << nz << " nonzeros" << std::endl;
+    }
+    bool operator==(const SpParMat& rhs) const {
+        const int local = (seq() == rhs.seq()) ? 1 : 0;
+        return commGrid->MinWorld(local) == 1;
+    }
+
+    // Owner of global entry (grow, gcol) and its local indices (SpParMat.cpp:5066-5096)
+    template <typename LIT>
+    int Owner(IT total_m, IT total_n, IT grow, IT gcol, LIT& lrow, LIT& lcol) const {
+        const int procrows = commGrid->GetGridRows(), proccols = commGrid->GetGridCols();
+        const IT m_perproc = total_m / procrows, n_perproc = total_n / proccols;
+        const int own_procrow = m_perproc ? std::min((int)(grow / m_perproc), procrows - 1) : procrows - 1;
+        const int own_proccol = n_perproc ? std::min((int)(gcol / n_perproc), proccols - 1) : proccols - 1;
+        lrow = (LIT)(grow - own_procrow * m_perproc);
+        lcol = (LIT)(gcol - own_proccol * n_perproc);
+        return commGrid->GetRank(own_procrow, own_proccol);
+    }
+    void GetPlaceInGlobalGrid(IT& rowOffset, IT& colOffset) const {
+        rowOffset = commGrid->GetRankInProcCol() * (getnrow() / commGrid->GetGridRows());
+        colOffset = commGrid->GetRankInProcRow() * (getncol() / commGrid->GetGridCols());
+    }
+    static void BlockRange(IT total, int nb, int b, IT& start, IT& len) {
+        const IT per = total / nb;
+        start = (IT)b * per;
+        len = (b == nb - 1) ? total - start : per;
+    }
+
+    // ---- the device mirror: uploaded once, reused by every multiply
+    cb_tile* DeviceTile() const {
+        SpParMat* self = const_cast<SpParMat*>(this);
+        if (!self->dtile) {
+            cb_ctx* ctx = commGrid->GetContext();
+            self->Upload(ctx, *spSeq);
+            int64_t info[8];
+            cb_tile_info(self->dtile, info);
+            self->dnnz = info[0];
+        }
+        return self->dtile;
+    }
+    void FreeDeviceTile() { if (dtile) { cb_tile_free(dtile); dtile = nullptr; } }
+
+private:
+    template <typename BinOp = maximum<NT>>
+    void FromGlobalTriples(IT total_m, IT total_n, const std::vector<IT>& rows, const std::vector<IT>& cols, const std::vector<NT>& vals,
+                           bool mergedups, BinOp binop = BinOp()) {
+        Release();
+        gm = total_m; gn = total_n;
+        IT r0, rl, c0, cl;
+        BlockRange(gm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), r0, rl);
+        BlockRange(gn, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), c0, cl);
+        SpTuples<LocalIT, NT> mine(0, (LocalIT)rl, (LocalIT)cl);
+        const int me = commGrid->GetRank();
+        for (size_t i = 0; i < rows.size(); ++i) {
+            LocalIT lr, lc;
+            if (Owner(gm, gn, rows[i], cols[i], lr, lc) == me) mine.tuples.emplace_back(lr, lc, vals[i]);
+        }
+        if (mergedups) mine.RemoveDuplicates(binop);     // SparseCommon, SpParMat.cpp:2962-2967
+        else mine.SortColBased();
+        spSeq = new DER(mine, false);
+    }
+    void Upload(cb_ctx* ctx, const SpDCCols<LocalIT, NT>& t) {
+        const int idt = sizeof(LocalIT) == 4 ? CB_I32 : CB_I64;
+        const bool pattern = std::is_same<NT, bool>::value && std::all_of(t.numx.begin(), t.numx.end(), [](ST v) { return v != 0; });
+        cb_check(cb_tile_upload_csc(ctx, t.getnrow(), t.getncol(), t.getnnz(), t.getnzc(), t.cp.data(), t.jc.data(), t.ir.data(),
+                                    pattern ? nullptr : (const void*)t.numx.data(), idt, pattern ? CB_PATTERN : cb_dtype_of<NT>::value, &dtile),
+                 ctx, "cb_tile_upload_csc");
+    }
+    void Upload(cb_ctx* ctx, const SpCCols<LocalIT, NT>& t) {
+        const int idt = sizeof(LocalIT) == 4 ? CB_I32 : CB_I64;
+        const bool pattern = std::is_same<NT, bool>::value && std::all_of(t.num.begin(), t.num.end(), [](ST v) { return v != 0; });
+        cb_check(cb_tile_upload_csc(ctx, t.getnrow(), t.getncol(), t.getnnz(), 0, t.jc.data(), nullptr, t.ir.data(),
+                                    pattern ? nullptr : (const void*)t.num.data(), idt, pattern ? CB_PATTERN : cb_dtype_of<NT>::value, &dtile),
+                 ctx, "cb_tile_upload_csc");
+    }
+    LocalIT LocalRows() const { IT s, l; BlockRange(gm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), s, l); return (LocalIT)l; }
+    LocalIT LocalCols() const { IT s, l; BlockRange(gn, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), s, l); return (LocalIT)l; }
+    void MaterialiseHost() {
+        if (spSeq || !dtile) { if (!spSeq) spSeq = new DER(); return; }
+        // device tile (generated on the GPU) -> host tile, through CSR triples
+        const LocalIT lm = LocalRows(), ln = LocalCols();
+        std::vector<int64_t> rowptr((size_t)lm + 1), col((size_t)dnnz);
+        std::vector<ST> vals;
+        int64_t info[8];
+        cb_tile_info(dtile, info);
+        const bool hasvals = !std::is_same<NT, bool>::value && cb_tile_has_values();
+        if (hasvals) vals.resize((size_t)dnnz);
+        cb_check(cb_tile_download_csr(dtile, rowptr.data(), col.data(), hasvals ? vals.data() : nullptr), commGrid->GetContext(), "cb_tile_download_csr");
+        SpTuples<LocalIT, NT> t(0, lm, ln);
+        t.tuples.reserve((size_t)dnnz);
+        for (LocalIT r = 0; r < lm; ++r)
+            for (int64_t p = rowptr[(size_t)r]; p < rowptr[(size_t)r + 1]; ++p)
+                t.tuples.emplace_back(r, (LocalIT)col[(size_t)p], hasvals ? (NT)vals[(size_t)p] : NT(1));
+        t.SortColBased();
+        spSeq = new DER(t, false);
+    }
+    bool cb_tile_has_values() const { return devvals; }
+    void Release() {
+        FreeDeviceTile();
+        delete spSeq;
+        spSeq = nullptr;
+    }
+
+    std::shared_ptr<CommGrid> commGrid;
+    DER* spSeq;
+    IT gm = -1, gn = -1;            // global dimensions when known without communication
+    cb_tile* dtile = nullptr;
+    int64_t dnnz = 0;
+    bool devvals = false;
+};
+
+}  // namespace combblas
+#endif

@@ -145,6 +145,10 @@ int cb_spmm_local(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
  * Works on any pr x pc (the reference only on square grids, src/CommGrid.cpp:164-180). */
 int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense* Y, int semiring,
                   int64_t gm, int64_t gn, int64_t gk);
+/* Small host-side reductions over the grid's communicators, for the metadata the reference gets with MPI_Allreduce
+ * (SpParMat::getnnz/getnrow/getncol, include/CombBLAS/SpParMat.cpp:773-797).  which: 0 = world, 1 = processor row
+ * ("RowWorld"), 2 = processor column ("ColWorld"); op: 0 = sum, 1 = max, 2 = min.  Collective. */
+int cb_comm_allreduce_i64(cb_ctx* ctx, int which, int op, int64_t* inout, int count);
 /* A-part caching (default on).  Tiles are immutable, so the parts of A a rank receives from its row neighbours
  * during the first cb_spmm_summa with a tile are kept in its HBM (one block-row of A per GPU: a few GB of 180 GB)
  * and later multiplies with the same tile only move the dense panels.  The reference re-broadcasts A on every call
