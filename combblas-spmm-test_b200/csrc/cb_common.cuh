@@ -24,6 +24,8 @@ struct cb_ctx {
     void* nccl_col = nullptr;         // ranks with the same myproccol ("ColWorld", src/CommGrid.cpp:67)
     int64_t launches = 0;
     bool summa_cache_a = true;        // keep received A parts on the device between multiplies (cb_summa_cache_a)
+    bool summa_p2p = true;            // dense panels travel by copy-engine pushes into peer memory (cb_p2p.cu), not NCCL
+    void* p2p_state = nullptr;
     // optional per-kernel device timing (bench.py's roofline): event pairs around K3 / K2 / fix-up launches
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events[3];     // [kind] -> begin,end,begin,end,...
@@ -184,3 +186,13 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
 int cb_nccl_init(cb_ctx* ctx, const void* id128);
 void cb_nccl_destroy(cb_ctx* ctx);
 void cb_summa_release(cb_ctx* ctx);
+int cb_p2p_prepare(cb_ctx* ctx, size_t need_bytes);
+bool cb_p2p_active(cb_ctx* ctx);
+char* cb_p2p_xfull(cb_ctx* ctx);
+int cb_p2p_begin(cb_ctx* ctx);
+int cb_p2p_push(cb_ctx* ctx, cudaEvent_t operands_ready, int stage, size_t dst_off, const void* src, size_t bytes);
+int cb_p2p_wait_stage(cb_ctx* ctx, cudaStream_t stream, int stage);
+int cb_p2p_finish(cb_ctx* ctx, cudaStream_t compute);
+void cb_p2p_release(cb_ctx* ctx);
+int cb_p2p_debug_times(cb_ctx* ctx, cudaEvent_t origin, float* t_start, float* t_end);
+int cb_nccl_allgather_col(cb_ctx* ctx, const void* send_host, void* recv_host, size_t bytes);

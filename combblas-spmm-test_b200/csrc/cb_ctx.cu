@@ -89,6 +89,7 @@ int cb_ctx_create_grid(int device, int rank, int nranks, int pr, int pc, const v
     CB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
     CB_CUDA(nullptr, cudaEventCreate(&c->t0));
     CB_CUDA(nullptr, cudaEventCreate(&c->t1));
+    if (const char* tr = getenv("CB_SUMMA_TRANSPORT")) c->summa_p2p = strcmp(tr, "nccl") != 0;
     if (nranks > 1) {
         if (!id128) { cb_ctx_destroy(c); return cb_fail(nullptr, CB_ERR_INVALIDPARAMS, "a unique id is required for %d ranks", nranks); }
         int s = cb_nccl_init(c, id128);
@@ -106,6 +107,7 @@ int cb_ctx_destroy(cb_ctx* c) {
     if (c->compute) cudaStreamSynchronize(c->compute);
     if (c->comm) cudaStreamSynchronize(c->comm);
     cb_summa_release(c);
+    cb_p2p_release(c);
     cb_nccl_destroy(c);
     for (int k = 0; k < 3; ++k) for (cudaEvent_t e : c->prof_events[k]) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);

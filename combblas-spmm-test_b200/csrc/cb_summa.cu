@@ -365,11 +365,14 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
             mt->summa_remote[s] = v;
         }
     }
-    // ---- receive buffers
+    // ---- panel transport: copy-engine pushes into peer memory (cb_p2p.cu) unless CB_SUMMA_TRANSPORT=nccl
+    const bool p2p = pr > 1 && ctx->summa_p2p;
+    if (p2p) CB_TRY(cb_p2p_prepare(ctx, (size_t)gn * (size_t)X->ld * es));
+    // ---- receive buffers of the NCCL paths
     size_t needA = 0, needX = 0;
     for (int s = 0; s < ns; ++s) {
         if (!cache && S->a_root[s] != ctx->myproccol) needA = std::max(needA, cb_layout(S->metas[s]).total);
-        if (S->x_root[s] != ctx->myprocrow) needX = std::max(needX, (size_t)(S->seg[s + 1] - S->seg[s]) * (size_t)X->ld * es);
+        if (!p2p && S->x_root[s] != ctx->myprocrow) needX = std::max(needX, (size_t)(S->seg[s + 1] - S->seg[s]) * (size_t)X->ld * es);
     }
     if (needA > S->slotA_bytes || needX > S->slotX_bytes) {
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
@@ -391,47 +394,90 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     // ---- stage loop
     CB_CUDA(ctx, cudaEventRecord(S->begin, ctx->compute));
     CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->begin, 0));      // operands produced on the compute stream are ready
+    if (p2p) {
+        // all panels this rank owns leave right away, one DMA stream per column peer
+        CB_TRY(cb_p2p_begin(ctx));
+        for (int s = 0; s < ns; ++s) {
+            const int64_t seg_len = S->seg[s + 1] - S->seg[s];
+            if (S->x_root[s] != ctx->myprocrow || seg_len <= 0 || kl <= 0) continue;
+            CB_TRY(cb_p2p_push(ctx, S->begin, s, (size_t)S->seg[s] * (size_t)X->ld * es,
+                               (const char*)X->ptr + (size_t)(S->seg[s] - x0) * (size_t)X->ld * es, (size_t)seg_len * (size_t)X->ld * es));
+        }
+    }
+    // Stage order.  With the peer transport nothing about X is collective, so a rank multiplies the stages whose panel it
+    // owns first (no waiting) while the other panels are still in flight; ranks of one processor row share the order, which
+    // keeps the row-communicator broadcasts of A matched.  (The merge is order independent: (+) is commutative; for
+    // floating point the order is still fixed per rank, so results are reproducible.)
+    std::vector<int> order;
+    for (int s = 0; s < ns; ++s) if (p2p && S->x_root[s] == ctx->myprocrow) order.push_back(s);
+    for (int s = 0; s < ns; ++s) if (!(p2p && S->x_root[s] == ctx->myprocrow)) order.push_back(s);
     bool wrote = false;
-    for (int s = 0; s < ns; ++s) {
-        const int slot = s & 1;
+    for (int oi = 0; oi < ns; ++oi) {
+        const int s = order[oi];
+        const int slot = oi & 1;
         const int64_t seg_a = S->seg[s], seg_len = S->seg[s + 1] - S->seg[s];
         const bool a_mine = S->a_root[s] == ctx->myproccol, x_mine = S->x_root[s] == ctx->myprocrow;
         const cb_tile_meta& meta = S->metas[s];
-        if (s >= 2) CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->done[slot], 0));     // slot free again
+        const bool bcast_a = pc > 1 && !cached;                    // also for an empty part: the receiver needs its empty-row list
+        const bool bcast_x = !p2p && pr > 1 && seg_len > 0 && kl > 0;
         const cb_tile* part = a_mine ? my_part(s) : (cache ? mt->summa_remote[s] : S->view[slot]);
-        const char* xsrc = x_mine ? (const char*)X->ptr + (size_t)(seg_a - x0) * (size_t)X->ld * es : S->slotX[slot];
-        CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s], ctx->comm));
-        CB_NCCL(ctx, nccl().GroupStart());
-        if (pc > 1 && !cached) {   // also for an empty part: the receiver needs its empty-row list for the identity fill
-            const size_t bytes = cb_layout(meta).total;
-            char* buf = a_mine ? my_part(s)->slab : (cache ? mt->summa_remote[s]->slab : S->slotA[slot]);
-            CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->a_root[s], (ncclComm_t)ctx->nccl_row, ctx->comm));
+        const char* xsrc = x_mine ? (const char*)X->ptr + (size_t)(seg_a - x0) * (size_t)X->ld * es
+                                  : (p2p ? cb_p2p_xfull(ctx) + (size_t)seg_a * (size_t)X->ld * es : S->slotX[slot]);
+        if (bcast_a || bcast_x) {
+            if (oi >= 2) CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->done[slot], 0));     // slot free again
+            CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s], ctx->comm));
+            CB_NCCL(ctx, nccl().GroupStart());
+            if (bcast_a) {
+                const size_t bytes = cb_layout(meta).total;
+                char* buf = a_mine ? my_part(s)->slab : (cache ? mt->summa_remote[s]->slab : S->slotA[slot]);
+                CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->a_root[s], (ncclComm_t)ctx->nccl_row, ctx->comm));
+            }
+            if (bcast_x) {
+                const size_t bytes = (size_t)seg_len * (size_t)X->ld * es;
+                char* buf = const_cast<char*>(xsrc);
+                CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->x_root[s], (ncclComm_t)ctx->nccl_col, ctx->comm));
+            }
+            CB_NCCL(ctx, nccl().GroupEnd());
+            CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s + 1], ctx->comm));
+            CB_CUDA(ctx, cudaEventRecord(S->ready[slot], ctx->comm));
+            CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, S->ready[slot], 0));
         }
-        if (pr > 1 && seg_len > 0 && kl > 0) {
-            const size_t bytes = (size_t)seg_len * (size_t)X->ld * es;
-            char* buf = const_cast<char*>(xsrc);
-            CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, S->x_root[s], (ncclComm_t)ctx->nccl_col, ctx->comm));
-        }
-        CB_NCCL(ctx, nccl().GroupEnd());
-        CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s + 1], ctx->comm));
-        CB_CUDA(ctx, cudaEventRecord(S->ready[slot], ctx->comm));
-        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, S->ready[slot], 0));
+        if (p2p && !x_mine && seg_len > 0 && kl > 0) CB_TRY(cb_p2p_wait_stage(ctx, ctx->compute, s));
         if (!a_mine && !cache) {
             cb_tile* v = S->view[slot];
             void* keep_carry = v->carry; size_t keep_bytes = v->carry_bytes;
             cb_tile_bind(v, meta, S->slotA[slot]);
             v->carry = keep_carry; v->carry_bytes = keep_bytes;
         }
-        if (meta.nnz > 0 || !wrote) {
+        static const bool skip_compute = getenv("CB_SUMMA_SKIP_COMPUTE") != nullptr;     // transport-only timing (debug)
+        if (!skip_compute && (meta.nnz > 0 || !wrote)) {
             // a stage whose A part is empty still has to give Y its identity fill if nothing was written yet
             CB_TRY(cb_spmm_launch(ctx, ctx->compute, part, xsrc, X->ld, Y->ptr, Y->ld, kl, X->dtype, semiring, wrote ? 1 : 0));
             wrote = true;
         }
         CB_CUDA(ctx, cudaEventRecord(S->done[slot], ctx->compute));
     }
+    if (p2p) CB_TRY(cb_p2p_finish(ctx, ctx->compute));
     CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
     return CB_OK;
 }
+
+// byte allgather over the processor column with host buffers (set-up traffic of the peer transport)
+}  // extern "C"
+int cb_nccl_allgather_col(cb_ctx* ctx, const void* send_host, void* recv_host, size_t bytes) {
+    const int np = ctx->pr;
+    if (np == 1) { memcpy(recv_host, send_host, bytes); return CB_OK; }
+    cb_scratch sc;
+    char *d_send, *d_recv;
+    CB_CUDA(ctx, sc.alloc(&d_send, bytes));
+    CB_CUDA(ctx, sc.alloc(&d_recv, bytes * (size_t)np));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_send, send_host, bytes, cudaMemcpyHostToDevice, ctx->comm));
+    CB_NCCL(ctx, nccl().AllGather(d_send, d_recv, bytes, ncclInt8, (ncclComm_t)ctx->nccl_col, ctx->comm));
+    CB_CUDA(ctx, cudaMemcpyAsync(recv_host, d_recv, bytes * (size_t)np, cudaMemcpyDeviceToHost, ctx->comm));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+    return CB_OK;
+}
+extern "C" {
 
 // Small host-side reductions over the grid's communicators: what SpParMat::getnnz/getnrow/getncol do with
 // MPI_Allreduce (reference include/CombBLAS/SpParMat.cpp:773-797).  which: 0 world, 1 row, 2 column; op: 0 sum, 1 max, 2 min.
@@ -466,10 +512,16 @@ int cb_summa_times(cb_ctx* ctx, float ms[4]) {
     CB_CUDA(ctx, cudaEventElapsedTime(&ms[0], S->begin, S->end));
     for (int s = 0; s < S->nstages; ++s) {
         float t = 0;
-        if (cudaEventElapsedTime(&t, S->comm_ev[2 * s], S->comm_ev[2 * s + 1]) == cudaSuccess) ms[1] += t;
+        if (cudaEventQuery(S->comm_ev[2 * s + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&t, S->comm_ev[2 * s], S->comm_ev[2 * s + 1]) == cudaSuccess && t > 0) ms[1] += t;
     }
     cudaGetLastError();
     ms[3] = (float)S->nstages;
+    if (getenv("CB_SUMMA_DEBUG")) {
+        float a = -1, b = -1;
+        cb_p2p_debug_times(ctx, S->begin, &a, &b);
+        fprintf(stderr, "[summa rank %d] stage loop %.3f ms; pushes to first peer started at %.3f ms, done at %.3f ms after begin\n", ctx->rank, ms[0], a, b);
+    }
     return CB_OK;
 }
 
