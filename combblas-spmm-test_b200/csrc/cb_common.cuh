@@ -24,6 +24,7 @@ struct cb_ctx {
     void* nccl_col = nullptr;         // ranks with the same myproccol ("ColWorld", src/CommGrid.cpp:67)
     int64_t launches = 0;
     bool summa_cache_a = true;        // keep received A parts on the device between multiplies (cb_summa_cache_a)
+    bool summa_merge = true;          // fuse the resident parts of a block-row per X owner (CB_SUMMA_MERGE=0 disables)
     bool summa_p2p = true;            // dense panels travel by copy-engine pushes into peer memory (cb_p2p.cu), not NCCL
     void* p2p_state = nullptr;
     // optional per-kernel device timing (bench.py's roofline): event pairs around K3 / K2 / fix-up launches
@@ -99,6 +100,9 @@ struct cb_tile {
     // parts of the other ranks of my processor row, kept after the first cb_spmm_summa with this tile so that later
     // multiplies with the same (immutable) matrix move only the dense panels (cb_summa_cache_a)
     std::vector<cb_tile*> summa_remote;
+    // my whole block-row of A regrouped by the X row block it multiplies (one tile per processor row), built from the
+    // own + cached parts at the second multiply; entries stay NULL where a single existing part already is that tile
+    std::vector<cb_tile*> summa_merged;
 };
 
 static inline cb_tile_meta cb_tile_get_meta(const cb_tile* t) {

@@ -90,6 +90,7 @@ int cb_ctx_create_grid(int device, int rank, int nranks, int pr, int pc, const v
     CB_CUDA(nullptr, cudaEventCreate(&c->t0));
     CB_CUDA(nullptr, cudaEventCreate(&c->t1));
     if (const char* tr = getenv("CB_SUMMA_TRANSPORT")) c->summa_p2p = strcmp(tr, "nccl") != 0;
+    if (const char* mg = getenv("CB_SUMMA_MERGE")) c->summa_merge = strcmp(mg, "0") != 0;
     if (nranks > 1) {
         if (!id128) { cb_ctx_destroy(c); return cb_fail(nullptr, CB_ERR_INVALIDPARAMS, "a unique id is required for %d ranks", nranks); }
         int s = cb_nccl_init(c, id128);

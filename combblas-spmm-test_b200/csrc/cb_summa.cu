@@ -219,6 +219,43 @@ int slice_cols(cb_ctx* ctx, const cb_tile* t, int64_t c0, int64_t c1, cb_tile** 
     return cb_tile_build_from_keys(ctx, t->m, c1 - c0, nsel, keys_sel, (t->vals && nsel) ? vals_sel : nullptr, t->val_dtype, true, sc, out);
 }
 
+// all nonzeros of `t` as keys row<<32 | (col + coloff), for concatenating column-disjoint parts of one block-row
+__global__ void emit_keys_kernel(const int32_t* __restrict__ colflag, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ nzrows, int64_t nzr, int64_t nz, int32_t coloff,
+                                 uint64_t* __restrict__ keys) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nzr;           // largest ridx with rowptr[ridx] <= p
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rowptr[mid] <= p) lo = mid; else hi = mid; }
+        keys[p] = ((uint64_t)(uint32_t)nzrows[lo] << 32) | (uint64_t)(uint32_t)((colflag[p] & 0x7fffffff) + coloff);
+    }
+}
+
+// one tile from column-disjoint parts of the same rows; part i's columns are shifted by coloff[i]
+int merge_parts(cb_ctx* ctx, const std::vector<const cb_tile*>& parts, const std::vector<int64_t>& coloff, int64_t m, int64_t n,
+                int val_dtype, cb_tile** out) {
+    cb_scratch sc;
+    cudaStream_t st = ctx->compute;
+    int64_t nz = 0;
+    for (const cb_tile* p : parts) nz += p->nnz;
+    if (nz >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "merged block-row part has %lld nonzeros", (long long)nz);
+    const size_t vs = cb_dtype_size(val_dtype);
+    uint64_t* keys = nullptr;
+    char* vals = nullptr;
+    CB_CUDA(ctx, sc.alloc(&keys, (size_t)nz));
+    if (vs) CB_CUDA(ctx, sc.alloc(&vals, vs * (size_t)nz));
+    int64_t off = 0;
+    for (size_t i = 0; i < parts.size(); ++i) {
+        const cb_tile* p = parts[i];
+        if (p->nnz == 0) continue;
+        emit_keys_kernel<<<grid_for(p->nnz, ctx->sm_count), 256, 0, st>>>(p->colflag, p->rowptr, p->nzrows, p->nzr, p->nnz, (int32_t)coloff[i], keys + off);
+        CB_LAUNCHED(ctx);
+        if (vs) CB_CUDA(ctx, cudaMemcpyAsync(vals + vs * (size_t)off, p->vals, vs * (size_t)p->nnz, cudaMemcpyDeviceToDevice, st));
+        off += p->nnz;
+    }
+    CB_CUDA(ctx, cudaGetLastError());
+    return cb_tile_build_from_keys(ctx, m, n, nz, keys, (vs && nz) ? vals : nullptr, val_dtype, false, sc, out);
+}
+
 }  // namespace
 
 extern "C" {
@@ -309,6 +346,8 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         for (cb_tile* p : mt->summa_parts) cb_tile_free(p);
         for (cb_tile* p : mt->summa_remote) cb_tile_free(p);
         mt->summa_remote.clear();
+        for (cb_tile* p : mt->summa_merged) cb_tile_free(p);
+        mt->summa_merged.clear();
         mt->summa_parts.assign(ns, nullptr);
         for (int s = 0; s < ns; ++s) {
             if (S->a_root[s] != ctx->myproccol) continue;
@@ -368,6 +407,58 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     // ---- panel transport: copy-engine pushes into peer memory (cb_p2p.cu) unless CB_SUMMA_TRANSPORT=nccl
     const bool p2p = pr > 1 && ctx->summa_p2p;
     if (p2p) CB_TRY(cb_p2p_prepare(ctx, (size_t)gn * (size_t)X->ld * es));
+
+    // ---- steady state with a resident block-row: once every part of my block-row of A is on this GPU (second multiply with
+    // the same tile onwards) the parts that meet the same X row block are fused into one tile, so a multiply is pr kernel
+    // launches over full-length rows instead of one launch per stage over row fragments.
+    if (cached && ctx->summa_merge && (p2p || pr == 1)) {
+        if ((int)mt->summa_merged.size() != pr) {
+            for (cb_tile* p : mt->summa_merged) cb_tile_free(p);
+            mt->summa_merged.assign(pr, nullptr);
+            for (int r = 0; r < pr; ++r) {
+                int64_t b0, bl;
+                block_range(gn, pr, r, &b0, &bl);
+                std::vector<const cb_tile*> parts;
+                std::vector<int64_t> offs;
+                for (int s = 0; s < ns; ++s) {
+                    if (S->x_root[s] != r) continue;
+                    parts.push_back(S->a_root[s] == ctx->myproccol ? my_part(s) : mt->summa_remote[s]);
+                    offs.push_back(S->seg[s] - b0);
+                }
+                if (parts.size() == 1 && offs[0] == 0 && parts[0]->n == bl) continue;      // a single part is already the tile
+                CB_TRY(merge_parts(ctx, parts, offs, rl, bl, tile->val_dtype, &mt->summa_merged[r]));
+            }
+        }
+        CB_CUDA(ctx, cudaEventRecord(S->begin, ctx->compute));
+        if (p2p) {
+            CB_TRY(cb_p2p_begin(ctx));
+            for (int s = 0; s < ns; ++s) {
+                const int64_t seg_len = S->seg[s + 1] - S->seg[s];
+                if (S->x_root[s] != ctx->myprocrow || seg_len <= 0 || kl <= 0) continue;
+                CB_TRY(cb_p2p_push(ctx, S->begin, s, (size_t)S->seg[s] * (size_t)X->ld * es,
+                                   (const char*)X->ptr + (size_t)(S->seg[s] - x0) * (size_t)X->ld * es, (size_t)seg_len * (size_t)X->ld * es));
+            }
+        }
+        bool wrote_m = false;
+        for (int oi = 0; oi < pr; ++oi) {
+            const int r = oi == 0 ? ctx->myprocrow : (oi <= ctx->myprocrow ? oi - 1 : oi);     // my own X block first
+            int64_t b0, bl;
+            block_range(gn, pr, r, &b0, &bl);
+            const cb_tile* part = mt->summa_merged[r];
+            if (!part) for (int s = 0; s < ns; ++s) if (S->x_root[s] == r) part = S->a_root[s] == ctx->myproccol ? my_part(s) : mt->summa_remote[s];
+            if (r != ctx->myprocrow && kl > 0)
+                for (int s = 0; s < ns; ++s) if (S->x_root[s] == r && S->seg[s + 1] > S->seg[s]) CB_TRY(cb_p2p_wait_stage(ctx, ctx->compute, s));
+            const char* xsrc = r == ctx->myprocrow ? (const char*)X->ptr : cb_p2p_xfull(ctx) + (size_t)b0 * (size_t)X->ld * es;
+            if (!part) continue;
+            if (part->nnz > 0 || !wrote_m) {
+                CB_TRY(cb_spmm_launch(ctx, ctx->compute, part, xsrc, X->ld, Y->ptr, Y->ld, kl, X->dtype, semiring, wrote_m ? 1 : 0));
+                wrote_m = true;
+            }
+        }
+        if (p2p) CB_TRY(cb_p2p_finish(ctx, ctx->compute));
+        CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
+        return CB_OK;
+    }
     // ---- receive buffers of the NCCL paths
     size_t needA = 0, needX = 0;
     for (int s = 0; s < ns; ++s) {
