@@ -164,13 +164,15 @@ def main():
     ap.add_argument("--ref-scale", type=int, default=18, help="largest generator scale the CPU reference sample uses")
     ap.add_argument("--ref-cols", type=int, default=16, help="panel columns of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--grid", default=None, help="process grid as PRxPC (default: as square as possible, pr <= pc)")
     ap.add_argument("--no-cache-a", action="store_true", help="re-broadcast the A parts every multiply like the reference does")
     args = ap.parse_args()
     if args.workload is None:
-        # N=1: the configuration the metric is quoted on that fits one GPU (BASELINE configs[1]); N>1: the 2D SUMMA configs
-        args.workload = "c2" if args.gpus == 1 else "c3"
+        # One workload for every N so the 1/2/4/8 series is a strong-scaling series: BASELINE configs[2], the configuration
+        # the metric is quoted on "at 1/2/4/8 B200" (ER n=2^24 x k=128 fp32).  It fits one GPU (2.1 GB A + 2 x 8.6 GB panels).
+        # configs[1] (R-MAT s20 x 64) and the others run with --workload c2|c4|c5|...; their numbers are in profiles/.
+        args.workload = "c3"
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
@@ -269,14 +271,20 @@ def main():
     k2_ms = prof_ms["spmm"] / max(prof_n["spmm"], 1)
     stages = len(cb.capi.summa_plan(pr, pc, N)[1])
     summa_ms = ctx.summa_times() if world > 1 else None
-    b_alg_local = alg_bytes(tile.nnz, tile.m, tile.nzc, kl, s_val, s_t)      # per multiply on this rank (all stages together)
-    k2_per_step = prof_n["spmm"] / args.steps if args.steps else 1
-    achieved = b_alg_local / max(k2_per_step, 1) / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    # this rank multiplies its whole block-row of A (nnz/pr nonzeros, all column blocks) by its k-block of X
+    nzc_total = float(tile.nzc) if dist is None else sm[2].item()       # nonempty columns summed over all tiles
+    nnz_rank = nnz_total / pr
+    nzc_rank = nzc_total / pr                                            # nonempty columns of a block-row (grid-row average)
+    b_alg_local = alg_bytes(nnz_rank, tile.m, nzc_rank, kl, s_val, s_t)
+    k2_per_step = prof_n["spmm"] / args.steps if args.steps else 1       # launches per multiply (1, or one per X owner / stage)
+    k2_ms_step = prof_ms["spmm"] / args.steps if args.steps else 0.0     # K2 time per multiply on this rank
+    achieved = b_alg_local / (k2_ms_step * 1e-3) / 1e9 if k2_ms_step > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "cb_spmm_kernel", "kernel_ms": k2_ms, "kernel_share_of_step": (prof_ms["spmm"] / args.steps) / ms_step if ms_step else None,
-                "peak_source": peak_src, "alg_bytes_per_launch": b_alg_local / max(k2_per_step, 1),
-                "gather_bytes_per_launch": (tile.nnz * (4 + s_val) + tile.nnz * kl * s_t + tile.m * kl * s_t) / max(k2_per_step, 1),
-                "whole_step_gbs": alg_bytes(nnz_total, N, tile.nzc if world == 1 else N, k, s_val, s_t) / (ms_step * 1e-3) / 1e9}
+                "kernel": "cb_spmm_kernel", "kernel_ms": k2_ms, "kernel_launches_per_step": k2_per_step,
+                "kernel_ms_per_step": k2_ms_step, "kernel_share_of_step": k2_ms_step / ms_step if ms_step else None,
+                "peak_source": peak_src, "alg_bytes_per_step_this_rank": b_alg_local,
+                "gather_bytes_per_step_this_rank": nnz_rank * (4 + s_val) + nnz_rank * kl * s_t + tile.m * kl * s_t,
+                "whole_job_alg_gbs": alg_bytes(nnz_total, N, nzc_total / pr if world > 1 else tile.nzc, k, s_val, s_t) / (ms_step * 1e-3) / 1e9}
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(traffic_file):
         try:
@@ -284,23 +292,38 @@ def main():
         except Exception:
             pass
 
-    # e2e: host panels through the C ABI (single GPU: cb_spmm_host; pinned buffers), X up + Y down every step
-    e2e = None
-    if world == 1:
-        Xh = torch.empty((N, k), dtype=getattr(torch, {"f32": "float32", "f64": "float64", "i32": "int32", "i64": "int64", "u8": "uint8"}[w["xdt"]]), pin_memory=True)
-        Yh = torch.empty((N, k), dtype=Xh.dtype, pin_memory=True)
-        X.download(Xh.numpy())
-        ctx.spmm_host(tile, Xh.numpy(), sr, Yh.numpy())          # warm-up (allocates the workspace panels)
-        ctx.spmm_host(tile, Xh.numpy(), sr, Yh.numpy())
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+    # e2e: the multiply through the public host-panel path, every step: X panel copied up from pinned host memory,
+    # multiply, Y panel copied back.  1 GPU: cb_spmm_host.  N GPUs: each rank uploads its X tile, cb_spmm_summa, downloads
+    # its Y tile (what SpMM<SR>(A, X) of the C++ layer does); timed with a barrier on both sides, max over ranks.
+    tdt = getattr(torch, {"f32": "float32", "f64": "float64", "i32": "int32", "i64": "int64", "u8": "uint8"}[w["xdt"]])
+    xr, xc = (N, k) if world == 1 else (rl, kl)
+    Xh = torch.empty((xr, xc), dtype=tdt, pin_memory=True)
+    Yh = torch.empty((rl, xc), dtype=tdt, pin_memory=True)
+    X.download(Xh.numpy())
+
+    def e2e_step():
+        if world == 1:
             ctx.spmm_host(tile, Xh.numpy(), sr, Yh.numpy())
-        te = (time.perf_counter() - t0) / args.e2e_steps
-        e2e = {"value": flops / te / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(N * k * s_t), "d2h_bytes_per_step": int(N * k * s_t),
-               "ms_per_step": te * 1e3, "resident": "A tile (uploaded once, as SpParMat construction does)"}
-        checksum = float(np.asarray(Yh.numpy()[:1024], dtype=np.float64).sum())
-    else:
-        checksum = None
+        else:
+            X.upload(Xh.numpy())
+            ctx.spmm_summa(tile, X, Y, sr, N, N, k)
+            Y.download(Yh.numpy())
+
+    e2e_step()                                                   # warm-up (allocates the workspace panels)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    te = (time.perf_counter() - t0) / args.e2e_steps
+    if dist is not None:
+        tt = torch.tensor([te], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = tt.item()
+    e2e = {"value": flops / te / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(N * k * s_t), "d2h_bytes_per_step": int(N * k * s_t),
+           "ms_per_step": te * 1e3, "resident": "A (uploaded once, as SpParMat construction does); X and Y cross PCIe every step"}
+    checksum = float(np.asarray(Yh.numpy()[:1024], dtype=np.float64).sum())
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
