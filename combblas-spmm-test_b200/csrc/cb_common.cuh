@@ -10,6 +10,7 @@
 #include "combblas_b200.h"
 
 #define CB_WARP 32
+#define CB_MAX_SLABS 8
 
 struct cb_ctx {
     int device = 0;
@@ -34,6 +35,8 @@ struct cb_ctx {
     // device panels reused by cb_spmm_host (host operands): grown, never shrunk
     void* ws_x = nullptr; size_t ws_x_bytes = 0;
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
+    cudaStream_t h2d = nullptr, d2h = nullptr;               // column slabs of host panels flow up / down on these
+    cudaEvent_t slab_up[8] = {nullptr}, slab_done[8] = {nullptr}, host_begin = nullptr;
     float summa_ms[4] = {0, 0, 0, 0};
     void* summa_state = nullptr;      // receive buffers + events, owned by cb_summa.cu
     std::string err;

@@ -114,6 +114,12 @@ int cb_ctx_destroy(cb_ctx* c) {
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->ws_x);
     cudaFree(c->ws_y);
+    if (c->h2d) {
+        cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h);
+        cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h);
+        for (int i = 0; i < CB_MAX_SLABS; ++i) { cudaEventDestroy(c->slab_up[i]); cudaEventDestroy(c->slab_done[i]); }
+        cudaEventDestroy(c->host_begin);
+    }
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->compute) cudaStreamDestroy(c->compute);

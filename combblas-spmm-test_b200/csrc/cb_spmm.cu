@@ -1,4 +1,5 @@
 // cb_spmm_local / cb_spmm_host: validation, K3 (identity fill of empty rows) and dispatch into K2.
+#include <algorithm>
 #include "cb_spmm_dispatch.cuh"
 
 // K3: rows of the tile without nonzeros receive SR::id() - the dense-output convention of the reference's
@@ -115,7 +116,9 @@ static int ws_reserve(cb_ctx* ctx, void** p, size_t* have, size_t need) {
 
 int cb_spmm_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int64_t k,
                  int dtype, int semiring) {
-    // X up, multiply, Y down - all on the compute stream; the device panels are kept in the ctx between calls.
+    // Host panels in, host panel out.  The panel is cut into column slabs that flow through three streams - slab s+1 goes up
+    // (H2D) while slab s is multiplied and slab s-1 comes down (D2H) - so both PCIe directions and the kernel overlap;
+    // the device panels are kept in the ctx between calls.
     const size_t es = cb_dtype_size(dtype);
     if (!es || k <= 0 || ldx < k || ldy < k) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_host: bad dtype / k / leading dimension");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -123,10 +126,44 @@ int cb_spmm_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx,
     const int64_t ld = (k + per16 - 1) / per16 * per16;
     CB_TRY(ws_reserve(ctx, &ctx->ws_x, &ctx->ws_x_bytes, (size_t)(t->n > 0 ? t->n : 1) * (size_t)ld * es));
     CB_TRY(ws_reserve(ctx, &ctx->ws_y, &ctx->ws_y_bytes, (size_t)(t->m > 0 ? t->m : 1) * (size_t)ld * es));
+    if (!ctx->h2d) {
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < CB_MAX_SLABS; ++i) {
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slab_up[i], cudaEventDisableTiming));
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slab_done[i], cudaEventDisableTiming));
+        }
+        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->host_begin, cudaEventDisableTiming));
+    }
+    // slabs of whole 16-byte vectors, at least 256 bytes of every row per slab (measured: narrower 2D copies run PCIe
+    // at ~70% - 305 ms vs 257 ms per 17 GB round trip on C3)
+    static const int want = getenv("CB_HOST_SLABS") ? atoi(getenv("CB_HOST_SLABS")) : 4;
+    int nslab = 1;
+    if (ld == k) {
+        const int64_t min_cols = std::max<int64_t>(per16, 256 / (int64_t)es);
+        nslab = (int)std::min<int64_t>(std::min<int64_t>(want, CB_MAX_SLABS), std::max<int64_t>(1, k / min_cols));
+    }
+    const int64_t slab_cols = ((k + nslab - 1) / nslab + per16 - 1) / per16 * per16;
     if (ld != k) CB_CUDA(ctx, cudaMemsetAsync(ctx->ws_x, 0, (size_t)t->n * (size_t)ld * es, ctx->compute));
-    if (t->n) CB_CUDA(ctx, cudaMemcpy2DAsync(ctx->ws_x, (size_t)ld * es, X_host, (size_t)ldx * es, (size_t)k * es, (size_t)t->n, cudaMemcpyHostToDevice, ctx->compute));
-    CB_TRY(cb_spmm_launch(ctx, ctx->compute, t, ctx->ws_x, ld, ctx->ws_y, ld, k, dtype, semiring, 0));
-    if (t->m) CB_CUDA(ctx, cudaMemcpy2DAsync(Y_host, (size_t)ldy * es, ctx->ws_y, (size_t)ld * es, (size_t)k * es, (size_t)t->m, cudaMemcpyDeviceToHost, ctx->compute));
+    CB_CUDA(ctx, cudaEventRecord(ctx->host_begin, ctx->compute));       // earlier work on the panels has finished
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->host_begin, 0));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->host_begin, 0));
+    int used = 0;
+    for (int64_t c0 = 0; c0 < k; c0 += slab_cols, ++used) {
+        const int64_t cw = std::min(slab_cols, k - c0);
+        char* dx = (char*)ctx->ws_x + (size_t)c0 * es;
+        char* dy = (char*)ctx->ws_y + (size_t)c0 * es;
+        if (t->n) CB_CUDA(ctx, cudaMemcpy2DAsync(dx, (size_t)ld * es, (const char*)X_host + (size_t)c0 * es, (size_t)ldx * es, (size_t)cw * es,
+                                                 (size_t)t->n, cudaMemcpyHostToDevice, ctx->h2d));
+        CB_CUDA(ctx, cudaEventRecord(ctx->slab_up[used], ctx->h2d));
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->slab_up[used], 0));
+        CB_TRY(cb_spmm_launch(ctx, ctx->compute, t, dx, ld, dy, ld, cw, dtype, semiring, 0));
+        CB_CUDA(ctx, cudaEventRecord(ctx->slab_done[used], ctx->compute));
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->slab_done[used], 0));
+        if (t->m) CB_CUDA(ctx, cudaMemcpy2DAsync((char*)Y_host + (size_t)c0 * es, (size_t)ldy * es, dy, (size_t)ld * es, (size_t)cw * es,
+                                                 (size_t)t->m, cudaMemcpyDeviceToHost, ctx->d2h));
+    }
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return CB_OK;
 }

@@ -192,11 +192,16 @@ def test_tile_structure_round_trip(ctx):
         t.free()
 
 
-def test_host_panel_entry_point(ctx):
+@pytest.mark.parametrize("k,adt,xdt,sr,kind", [(48, np.float32, np.float32, 0, "value"), (100, np.float32, np.float32, 0, "value"),
+                                               (128, np.float32, np.float32, 0, "value"), (64, np.int64, np.int64, 1, "x_minplus"),
+                                               (7, None, np.int32, 2, "value"), (256, None, np.uint8, 3, "value")])
+def test_host_panel_entry_point(ctx, k, adt, xdt, sr, kind):
+    # host panels in / out; wide panels are pipelined as column slabs over three streams
     rng = np.random.default_rng(2)
-    I, J, V, X = random_case(rng, 500, 400, 5000, np.float32, np.float32, 48)
+    I, J, V, X = random_case(rng, 500, 400, 5000, adt, xdt, k, kind)
     t = ctx.tile_from_coo(500, 400, I, J, V)
-    check(ctx.spmm_host(t, X, cb.PLUS_TIMES), O.spmm(O.PLUS_TIMES, 500, 400, I, J, V, X))
+    for _ in range(2):
+        check(ctx.spmm_host(t, X, sr), O.spmm(sr, 500, 400, I, J, V, X))
     t.free()
 
 
