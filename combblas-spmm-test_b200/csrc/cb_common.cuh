@@ -37,7 +37,6 @@ struct cb_ctx {
     void* ws_y = nullptr; size_t ws_y_bytes = 0;
     cudaStream_t h2d = nullptr, d2h = nullptr;               // column slabs of host panels flow up / down on these
     cudaEvent_t slab_up[8] = {nullptr}, slab_done[8] = {nullptr}, host_begin = nullptr;
-    float summa_ms[4] = {0, 0, 0, 0};
     void* summa_state = nullptr;      // receive buffers + events, owned by cb_summa.cu
     std::string err;
 };

@@ -99,6 +99,7 @@ struct SummaState {
     cb_tile* view[2] = {nullptr, nullptr};
     cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, begin = nullptr, end = nullptr;
     std::vector<cudaEvent_t> comm_ev;  // begin/end pairs per stage on the communication stream
+    std::vector<char> comm_used;       // stage s used the communication stream in the last call
     // metas of every stage's A part as seen by this rank's row communicator, valid for `meta_tile`
     const cb_tile* meta_tile = nullptr;
     uint64_t meta_uid = 0;
@@ -339,6 +340,7 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         while ((int)S->comm_ev.size() < 2 * S->nstages) { cudaEvent_t e; CB_CUDA(ctx, cudaEventCreate(&e)); S->comm_ev.push_back(e); }
     }
     const int ns = S->nstages;
+    S->comm_used.assign(ns, 0);
     // ---- my parts of A: one column slice per stage this rank roots (cached on the tile)
     cb_tile* mt = const_cast<cb_tile*>(tile);
     const int64_t key[3] = {(int64_t)pr * 1000 + pc, gn, ns};
@@ -516,6 +518,7 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
                                   : (p2p ? cb_p2p_xfull(ctx) + (size_t)seg_a * (size_t)X->ld * es : S->slotX[slot]);
         if (bcast_a || bcast_x) {
             if (oi >= 2) CB_CUDA(ctx, cudaStreamWaitEvent(ctx->comm, S->done[slot], 0));     // slot free again
+            S->comm_used[s] = 1;
             CB_CUDA(ctx, cudaEventRecord(S->comm_ev[2 * s], ctx->comm));
             CB_NCCL(ctx, nccl().GroupStart());
             if (bcast_a) {
@@ -603,7 +606,7 @@ int cb_summa_times(cb_ctx* ctx, float ms[4]) {
     CB_CUDA(ctx, cudaEventElapsedTime(&ms[0], S->begin, S->end));
     for (int s = 0; s < S->nstages; ++s) {
         float t = 0;
-        if (cudaEventQuery(S->comm_ev[2 * s + 1]) == cudaSuccess &&
+        if (S->comm_used[s] && cudaEventQuery(S->comm_ev[2 * s + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&t, S->comm_ev[2 * s], S->comm_ev[2 * s + 1]) == cudaSuccess && t > 0) ms[1] += t;
     }
     cudaGetLastError();
