@@ -193,7 +193,6 @@ int cb_nccl_init(cb_ctx* ctx, const void* id128);
 void cb_nccl_destroy(cb_ctx* ctx);
 void cb_summa_release(cb_ctx* ctx);
 int cb_p2p_prepare(cb_ctx* ctx, size_t need_bytes);
-bool cb_p2p_active(cb_ctx* ctx);
 char* cb_p2p_xfull(cb_ctx* ctx);
 int cb_p2p_begin(cb_ctx* ctx);
 int cb_p2p_push(cb_ctx* ctx, cudaEvent_t operands_ready, int stage, size_t dst_off, const void* src, size_t bytes);

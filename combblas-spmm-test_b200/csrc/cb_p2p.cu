@@ -128,7 +128,6 @@ int cb_p2p_prepare(cb_ctx* ctx, size_t need) {
     return CB_OK;
 }
 
-bool cb_p2p_active(cb_ctx* ctx) { return get(ctx) && get(ctx)->mailbox_mapped; }
 char* cb_p2p_xfull(cb_ctx* ctx) { P2P* P = get(ctx); return P->xfull + (size_t)(P->epoch & 1u) * P->xfull_bytes; }
 
 int cb_p2p_begin(cb_ctx* ctx) {

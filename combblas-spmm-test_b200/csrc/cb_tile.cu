@@ -252,10 +252,6 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
 
 namespace {
 
-template <typename T> __global__ void widen_kernel(const T* in, int64_t n, int64_t* out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
-}
-
 __global__ void keys_to_csr_kernel(const int32_t* __restrict__ colflag, int64_t nz, int64_t* __restrict__ colidx) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nz; i += (int64_t)gridDim.x * blockDim.x) colidx[i] = colflag[i] & 0x7fffffff;
 }
