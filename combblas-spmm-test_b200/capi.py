@@ -32,7 +32,8 @@ class CBError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "lib", "libcombblas_b200.so")
+    # CB_LIB lets tuning experiments point at a variant build; the product path is lib/libcombblas_b200.so
+    return os.environ.get("CB_LIB") or os.path.join(HERE, "lib", "libcombblas_b200.so")
 
 
 def build_library(jobs: int = 8) -> str:

@@ -16,7 +16,7 @@ struct LaunchParams {
     int accumulate;
 };
 
-template <class Op, int VW, int R, int U>
+template <class Op, int VW, int R, int U, int MINB>
 static int launch_layout(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -41,7 +41,7 @@ static int launch_layout(const LaunchParams& p) {
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
-        cb_spmm_kernel<Op, VW, R, U><<<grid, 256, 0, p.stream>>>(a);
+        cb_spmm_kernel<Op, VW, R, U, MINB><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
     CB_CUDA(p.ctx, cudaGetLastError());
@@ -54,11 +54,14 @@ static int launch_op(const LaunchParams& p) {
     if (t->nnz > 0) {
         const int nvec = p.total_row_bytes / 16;
         int s;
-        if (nvec <= 4) s = launch_layout<Op, 4, 1, 4>(p);
-        else if (nvec <= 8) s = launch_layout<Op, 8, 1, 8>(p);
-        else if (nvec <= 16) s = launch_layout<Op, 16, 1, 8>(p);
-        else if (nvec <= 32) s = launch_layout<Op, 32, 1, 8>(p);
-        else s = launch_layout<Op, 32, 2, 4>(p);
+        // X rows this tile touches: mostly L2-resident (R-MAT scale <= 22 class) or streaming from DRAM?
+        static const int force = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;      // 0 deep, 1 wide (experiments)
+        const bool wide = force >= 0 ? force == 1 : (double)t->nzc * (double)p.total_row_bytes < 1.0e9;
+        if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
+        else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, 4, 4>(p) : launch_layout<Op, 8, 1, 8, 3>(p);
+        else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, 4, 4>(p) : launch_layout<Op, 16, 1, 8, 3>(p);
+        else if (nvec <= 32) s = launch_layout<Op, 32, 1, 8, 3>(p);
+        else s = launch_layout<Op, 32, 2, 4, 3>(p);
         if (s != CB_OK) return s;
         if (t->nsplit > 0) {
             FixupArgs f;

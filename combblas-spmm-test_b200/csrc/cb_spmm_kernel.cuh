@@ -29,6 +29,11 @@
 #pragma once
 #include "cb_common.cuh"
 
+// Tuning (profiles/r01_tuning.md).  Two operating points per layout:
+//   deep  : U=8 row gathers in flight per lane, 3 CTAs/SM (80 regs)  - best when the gathers mostly miss L2 (DRAM latency)
+//   wide  : U=4, 4 CTAs/SM (64 regs)                                 - best when the used X rows mostly sit in L2 (more warps)
+// launch_op picks by the footprint of the X rows the tile touches.
+
 namespace cbk {
 
 // ------------------------------------------------------------------------------ semiring functors
@@ -165,8 +170,8 @@ __device__ __forceinline__ void st16_stream(void* p, const Vec16<T>& v) {
     __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&v));
 }
 
-template <class Op, int VW, int R, int U>
-__global__ void __launch_bounds__(256, 3)
+template <class Op, int VW, int R, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 cb_spmm_kernel(const SpmmArgs a) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
