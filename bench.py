@@ -286,7 +286,7 @@ def main():
                 "gather_bytes_per_step_this_rank": nnz_rank * (4 + s_val) + nnz_rank * kl * s_t + tile.m * kl * s_t,
                 "whole_job_alg_gbs": alg_bytes(nnz_total, N, nzc_total / pr if world > 1 else tile.nzc, k, s_val, s_t) / (ms_step * 1e-3) / 1e9}
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
-    if os.path.exists(traffic_file):
+    if world == 1 and os.path.exists(traffic_file):       # the capture is of the single-GPU launch
         try:
             roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
         except Exception:

@@ -20,7 +20,7 @@ CODE_OF = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int
 SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_create", "cb_ctx_create_grid",
            "cb_ctx_destroy", "cb_ctx_grid", "cb_ctx_sync", "cb_ctx_stream", "cb_last_error", "cb_status_string",
            "cb_timer_start", "cb_timer_stop", "cb_tile_upload_csc", "cb_tile_upload_coo", "cb_tile_from_device_coo",
-           "cb_tile_free", "cb_tile_info", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
+           "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
 
@@ -77,6 +77,7 @@ def lib():
                                               POINTER(c_void_p)]
         L.cb_tile_free.argtypes = [c_void_p]
         L.cb_tile_info.argtypes = [c_void_p, POINTER(c_int64)]
+        L.cb_tile_pattern_view.argtypes = [c_void_p, POINTER(c_void_p)]
         L.cb_tile_download_csr.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
         L.cb_dense_alloc.argtypes = [c_void_p, c_int64, c_int64, c_int, POINTER(c_void_p)]
         L.cb_dense_wrap.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]
@@ -299,6 +300,11 @@ class Tile:
         if self.h:
             lib().cb_tile_free(self.h)
             self.h = c_void_p()
+
+    def pattern_view(self):
+        v = c_void_p()
+        _check(lib().cb_tile_pattern_view(self.h, byref(v)), self.ctx.h)
+        return Tile(self.ctx, v)
 
     def to_csr(self, val_dtype=None):
         rowptr = np.empty(self.m + 1, np.int64)

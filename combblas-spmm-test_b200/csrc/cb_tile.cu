@@ -360,6 +360,19 @@ int cb_tile_free(cb_tile* t) {
     return CB_OK;
 }
 
+int cb_tile_pattern_view(const cb_tile* t, cb_tile** view) {
+    cb_tile* v = new cb_tile();
+    v->ctx = t->ctx; v->uid = 0;
+    v->m = t->m; v->n = t->n; v->nnz = t->nnz; v->nzr = t->nzr; v->nzc = t->nzc;
+    v->val_dtype = CB_PATTERN;
+    v->slab = t->slab; v->slab_bytes = t->slab_bytes; v->owns_slab = false;
+    v->colflag = t->colflag; v->vals = nullptr; v->nzrows = t->nzrows; v->rowptr = t->rowptr; v->emptyrows = t->emptyrows;
+    v->nchunks = t->nchunks; v->chunk_len = t->chunk_len; v->chunk_start = t->chunk_start; v->chunk_row = t->chunk_row;
+    v->nsplit = t->nsplit; v->split_row = t->split_row;
+    *view = v;
+    return CB_OK;
+}
+
 int cb_tile_info(const cb_tile* t, int64_t info[8]) {
     info[0] = t->nnz; info[1] = t->m; info[2] = t->n; info[3] = t->nzr; info[4] = t->nzc;
     info[5] = t->nchunks; info[6] = t->nsplit; info[7] = (int64_t)t->slab_bytes;

@@ -3,6 +3,7 @@
 //
 //   spmm_driver mtx  <file.mtx> <k> [ydump.bin]          fp64 PlusTimes on a Matrix Market file (BASELINE config C1)
 //   spmm_driver rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]   Kronecker matrix generated on the GPU
+//   spmm_driver torus                                    the sparse x sparse program of Applications/SpMMError.cpp
 //
 // Single process, or one process per GPU under a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK
 // (python -m torch.distributed.run --no-python ./spmm_driver ...).  Verification replays the multiply with the
@@ -90,14 +91,91 @@ int RunRmat(int scale, int64_t k, int pr, int pc, double tol, bool values) {
 int main(int argc, char* argv[]) {
     MPI_Init(&argc, &argv);
     int rc = 0;
-    if (argc < 4) {
+    if (argc < 4 && !(argc >= 2 && std::string(argv[1]) == "torus")) {
         SpParHelper::Print("Usage: spmm_driver mtx <file.mtx> <k> [ydump.bin] | rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]\n");
         MPI_Finalize();
         return 2;
     }
     {
         const std::string mode = argv[1];
-        if (mode == "mtx") {
+        if (mode == "torus") {
+            // the program of Applications/SpMMError.cpp: G1, G2 from the built-in 16x16 torus arrays, G3 a copy,
+            // three sparse x sparse products through Mult_AnXBn_Synch; "The nnz values should be 112, 112, 112" (:80)
+            typedef SpDCCols<int64_t, int64_t> DCColsType;
+            typedef SpParMat<int64_t, int64_t, DCColsType> MatType;
+            const int64_t tj[64] = {3,0,1,2,7,4,5,6,11,8,9,10,15,12,13,14,1,2,3,0,5,6,7,4,9,10,11,8,13,14,15,12,
+                                    12,13,14,15,0,1,2,3,4,5,6,7,8,9,10,11,4,5,6,7,8,9,10,11,12,13,14,15,0,1,2,3};
+            std::vector<int64_t> ri(64), ci(tj, tj + 64), vv(64, 1);
+            for (int i = 0; i < 64; ++i) ri[i] = i % 16;
+            std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+            MatType G1(16, 16, ri, ci, vv, grid), G2(16, 16, ri, ci, vv, grid);
+            MatType G3(G1);
+            G1.PrintInfo(); G2.PrintInfo(); G3.PrintInfo();
+            SpParHelper::Print("The nnz values should be 112, 112, 112:\n");
+            MatType G12 = Mult_AnXBn_Synch<PlusTimesSRing<int64_t, int64_t>, int64_t, DCColsType>(G1, G2);
+            G12.PrintInfo();
+            MatType G13 = PSpGEMM<PlusTimesSRing<int64_t, int64_t>>(G1, G3);
+            G13.PrintInfo();
+            MatType G23 = Mult_AnXBn_Synch<PlusTimesSRing<int64_t, int64_t>, int64_t, DCColsType>(G2, G3);
+            G23.PrintInfo();
+            int64_t twos = 0, fours = 0;
+            for (int64_t v : G12.seq().numx) { twos += v == 2; fours += v == 4; }
+            twos = grid->SumWorld(twos); fours = grid->SumWorld(fours);
+            if (G12.getnnz() == 112 && G13 == G12 && G23 == G12 && twos == 96 && fours == 16) SpParHelper::Print("SpGEMM (sparse x sparse) working correctly\n");
+            else { SpParHelper::Print("ERROR in SpGEMM, go fix it!\n"); rc = 1; }
+        } else if (mode == "spgemm") {
+            // A (Kronecker, int64 weights) times a tall-skinny SPARSE B with ~d nonzeros per column, MinPlus semiring;
+            // verified entry by entry (structure and values) against a host replay with the semiring's own functors
+            typedef SpDCCols<int64_t, int64_t> DC;
+            typedef SpParMat<int64_t, int64_t, DC> Mat;
+            typedef MinPlusSRing<int64_t, int64_t> SRmp;
+            const int scale = std::atoi(argv[2]);
+            const int64_t k = std::atoll(argv[3]), d = argc > 4 ? std::atoll(argv[4]) : 3;
+            std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+            Mat A(grid);
+            A.GenGraph500(scale, 8, true, 0, true, 1);
+            const int64_t n = A.getncol();
+            std::vector<int64_t> bi, bj, bv;
+            for (int64_t j = 0; j < k; ++j)
+                for (int64_t e = 0; e < d; ++e) {
+                    const uint64_t h = splitmix64((uint64_t)(j * 131 + e) ^ 0xB5ULL);
+                    bi.push_back((int64_t)(h % (uint64_t)n)); bj.push_back(j); bv.push_back(1 + (int64_t)((h >> 40) % 50));
+                }
+            Mat B(n, k, bi, bj, bv, grid, true);
+            A.PrintInfo(); B.PrintInfo();
+            Mat C = Mult_AnXBn_Synch<SRmp, int64_t, DC>(A, B);
+            C.PrintInfo();
+            if (grid->GetSize() == 1) {
+                const DC &a = A.seq(), &b = B.seq(), &c = C.seq();
+                std::vector<int64_t> acc((size_t)n * (size_t)k, 0);
+                std::vector<char> hit((size_t)n * (size_t)k, 0);
+                std::vector<std::vector<std::pair<int64_t, int64_t>>> bcol((size_t)k);      // column j of B: (row, value)
+                for (size_t cc = 0; cc < b.jc.size(); ++cc)
+                    for (int64_t p = b.cp[cc]; p < b.cp[cc + 1]; ++p) bcol[(size_t)b.jc[cc]].push_back({b.ir[(size_t)p], b.numx[(size_t)p]});
+                std::vector<int64_t> acol_of((size_t)n, -1);
+                for (size_t cc = 0; cc < a.jc.size(); ++cc) acol_of[(size_t)a.jc[cc]] = (int64_t)cc;
+                for (int64_t j = 0; j < k; ++j)
+                    for (auto& e : bcol[(size_t)j]) {
+                        const int64_t cc = acol_of[(size_t)e.first];
+                        if (cc < 0) continue;
+                        for (int64_t p = a.cp[(size_t)cc]; p < a.cp[(size_t)cc + 1]; ++p) {
+                            const size_t q = (size_t)a.ir[(size_t)p] * (size_t)k + (size_t)j;
+                            const int64_t prod = SRmp::multiply(a.numx[(size_t)p], e.second);
+                            acc[q] = hit[q] ? SRmp::add(prod, acc[q]) : prod;
+                            hit[q] = 1;
+                        }
+                    }
+                int64_t want = 0, bad = 0;
+                for (char h : hit) want += h;
+                for (size_t cc = 0; cc < c.jc.size(); ++cc)
+                    for (int64_t p = c.cp[cc]; p < c.cp[cc + 1]; ++p) {
+                        const size_t q = (size_t)c.ir[(size_t)p] * (size_t)k + (size_t)c.jc[cc];
+                        if (!hit[q] || acc[q] != c.numx[(size_t)p]) ++bad;
+                    }
+                if (bad == 0 && want == c.getnnz()) SpParHelper::Print("SpGEMM (sparse x sparse) working correctly\n");
+                else { SpParHelper::Print("ERROR in SpGEMM, go fix it!\n"); rc = 1; }
+            }
+        } else if (mode == "mtx") {
             typedef SpParMat<int64_t, double, SpDCCols<int64_t, double>> PSpMat_Double;
             std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
             PSpMat_Double A(grid);

@@ -59,5 +59,93 @@ DenseParMat<IU, typename promote_trait<NUM, NUV>::T_promote> SpMM(const SpParMat
     return Y;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mult_AnXBn_Synch / PSpGEMM with a SPARSE tall-skinny right-hand side - the call Applications/SpMMError.cpp:83 and
+// ReleaseTests/MultTest.cpp:162 make (reference include/CombBLAS/ParFriends.h:1004-1108, SpParMat.h:454-467).
+// Lowered onto the dense engine: B's tiles are expanded into dense panels, the values come from SpMM under SR and the
+// nonzero STRUCTURE of C from a second SpMM of the two patterns under the boolean semiring, so C has an entry exactly
+// where the reference's sparse accumulator would create one (also when the folded value equals SR::id()).
+// Meant for tall-skinny B (the dense panels are m x k per block-row); cost is nnz(A)*k regardless of nnz(B).
+template <typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+bool CheckSpGEMMCompliance(const SpParMat<IU, NU1, UDERA>& A, const SpParMat<IU, NU2, UDERB>& B) {     // ParFriends.h:160-181
+    if (A.getncol() != B.getnrow()) {
+        std::ostringstream outs;
+        outs << "Can not multiply, dimensions does not match" << std::endl << A.getncol() << " != " << B.getnrow() << std::endl;
+        SpParHelper::Print(outs.str());
+        MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+        return false;
+    }
+    if ((void*)&A == (void*)&B) {
+        SpParHelper::Print("Can not multiply, inputs alias (make a temporary copy of one of them first)\n");
+        MPI_Abort(MPI_COMM_WORLD, MATRIXALIAS);
+        return false;
+    }
+    return true;
+}
+
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {
+    typedef typename promote_trait<NU1, NU2>::T_promote T_promote;
+    static_assert(semiring_traits<SR>::supported, "this semiring / type combination is not implemented by the B200 engine");
+    static_assert(std::is_same<T_promote, NUO>::value, "the output value type must be the promoted type of the operands");
+    typedef typename UDERB::LocalIT LIT;
+    if (!CheckSpGEMMCompliance(A, B)) return SpParMat<IU, NUO, UDERO>();
+    int stages, dummy;
+    std::shared_ptr<CommGrid> grid = ProductGrid(A.getcommgrid().get(), B.getcommgrid().get(), stages, dummy, dummy);
+    const IU gm = A.getnrow(), gn = A.getncol(), gk = B.getncol();
+    // dense images of my tile of B: values (promoted type) and structure
+    const UDERB& bt = B.seq();
+    const IU xl = bt.getnrow(), kl = bt.getncol(), lm = A.getlocalrows();
+    // absent entries of B hold SR::id(): it annihilates under every supported multiply (0*a, inf_plus(a, max), a AND false,
+    // select2nd -> id), so they cannot change a folded value; which entries of C exist is decided by the structure product
+    DenseParMat<IU, T_promote> Xv(SR::id(), grid, xl, kl);
+    DenseParMat<IU, bool> Xs(false, grid, xl, kl);
+    {
+        SpTuples<LIT, NU2> bt_tuples = TilesToTuples(bt);
+        for (int64_t p = 0; p < bt_tuples.getnnz(); ++p) {
+            Xv(bt_tuples.rowindex(p), bt_tuples.colindex(p)) = (typename cb_storage<T_promote>::type)bt_tuples.numvalue(p);
+            Xs(bt_tuples.rowindex(p), bt_tuples.colindex(p)) = 1;
+        }
+    }
+    cb_ctx* ctx = grid->GetContext();
+    cb_dense *dX = nullptr, *dY = nullptr, *dS = nullptr, *dM = nullptr;
+    const int dt = cb_dtype_of<T_promote>::value;
+    cb_check(cb_dense_alloc(ctx, xl, kl, dt, &dX), ctx, "cb_dense_alloc");
+    cb_check(cb_dense_alloc(ctx, lm, kl, dt, &dY), ctx, "cb_dense_alloc");
+    cb_check(cb_dense_alloc(ctx, xl, kl, CB_U8, &dS), ctx, "cb_dense_alloc");
+    cb_check(cb_dense_alloc(ctx, lm, kl, CB_U8, &dM), ctx, "cb_dense_alloc");
+    std::vector<typename cb_storage<T_promote>::type> Y((size_t)lm * (size_t)kl);
+    std::vector<uint8_t> M((size_t)lm * (size_t)kl);
+    if (kl > 0) {
+        cb_check(cb_dense_upload(dX, Xv.data(), kl), ctx, "cb_dense_upload");
+        cb_check(cb_dense_upload(dS, Xs.data(), kl), ctx, "cb_dense_upload");
+    }
+    cb_check(cb_spmm_summa(ctx, A.DeviceTile(), dX, dY, semiring_traits<SR>::op, gm, gn, gk), ctx, "cb_spmm_summa");
+    cb_check(cb_spmm_summa(ctx, A.DevicePatternTile(), dS, dM, CB_OR_AND, gm, gn, gk), ctx, "cb_spmm_summa (structure)");
+    if (kl > 0) {
+        cb_check(cb_dense_download(dY, Y.data(), kl), ctx, "cb_dense_download");
+        cb_check(cb_dense_download(dM, M.data(), kl), ctx, "cb_dense_download");
+    }
+    cb_check(cb_ctx_sync(ctx), ctx, "cb_ctx_sync");
+    cb_dense_free(dX); cb_dense_free(dY); cb_dense_free(dS); cb_dense_free(dM);
+    // C tile: one entry per structural hit, column-major like every SpTuples the reference's local multiply returns
+    typedef typename UDERO::LocalIT OIT;
+    SpTuples<OIT, NUO> ct(0, (OIT)lm, (OIT)kl);
+    for (IU j = 0; j < kl; ++j)
+        for (IU i = 0; i < lm; ++i)
+            if (M[(size_t)i * (size_t)kl + (size_t)j]) ct.tuples.emplace_back((OIT)i, (OIT)j, (NUO)Y[(size_t)i * (size_t)kl + (size_t)j]);
+    if (clearA) A.FreeDeviceTile();
+    if (clearB) B.FreeDeviceTile();
+    return SpParMat<IU, NUO, UDERO>(new UDERO(ct, false), grid, gm, gk);
+}
+
+template <typename SR, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, typename promote_trait<NU1, NU2>::T_promote, typename create_trait<UDERA, typename UDERA::LocalIT, typename promote_trait<NU1, NU2>::T_promote>::T_inferred>
+PSpGEMM(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {        // SpParMat.h:454-467
+    typedef typename promote_trait<NU1, NU2>::T_promote N_promote;
+    typedef typename create_trait<UDERA, typename UDERA::LocalIT, N_promote>::T_inferred DER_promote;
+    return Mult_AnXBn_Synch<SR, N_promote, DER_promote>(A, B, clearA, clearB);
+}
+
 }  // namespace combblas
 #endif

@@ -37,6 +37,7 @@ public:
     SpParMat() : commGrid(new CommGrid(MPI_COMM_WORLD, 0, 0)), spSeq(new DER()) {}
     explicit SpParMat(std::shared_ptr<CommGrid> grid) : commGrid(grid), spSeq(new DER()) {}
     SpParMat(DER* myseq, std::shared_ptr<CommGrid> grid) : commGrid(grid), spSeq(myseq) {}
+    SpParMat(DER* myseq, std::shared_ptr<CommGrid> grid, IT total_m, IT total_n) : commGrid(grid), spSeq(myseq), gm(total_m), gn(total_n) {}
     // "matlab sparse" form (SpParMat.cpp:3066-3099) on replicated global triples
     SpParMat(IT total_m, IT total_n, const std::vector<IT>& rows, const std::vector<IT>& cols, const std::vector<NT>& vals,
              std::shared_ptr<CommGrid> grid, bool SumDuplicates = false)
@@ -49,8 +50,9 @@ public:
         return *this;
     }
     SpParMat(SpParMat&& rhs) noexcept
-        : commGrid(rhs.commGrid), spSeq(rhs.spSeq), gm(rhs.gm), gn(rhs.gn), dtile(rhs.dtile), dnnz(rhs.dnnz), devvals(rhs.devvals) {
-        rhs.spSeq = nullptr; rhs.dtile = nullptr;
+        : commGrid(rhs.commGrid), spSeq(rhs.spSeq), gm(rhs.gm), gn(rhs.gn), dtile(rhs.dtile), dpattern(rhs.dpattern), dnnz(rhs.dnnz),
+          devvals(rhs.devvals) {
+        rhs.spSeq = nullptr; rhs.dtile = nullptr; rhs.dpattern = nullptr;
     }
     ~SpParMat() { Release(); }
 
@@ -164,7 +166,16 @@ public:
         }
         return self->dtile;
     }
-    void FreeDeviceTile() { if (dtile) { cb_tile_free(dtile); dtile = nullptr; } }
+    // the same tile without its values (structure only), for structural products under the boolean semiring
+    cb_tile* DevicePatternTile() const {
+        SpParMat* self = const_cast<SpParMat*>(this);
+        if (!self->dpattern) cb_check(cb_tile_pattern_view(DeviceTile(), &self->dpattern), commGrid->GetContext(), "cb_tile_pattern_view");
+        return self->dpattern;
+    }
+    void FreeDeviceTile() {
+        if (dpattern) { cb_tile_free(dpattern); dpattern = nullptr; }
+        if (dtile) { cb_tile_free(dtile); dtile = nullptr; }
+    }
 
 private:
     template <typename BinOp = maximum<NT>>
@@ -231,6 +242,7 @@ private:
     DER* spSeq;
     IT gm = -1, gn = -1;            // global dimensions when known without communication
     cb_tile* dtile = nullptr;
+    cb_tile* dpattern = nullptr;
     int64_t dnnz = 0;
     bool devvals = false;
 };

@@ -214,5 +214,28 @@ private:
     IT m, n;
 };
 
+// tile -> tuples (what SpDCCols::operator SpTuples does in the reference)
+template <class IT, class NT>
+SpTuples<IT, NT> TilesToTuples(const SpDCCols<IT, NT>& t) {
+    SpTuples<IT, NT> out(0, t.getnrow(), t.getncol());
+    out.tuples.reserve((size_t)t.getnnz());
+    for (size_t c = 0; c < t.jc.size(); ++c)
+        for (IT p = t.cp[c]; p < t.cp[c + 1]; ++p) out.tuples.emplace_back(t.ir[(size_t)p], t.jc[c], (NT)t.numx[(size_t)p]);
+    return out;
+}
+template <class IT, class NT>
+SpTuples<IT, NT> TilesToTuples(const SpCCols<IT, NT>& t) {
+    SpTuples<IT, NT> out(0, t.getnrow(), t.getncol());
+    out.tuples.reserve((size_t)t.getnnz());
+    for (IT c = 0; c < t.getncol(); ++c)
+        for (IT p = t.jc[(size_t)c]; p < t.jc[(size_t)c + 1]; ++p) out.tuples.emplace_back(t.ir[(size_t)p], c, (NT)t.num[(size_t)p]);
+    return out;
+}
+
+// infer the tile type of a result from the tile type of an operand (SpDCCols.h:454-475 of the reference)
+template <class DER, class NIT, class NNT> struct create_trait {};
+template <class NIT, class NNT, class OIT, class ONT> struct create_trait<SpDCCols<OIT, ONT>, NIT, NNT> { typedef SpDCCols<NIT, NNT> T_inferred; };
+template <class NIT, class NNT, class OIT, class ONT> struct create_trait<SpCCols<OIT, ONT>, NIT, NNT> { typedef SpCCols<NIT, NNT> T_inferred; };
+
 }  // namespace combblas
 #endif

@@ -105,6 +105,10 @@ int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const
 int cb_tile_free(cb_tile* tile);
 /* {nnz, m, n, nonempty rows, nonempty columns, work chunks, split rows, bytes resident} */
 int cb_tile_info(const cb_tile* tile, int64_t info[8]);
+/* a second handle onto the same device arrays that ignores the values: the structure of the tile as a CB_PATTERN
+ * matrix (used to compute the nonzero structure of a product with the boolean semiring).  The view borrows the
+ * original's memory: free it before the original; freeing the view does not free the arrays. */
+int cb_tile_pattern_view(const cb_tile* tile, cb_tile** view);
 /* copy the device tile back as CSR (rowptr[m+1], colidx[nnz], vals) for inspection/tests; any pointer may be NULL */
 int cb_tile_download_csr(cb_tile* tile, int64_t* rowptr, int64_t* colidx, void* vals);
 

@@ -64,6 +64,36 @@ def test_driver_generated_matrix_every_semiring(what):
 
 
 @pytest.mark.gpu
+def test_driver_spmmerror_program_sparse_times_sparse():
+    # Applications/SpMMError.cpp: three products of 16x16 torus matrices, "The nnz values should be 112, 112, 112" (:80)
+    build()
+    r = subprocess.run([DRIVER, "torus"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("112 nonzeros") == 3 and r.stdout.count("64 nonzeros") == 3
+    assert "SpGEMM (sparse x sparse) working correctly" in r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_sparse_rhs_min_plus_structure_and_values():
+    build()
+    r = subprocess.run([DRIVER, "spgemm", "11", "40", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SpGEMM (sparse x sparse) working correctly" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_spmmerror_program_on_a_2x2_grid():
+    import torch
+    from tests.test_summa_cpu import free_port
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    build()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), DRIVER, "torus"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("112 nonzeros") == 3 and "working correctly" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_driver_multi_process_grid():
     import torch
     from tests.test_summa_cpu import free_port
