@@ -191,7 +191,6 @@ cb_spmm_kernel(const SpmmArgs a) {
     bool lane_on[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) lane_on[r] = (vl + r * VW) * 16 < slab_row_bytes;
-    const bool all_on = lane_on[R - 1];               // lanes are switched on in order
     const char* const xbase = a.X + slab_off + vl * 16;
     const uint32_t ldx = (uint32_t)a.ldx_bytes;
 
@@ -267,7 +266,9 @@ cb_spmm_kernel(const SpmmArgs a) {
         // end-of-row flags of this virtual warp's VW entries, one bit each
         const uint32_t fm = (__ballot_sync(0xffffffffu, cf < 0) >> vshift) & (VW == 32 ? 0xffffffffu : ((1u << VW) - 1u));
         const uint32_t cm = (uint32_t)cf & 0x7fffffffu;
-        const bool fullwarp = __all_sync(0xffffffffu, rem >= VW) && all_on;   // warp-uniform: no predicates needed
+        // warp-uniform (every lane takes the same side of the branches below, so the shuffles inside them stay convergent):
+        // all virtual warps of this warp still own a full block, hence no bounds predicates on the entries
+        const bool fullwarp = __all_sync(0xffffffffu, rem >= VW);
 #pragma unroll
         for (int j0 = 0; j0 < VW; j0 += U) {
             RowFrag<Op, R> x[U];
@@ -278,7 +279,8 @@ cb_spmm_kernel(const SpmmArgs a) {
                     const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
                     const char* xr = xbase + (uint64_t)c * ldx;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                    for (int r = 0; r < R; ++r)
+                        if (lane_on[r]) x[u].v[r] = ldg16<T>(xr + r * VW * 16);      // lane-constant predicate (panel narrower than VW*R vectors)
                 }
             } else {
 #pragma unroll
