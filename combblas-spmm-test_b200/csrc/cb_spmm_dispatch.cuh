@@ -2,6 +2,21 @@
 #pragma once
 #include "cb_spmm_kernel.cuh"
 
+#ifndef CB_WIDE_U
+#define CB_WIDE_U 4
+#define CB_WIDE_B 5
+#endif
+#ifndef CB_WIDE_B64
+#define CB_WIDE_B64 4
+#endif
+#ifndef CB_DEEP_B64
+#define CB_DEEP_B64 3
+#endif
+#ifndef CB_DEEP_U
+#define CB_DEEP_U 8
+#define CB_DEEP_B 4
+#endif
+
 namespace cbk {
 
 struct LaunchParams {
@@ -16,8 +31,8 @@ struct LaunchParams {
     int accumulate;
 };
 
-template <class Op, int VW, int R, int U, int MINB>
-static int launch_layout(const LaunchParams& p) {
+template <class Op, int VW, int R, int U, int MINB, bool FULL>
+static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
     a.colflag = t->colflag;
@@ -41,11 +56,18 @@ static int launch_layout(const LaunchParams& p) {
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
-        cb_spmm_kernel<Op, VW, R, U, MINB><<<grid, 256, 0, p.stream>>>(a);
+        cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
     CB_CUDA(p.ctx, cudaGetLastError());
     return CB_OK;
+}
+
+// rows that fill the layout exactly (k*sizeof(T) == VW*R*16, the power-of-two panels) take the predicate-free kernel
+template <class Op, int VW, int R, int U, int MINB>
+static int launch_layout(const LaunchParams& p) {
+    if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true>(p);
+    return launch_layout_f<Op, VW, R, U, MINB, false>(p);
 }
 
 template <class Op>
@@ -56,12 +78,15 @@ static int launch_op(const LaunchParams& p) {
         int s;
         // X rows this tile touches: mostly L2-resident (R-MAT scale <= 22 class) or streaming from DRAM?
         static const int force = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;      // 0 deep, 1 wide (experiments)
-        const bool wide = force >= 0 ? force == 1 : (double)t->nzc * (double)p.total_row_bytes < 1.0e9;
+        const bool wide = force >= 0 ? force == 1 : (nvec <= 16 && (double)t->nzc * (double)p.total_row_bytes < 1.0e9);
+        // 64-bit element types need more registers per gathered vector's arithmetic: one CTA per SM fewer
+        constexpr int WB = sizeof(typename Op::T) == 8 ? CB_WIDE_B64 : CB_WIDE_B;
+        constexpr int DB = sizeof(typename Op::T) == 8 ? CB_DEEP_B64 : CB_DEEP_B;
         if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
-        else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, 4, 4>(p) : launch_layout<Op, 8, 1, 8, 3>(p);
-        else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, 4, 4>(p) : launch_layout<Op, 16, 1, 8, 3>(p);
-        else if (nvec <= 32) s = launch_layout<Op, 32, 1, 8, 3>(p);
-        else s = launch_layout<Op, 32, 2, 4, 3>(p);
+        else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 8, 1, CB_DEEP_U, DB>(p);
+        else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 16, 1, CB_DEEP_U, DB>(p);
+        else if (nvec <= 32) s = wide ? launch_layout<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 32, 1, CB_DEEP_U, DB>(p);
+        else s = launch_layout<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
         if (s != CB_OK) return s;
         if (t->nsplit > 0) {
             FixupArgs f;

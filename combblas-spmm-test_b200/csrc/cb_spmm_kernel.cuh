@@ -30,8 +30,8 @@
 #include "cb_common.cuh"
 
 // Tuning (profiles/r01_tuning.md).  Two operating points per layout:
-//   deep  : U=8 row gathers in flight per lane, 3 CTAs/SM (80 regs)  - best when the gathers mostly miss L2 (DRAM latency)
-//   wide  : U=4, 4 CTAs/SM (64 regs)                                 - best when the used X rows mostly sit in L2 (more warps)
+//   deep  : U=8 row gathers in flight per lane, 4 CTAs/SM (64 regs)  - best when the gathers mostly miss L2 (DRAM latency)
+//   wide  : U=4, 5 CTAs/SM (48 regs)                                 - best when the used X rows mostly sit in L2 (more warps)
 // launch_op picks by the footprint of the X rows the tile touches.
 
 namespace cbk {
@@ -170,7 +170,8 @@ __device__ __forceinline__ void st16_stream(void* p, const Vec16<T>& v) {
     __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&v));
 }
 
-template <class Op, int VW, int R, int U, int MINB>
+// FULL: the panel row is exactly VW*R vectors wide (every lane owns real columns) - no lane predicates are generated
+template <class Op, int VW, int R, int U, int MINB, bool FULL>
 __global__ void __launch_bounds__(256, MINB)
 cb_spmm_kernel(const SpmmArgs a) {
     typedef typename Op::T T;
@@ -190,7 +191,7 @@ cb_spmm_kernel(const SpmmArgs a) {
     const int slab_row_bytes = min(a.row_bytes, a.total_row_bytes - slab_off);
     bool lane_on[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) lane_on[r] = (vl + r * VW) * 16 < slab_row_bytes;
+    for (int r = 0; r < R; ++r) lane_on[r] = FULL || (vl + r * VW) * 16 < slab_row_bytes;
     const char* const xbase = a.X + slab_off + vl * 16;
     const uint32_t ldx = (uint32_t)a.ldx_bytes;
 

@@ -1,7 +1,9 @@
 #!/bin/bash
-# K2 tuning sweep over variant builds (lib_var/), 1 GPU
-for L in "" $(ls combblas-spmm-test_b200/lib_var/*.so); do
-  echo "== ${L:-default}"
-  CB_LIB=$L python tools/kbench.py c2 c5 s24f32 --steps 5 | cut -c1-200
-  CB_LIB=$L python tools/kbench.py c3 --steps 5 --k 32 | cut -c1-200
+# K2 tuning sweep over variant builds x forced operating point, 1 GPU.  usage: tools/tune.sh "<workloads>" [lib ...]
+W=${1:-"c2 c5 c3 s24f32"}; shift
+for L in "" "$@"; do
+  for P in 0 1; do
+    echo "== ${L:-default} point=$P (0 deep, 1 wide)"
+    CB_K2_POINT=$P CB_LIB=$L python tools/kbench.py $W --steps 5 | cut -c1-200
+  done
 done
