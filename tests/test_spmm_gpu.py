@@ -205,6 +205,26 @@ def test_host_panel_entry_point(ctx, k, adt, xdt, sr, kind):
     t.free()
 
 
+def test_wrapping_foreign_device_memory(ctx):
+    # panels that live in someone else's allocation (here: torch tensors) are used in place through cb_dense_wrap
+    import torch
+    rng = np.random.default_rng(6)
+    I, J, V, X = random_case(rng, 300, 260, 4000, np.float64, np.float64, 32)
+    t = ctx.tile_from_coo(300, 260, I, J, V)
+    Xt = torch.from_numpy(X).cuda()
+    Yt = torch.empty((300, 32), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    Xw, Yw = ctx.wrap(Xt.data_ptr(), 260, 32, 32, np.float64), ctx.wrap(Yt.data_ptr(), 300, 32, 32, np.float64)
+    ctx.spmm_local(t, Xw, Yw, cb.PLUS_TIMES)
+    ctx.sync()
+    check(Yt.cpu().numpy(), O.spmm(O.PLUS_TIMES, 300, 260, I, J, V, X))
+    with pytest.raises(cb.CBError) as e:                            # rows must start on 16-byte boundaries
+        ctx.spmm_local(t, ctx.wrap(Xt.data_ptr() + 8, 260, 31, 32, np.float64), Yw, cb.PLUS_TIMES)
+    assert e.value.status in (3002, 3007)
+    for h in (t, Xw, Yw):
+        h.free()
+
+
 def test_error_codes_follow_the_reference(ctx):
     t = ctx.tile_from_coo(4, 5, [0], [1], np.ones(1, np.float32))
     X, Xbad, Y = ctx.dense(5, 3, np.float32), ctx.dense(6, 3, np.float32), ctx.dense(4, 3, np.float32)
