@@ -46,12 +46,14 @@ struct cb_ctx {
 struct cb_tile_meta {
     int64_t m, n, nnz, nzr, nzc, nchunks, nsplit;
     int32_t chunk_len, val_dtype;
+    int32_t layout_dtype;     // value type the slab was laid out for (differs from val_dtype for a pattern view)
+    int32_t reserved;
 };
 struct cb_tile_layout { size_t colflag, vals, nzrows, rowptr, emptyrows, chunk_start, chunk_row, split_row, total; };
 static inline cb_tile_layout cb_layout(const cb_tile_meta& t) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t vs = 0;
-    switch (t.val_dtype) { case CB_F32: case CB_I32: vs = 4; break; case CB_F64: case CB_I64: vs = 8; break; case CB_U8: vs = 1; break; default: vs = 0; }
+    switch (t.layout_dtype) { case CB_F32: case CB_I32: vs = 4; break; case CB_F64: case CB_I64: vs = 8; break; case CB_U8: vs = 1; break; default: vs = 0; }
     cb_tile_layout L;
     size_t o = 0;
     L.colflag = o;     o = up(o + (size_t)t.nnz * 4);
@@ -74,6 +76,7 @@ struct cb_tile {
     int64_t nzr = 0;          // rows with at least one nonzero
     int64_t nzc = 0;          // columns with at least one nonzero (n_used of the traffic model)
     int val_dtype = CB_PATTERN;
+    int layout_dtype = CB_PATTERN;   // value type the slab is laid out for (== val_dtype except for pattern views)
     char* slab = nullptr;     // the one allocation holding every array below (cb_tile_layout)
     size_t slab_bytes = 0;
     bool owns_slab = false;
@@ -111,13 +114,13 @@ static inline cb_tile_meta cb_tile_get_meta(const cb_tile* t) {
     cb_tile_meta m;
     memset(&m, 0, sizeof m);
     m.m = t->m; m.n = t->n; m.nnz = t->nnz; m.nzr = t->nzr; m.nzc = t->nzc; m.nchunks = t->nchunks; m.nsplit = t->nsplit;
-    m.chunk_len = t->chunk_len; m.val_dtype = t->val_dtype;
+    m.chunk_len = t->chunk_len; m.val_dtype = t->val_dtype; m.layout_dtype = t->layout_dtype;
     return m;
 }
 static inline void cb_tile_bind(cb_tile* t, const cb_tile_meta& m, char* slab) {
     const cb_tile_layout L = cb_layout(m);
     t->m = m.m; t->n = m.n; t->nnz = m.nnz; t->nzr = m.nzr; t->nzc = m.nzc; t->nchunks = m.nchunks; t->nsplit = m.nsplit;
-    t->chunk_len = m.chunk_len; t->val_dtype = m.val_dtype;
+    t->chunk_len = m.chunk_len; t->val_dtype = m.val_dtype; t->layout_dtype = m.layout_dtype;
     t->slab = slab;
     t->colflag = (int32_t*)(slab + L.colflag);
     t->vals = (m.val_dtype == CB_PATTERN || m.nnz == 0) ? nullptr : (void*)(slab + L.vals);

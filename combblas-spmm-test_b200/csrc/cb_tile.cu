@@ -144,7 +144,7 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
     *out = nullptr;
     cb_tile_meta meta;
     memset(&meta, 0, sizeof meta);
-    meta.m = m; meta.n = n; meta.nnz = nz; meta.val_dtype = val_dtype; meta.chunk_len = 32;
+    meta.m = m; meta.n = n; meta.nnz = nz; meta.val_dtype = val_dtype; meta.layout_dtype = val_dtype; meta.chunk_len = 32;
     auto fail = [&](int s) { cb_tile_free(t); return s; };
 #define T_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cb_fail(ctx, e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return fail(e__ == cudaErrorMemoryAllocation ? CB_ERR_ALLOC : CB_ERR_CUDA); } } while (0)
     const size_t vs = cb_dtype_size(val_dtype);
@@ -365,6 +365,7 @@ int cb_tile_pattern_view(const cb_tile* t, cb_tile** view) {
     v->ctx = t->ctx; v->uid = 0;
     v->m = t->m; v->n = t->n; v->nnz = t->nnz; v->nzr = t->nzr; v->nzc = t->nzc;
     v->val_dtype = CB_PATTERN;
+    v->layout_dtype = t->layout_dtype;          // the shared slab keeps its value array; the view just does not look at it
     v->slab = t->slab; v->slab_bytes = t->slab_bytes; v->owns_slab = false;
     v->colflag = t->colflag; v->vals = nullptr; v->nzrows = t->nzrows; v->rowptr = t->rowptr; v->emptyrows = t->emptyrows;
     v->nchunks = t->nchunks; v->chunk_len = t->chunk_len; v->chunk_start = t->chunk_start; v->chunk_row = t->chunk_row;
