@@ -57,10 +57,13 @@ public:
     ~SpParMat() { Release(); }
 
     // ---- construction helpers
-    template <typename BinOp = maximum<NT>>
-    void ParallelReadMM(const std::string& filename, bool onebased, BinOp binop = BinOp()) {
+    // Matrix Market coordinate file -> 0-based triples, with the transpose of every off-diagonal entry added for
+    // symmetric files and value 1 for pattern files (ProcessLines / push_to_vectors, SpHelper.h:75-91,147-183).
+    // Pure host code, no grid needed.  Returns false if the file cannot be opened.
+    static bool ReadMMTriples(const std::string& filename, bool onebased, IT& tm, IT& tn, std::vector<IT>& rows,
+                              std::vector<IT>& cols, std::vector<NT>& vals) {
         std::ifstream in(filename);
-        if (!in) { SpParHelper::Print("COMBBLAS: Matrix-market file " + filename + " can not be found\n"); MPI_Abort(MPI_COMM_WORLD, NOFILE); }
+        if (!in) return false;
         std::string line;
         std::getline(in, line);
         std::string banner = line;
@@ -69,10 +72,9 @@ public:
         const bool pattern = hasbanner && banner.find("pattern") != std::string::npos;
         const bool symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
         if (hasbanner) do { std::getline(in, line); } while (!line.empty() && line[0] == '%');
-        long long tm, tn, tnz;
-        std::istringstream(line) >> tm >> tn >> tnz;
-        std::vector<IT> rows, cols;
-        std::vector<NT> vals;
+        long long m_ = 0, n_ = 0, nz_ = 0;
+        std::istringstream(line) >> m_ >> n_ >> nz_;
+        tm = (IT)m_; tn = (IT)n_;
         long long ii, jj;
         double vv = 1;
         while (std::getline(in, line)) {
@@ -84,7 +86,18 @@ public:
             rows.push_back((IT)ii); cols.push_back((IT)jj); vals.push_back((NT)vv);
             if (symmetric && ii != jj) { rows.push_back((IT)jj); cols.push_back((IT)ii); vals.push_back((NT)vv); }   // SpHelper.h:85-90
         }
-        FromGlobalTriples((IT)tm, (IT)tn, rows, cols, vals, true, binop);
+        return true;
+    }
+    template <typename BinOp = maximum<NT>>
+    void ParallelReadMM(const std::string& filename, bool onebased, BinOp binop = BinOp()) {
+        IT tm = 0, tn = 0;
+        std::vector<IT> rows, cols;
+        std::vector<NT> vals;
+        if (!ReadMMTriples(filename, onebased, tm, tn, rows, cols, vals)) {
+            SpParHelper::Print("COMBBLAS: Matrix-market file " + filename + " can not be found\n");
+            MPI_Abort(MPI_COMM_WORLD, NOFILE);
+        }
+        FromGlobalTriples(tm, tn, rows, cols, vals, true, binop);
     }
 
     // Graph500-style Kronecker matrix generated on the device (GenWriteMatrix.cpp:96-131 recipe).  The local tile never
@@ -147,6 +160,16 @@ public:
     void GetPlaceInGlobalGrid(IT& rowOffset, IT& colOffset) const {
         rowOffset = commGrid->GetRankInProcCol() * (getnrow() / commGrid->GetGridRows());
         colOffset = commGrid->GetRankInProcRow() * (getncol() / commGrid->GetGridCols());
+    }
+    // the same rule as Owner() for an explicit grid shape (usable without a CommGrid)
+    template <typename LIT>
+    static int OwnerOnGrid(int procrows, int proccols, IT total_m, IT total_n, IT grow, IT gcol, LIT& lrow, LIT& lcol) {
+        const IT m_perproc = total_m / procrows, n_perproc = total_n / proccols;
+        const int own_procrow = m_perproc ? std::min((int)(grow / m_perproc), procrows - 1) : procrows - 1;
+        const int own_proccol = n_perproc ? std::min((int)(gcol / n_perproc), proccols - 1) : proccols - 1;
+        lrow = (LIT)(grow - own_procrow * m_perproc);
+        lcol = (LIT)(gcol - own_proccol * n_perproc);
+        return own_procrow * proccols + own_proccol;
     }
     static void BlockRange(IT total, int nb, int b, IT& start, IT& len) {
         const IT per = total / nb;
