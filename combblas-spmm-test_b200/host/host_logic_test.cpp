@@ -1,5 +1,5 @@
 // CPU-only exercise of the host layer's containers and arithmetic (no CommGrid, no GPU).  Prints one line per check in a
-// "key value..." format that tests/test_host_logic_cpu.py compares with the numpy restatements in oracle/oracle.py.
+// "key value..." format that tests/test_host_logic_cpu.py compares with independent numpy restatements.
 //   host_logic_test tile <m> <n> <triples.txt>   -> DCSC and CSC arrays of the triples
 //   host_logic_test mm <file.mtx>                -> triples after Matrix Market expansion
 //   host_logic_test semirings                    -> functor tables
