@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--k", type=int, default=13)
     ap.add_argument("--cases", default="minplus_i32,pt_f64")
     ap.add_argument("--ragged", type=int, default=1, help="drop trailing rows/cols so nothing divides evenly")
+    ap.add_argument("--no-cache-a", action="store_true", help="re-broadcast the A parts on every multiply (reference behaviour)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -68,6 +69,8 @@ def main():
         holder = [cb.capi.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(holder, src=0)
         ctx = cb.Context(local, rank, world, pr, pc, holder[0])
+        if a.no_cache_a:
+            ctx.summa_cache_a(False)
     failures = 0
     for case in a.cases.split(","):
         sr, adt, xdt, kind = CASES[case]

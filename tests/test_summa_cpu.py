@@ -21,10 +21,10 @@ def free_port():
         return s.getsockname()[1]
 
 
-def torchrun(n, args, timeout=600):
+def torchrun(n, args, timeout=600, extra_env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(ROOT, "tests", "summa_worker.py")] + args
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", **(extra_env or {}))
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 

@@ -21,6 +21,23 @@ def test_summa_2gpu(pr, pc):
     assert r.returncode == 0 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("variant", ["nccl_transport", "no_cache", "nccl_no_cache", "no_merge"])
+@pytest.mark.parametrize("pr,pc", [(1, 2), (2, 1)])
+def test_summa_2gpu_alternate_paths(pr, pc, variant):
+    # the NCCL broadcast transport, the reference-style re-broadcast of A on every call, and the unfused stage loop
+    need(2)
+    env = {}
+    if "nccl" in variant:
+        env["CB_SUMMA_TRANSPORT"] = "nccl"
+    if variant == "no_merge":
+        env["CB_SUMMA_MERGE"] = "0"
+    args = ["--mode", "gpu", "--pr", str(pr), "--pc", str(pc), "--cases", "minplus_i32,pt_f64,or_and", "--scale", "11", "--k", "24"]
+    if "no_cache" in variant:
+        args.append("--no-cache-a")
+    r = torchrun(2, args, extra_env=env)
+    assert r.returncode == 0 and r.stdout.count(": ok") == 3, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("pr,pc", [(2, 2), (1, 4), (4, 1)])
 def test_summa_4gpu(pr, pc):
     need(4)
