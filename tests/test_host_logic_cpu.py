@@ -106,3 +106,24 @@ def test_owner_rule_matches_oracle(args):
     out = run("owner", *args)
     assert tuple(ints(out["owner"]).tolist()) == O.owner(m, n, pr, pc, r, c)
     assert tuple(ints(out["lastblock"]).tolist()) == O.block_range(m, pr, pr - 1)
+
+
+def test_unsupported_semiring_is_a_compile_time_error(tmp_path):
+    # no CPU fallback by design: a semiring outside the ABI must not compile (static_assert in SpMM<SR>)
+    src = tmp_path / "bad.cpp"
+    src.write_text('#include "CombBLAS/CombBLAS.h"\n'
+                   "using namespace combblas;\n"
+                   "template <class T1, class T2> struct MaxTimesSRing { typedef T2 T_promote; static T2 id() { return 0; } };\n"
+                   "int main() {\n"
+                   "  std::shared_ptr<CommGrid> g;\n"
+                   "  SpParMat<int64_t, double, SpDCCols<int64_t, double>> A(g);\n"
+                   "  DenseParMat<int64_t, double> X(0.0, g, 1, 1);\n"
+                   "  auto Y = SpMM<MaxTimesSRing<double, double>>(A, X);\n"
+                   "  return 0;\n}\n")
+    inc = [f"-I{os.path.join(ROOT, 'combblas-spmm-test_b200', 'include')}", f"-I{os.path.join(ROOT, 'include')}"]
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only"] + inc + [str(src)], capture_output=True, text=True)
+    assert r.returncode != 0 and "not implemented by the B200 SpMM" in r.stderr
+    ok = tmp_path / "ok.cpp"
+    ok.write_text(src.read_text().replace("MaxTimesSRing<double, double>>(A, X)", "MinPlusSRing<double, double>>(A, X)"))
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-Wno-int-in-bool-context"] + inc + [str(ok)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
