@@ -1,0 +1,147 @@
+// Runs the product's K2 (cb_spmm_kernel), fix-up and K3 row fill - compiled UNMODIFIED from csrc/cb_spmm_kernel.cuh - on the
+// lock-step warp emulator, on small random tiles with hub rows, empty rows, ragged panel widths, column slabs and the
+// accumulate mode; compares with a scalar loop over the same semiring functors.  Built with -fsanitize=address,undefined:
+// every device buffer is an exactly-sized heap vector, so an out-of-bounds access of the kernel is an ASan report.
+#include "cuda_emul.h"
+#include <cstdio>
+#include <random>
+#include "cb_spmm_kernel.cuh"
+
+using namespace cbk;
+
+struct HostTile {                       // host restatement of the tile layout (csrc/cb_tile.cu), for the emulator only
+    int64_t m, n, nnz, nzr, nchunks, nsplit;
+    int32_t L;
+    std::vector<int32_t> colflag, nzrows, rowptr, emptyrows, chunk_start, chunk_row, split_row;
+};
+
+static HostTile build(int64_t m, int64_t n, const std::vector<std::vector<int32_t>>& rows, int32_t L) {
+    HostTile t{};
+    t.m = m; t.n = n; t.L = L;
+    for (int64_t r = 0; r < m; ++r) {
+        if (rows[r].empty()) { t.emptyrows.push_back((int32_t)r); continue; }
+        t.nzrows.push_back((int32_t)r);
+        t.rowptr.push_back((int32_t)t.colflag.size());
+        for (size_t q = 0; q < rows[r].size(); ++q)
+            t.colflag.push_back((int32_t)((uint32_t)rows[r][q] | (q + 1 == rows[r].size() ? 0x80000000u : 0u)));
+    }
+    t.nnz = (int64_t)t.colflag.size();
+    t.rowptr.push_back((int32_t)t.nnz);
+    t.nzr = (int64_t)t.nzrows.size();
+    t.nchunks = (t.nnz + L - 1) / L;
+    for (int64_t g = 0; g < t.nchunks; ++g) {                       // chunk_kernel of cb_tile.cu
+        const int64_t pos = g * L;
+        int64_t lo = 0, hi = t.nzr;
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (t.rowptr[mid] <= pos) lo = mid; else hi = mid; }
+        const int32_t rs = t.rowptr[lo], re = t.rowptr[lo + 1];
+        if (re - rs > L) { t.chunk_start.push_back((int32_t)pos); t.chunk_row.push_back((int32_t)((uint32_t)lo | (pos > rs ? 0x80000000u : 0u))); }
+        else { t.chunk_start.push_back(rs); t.chunk_row.push_back((int32_t)lo); }
+    }
+    t.chunk_start.push_back((int32_t)t.nnz);
+    for (int64_t i = 0; i < t.nzr; ++i) if (t.rowptr[i + 1] - t.rowptr[i] > L) t.split_row.push_back((int32_t)i);
+    t.nsplit = (int64_t)t.split_row.size();
+    return t;
+}
+
+template <class T> static T rnd_val(std::mt19937& g) { return (T)(1 + g() % 9); }
+template <> float rnd_val<float>(std::mt19937& g) { return (float)(1 + g() % 64) / 8.0f; }
+template <> double rnd_val<double>(std::mt19937& g) { return (double)(1 + g() % 1024) / 32.0; }
+
+// one multiply on the emulator; returns the number of mismatching elements
+template <class Op, int VW, int R, int U, bool FULL>
+static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elements of Op::T per panel row */, int32_t L, int hub, unsigned seed,
+                     bool accumulate) {
+    typedef typename Op::T T;
+    typedef typename Op::TA TA;
+    std::mt19937 g(seed);
+    std::vector<std::vector<int32_t>> rows((size_t)m);
+    for (int64_t r = 0; r < m; ++r) {
+        int deg = (r % 5 == 3) ? 0 : (int)(g() % 7);                // empty rows and short rows
+        if (r == 2 || r == m - 1) deg = hub;                         // hub rows: split over several chunks, last row too
+        if (r == 7) deg = L;                                         // exactly one chunk long
+        if (r == 9) deg = L + 1;                                     // one more than a chunk
+        std::vector<char> used((size_t)n, 0);
+        for (int q = 0; q < deg && q < n; ++q) { int c; do { c = (int)(g() % n); } while (used[c]); used[c] = 1; }
+        for (int c = 0; c < n; ++c) if (used[c]) rows[r].push_back(c);
+    }
+    HostTile t = build(m, n, rows, L);
+    std::vector<TA> vals((size_t)t.nnz);
+    for (auto& v : vals) v = Op::akind == A_BOOL ? (TA)(g() % 4 != 0) : rnd_val<TA>(g);
+    const int row_bytes = (int)((k_elems * sizeof(T) + 15) / 16 * 16);
+    const int ld_elems = row_bytes / (int)sizeof(T);
+    std::vector<T> X((size_t)n * ld_elems), Y((size_t)m * ld_elems), Yref((size_t)m * ld_elems);
+    for (auto& x : X) x = rnd_val<T>(g);
+    for (auto& y : Y) y = rnd_val<T>(g);                            // stale content: must be overwritten or folded in
+    // scalar reference with the same functors
+    for (int64_t r = 0; r < m; ++r)
+        for (int c = 0; c < ld_elems; ++c) {
+            bool first = true;
+            T acc = Op::id();
+            int64_t i = std::lower_bound(t.nzrows.begin(), t.nzrows.end(), (int32_t)r) - t.nzrows.begin();
+            if (i < t.nzr && t.nzrows[i] == r)
+                for (int32_t p = t.rowptr[i]; p < t.rowptr[i + 1]; ++p) {
+                    const T prod = Op::mul(Op::akind != A_PATTERN ? vals[p] : TA(), X[(size_t)(t.colflag[p] & 0x7fffffff) * ld_elems + c]);
+                    acc = (Op::first_touch && first) ? prod : Op::add(prod, acc);
+                    first = false;
+                }
+            T& out = Yref[(size_t)r * ld_elems + c];
+            if (accumulate) out = first ? Y[(size_t)r * ld_elems + c] : Op::add(Y[(size_t)r * ld_elems + c], acc);
+            else out = acc;
+        }
+    // K3: identity into the rows K2 will not write
+    if (!accumulate)
+        for (int32_t r : t.emptyrows) for (int c = 0; c < ld_elems; ++c) Y[(size_t)r * ld_elems + c] = Op::id();
+    std::vector<char> carry((size_t)2 * t.nchunks * row_bytes);
+    SpmmArgs a{};
+    a.colflag = t.colflag.data(); a.vals = vals.data(); a.nzrows = t.nzrows.data();
+    a.chunk_start = t.chunk_start.data(); a.chunk_row = t.chunk_row.data(); a.nchunks = t.nchunks;
+    a.X = (const char*)X.data(); a.Y = (char*)Y.data();
+    a.ldx_bytes = row_bytes; a.ldy_bytes = row_bytes;
+    a.slab_bytes = VW * R * 16; a.row_bytes = a.slab_bytes; a.total_row_bytes = row_bytes;
+    a.carry = carry.data(); a.carry_stride = row_bytes; a.accumulate = accumulate ? 1 : 0;
+    constexpr int NV = 32 / VW;
+    dim3 grid((unsigned)((t.nchunks + 8 * NV - 1) / (8 * NV)), (unsigned)((row_bytes + a.slab_bytes - 1) / a.slab_bytes));
+    const long long syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
+    if (t.nsplit) {
+        FixupArgs f{};
+        f.split_row = t.split_row.data(); f.nsplit = t.nsplit; f.nzrows = t.nzrows.data(); f.rowptr = t.rowptr.data();
+        f.chunk_len = t.L; f.carry = carry.data(); f.carry_stride = row_bytes; f.Y = (char*)Y.data(); f.ldy_bytes = row_bytes;
+        f.total_row_bytes = row_bytes; f.accumulate = accumulate ? 1 : 0;
+        emul::launch(dim3((unsigned)((t.nsplit + 7) / 8)), dim3(256), [&] { cb_fixup_kernel<Op>(f); });
+    }
+    long bad = 0;
+    for (size_t q = 0; q < Y.size(); ++q) {
+        const double x = (double)Y[q], y = (double)Yref[q];
+        if (std::is_floating_point<T>::value ? std::abs(x - y) > 1e-5 * std::max(1.0, std::abs(y)) : Y[q] != Yref[q]) ++bad;
+    }
+    std::printf("%-28s m=%lld nnz=%lld chunks=%lld split=%lld slabs=%u warps=%u syncs=%lld mismatches=%ld\n", name, (long long)m, (long long)t.nnz,
+                (long long)t.nchunks, (long long)t.nsplit, grid.y, grid.x * 8, syncs, bad);
+    return bad;
+}
+
+int main(int argc, char** argv) {
+    long bad = 0;
+    const int rounds = argc > 1 ? std::atoi(argv[1]) : 1;
+    for (int it = 0; it < rounds; ++it) {
+    const unsigned sd = 100u * (unsigned)it;
+    // k=64 fp32: half-warp layout, exact fill (FULL); wide and deep operating points
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pt_f32 VW16 U4 full", 61, 97, 64, 32, 150, 1 + sd, false);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("pt_f32 VW16 U8 accumulate", 61, 97, 64, 32, 150, 2 + sd, true);
+    // ragged width: 25 vectors in a 32-lane layout (FULL = false), and a panel wider than one slab
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, false>("pt_f32 VW32 k=100", 40, 200, 100, 32, 90, 3 + sd, false);
+    bad += run_case<PlusTimes<float, A_PATTERN>, 32, 1, 8, false>("pt_f32 pattern 3 slabs", 33, 60, 300, 32, 55, 4 + sd, false);
+    // fp64 with two vectors per lane (k=128 doubles = 1 KB rows)
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, true>("pt_f64 VW32 R2", 30, 80, 128, 32, 70, 5 + sd, false);
+    bad += run_case<PlusTimes<double, A_BOOL>, 32, 2, 4, false>("pt_f64 boolA R2 ragged acc", 30, 80, 100, 32, 70, 6 + sd, true);
+    // integer semirings: quarter-warps, first-touch select, packed booleans
+    bad += run_case<MinPlus<int32_t>, 8, 1, 4, true>("minplus_i32 VW8", 70, 64, 32, 32, 60, 7 + sd, false);
+    bad += run_case<SelectMax<int64_t>, 8, 1, 8, false>("selectmax_i64 VW8 k=13", 45, 50, 13, 32, 45, 8 + sd, false);
+    bad += run_case<OrAnd<A_PATTERN>, 4, 1, 4, false>("or_and VW4 k=32 bytes", 50, 40, 8, 32, 38, 9 + sd, false);      // 8 uint32 = 32 bool columns
+    bad += run_case<OrAnd<A_BOOL>, 4, 1, 4, true>("or_and boolA VW4 acc", 50, 40, 16, 32, 38, 10 + sd, true);
+    // a larger tile: several blocks, chunk length 64, hub rows of ~11 chunks
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pt_f32 VW16 larger", 400, 900, 64, 64, 700, 11 + sd, false);
+    bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("minplus_i64 VW16 larger acc", 300, 500, 32, 64, 400, 12 + sd, true);
+    }
+    std::printf(bad ? "EMULATION FAILED\n" : "emulation ok\n");
+    return bad ? 1 : 0;
+}
