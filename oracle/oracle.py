@@ -231,6 +231,59 @@ def ref_spmm(semiring, m, n, I, J, V, X, via=0, panel=0, threads=None):
     return Y, sec.value
 
 
+def ref_grid_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "cbref_grid"))
+
+
+def _run_grid(args, ranks, threads=1, timeout=900):
+    env = dict(os.environ, CBMPI_NP=str(ranks), OMP_NUM_THREADS=str(threads), CBMPI_TIMEOUT=str(timeout))
+    r = subprocess.run([os.path.join(HERE, "_ref", "cbref_grid")] + args, env=env, capture_output=True, text=True, timeout=timeout + 30)
+    if r.returncode:
+        raise RuntimeError(f"cbref_grid {args} on {ranks} ranks: rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return r.stdout
+
+
+def ref_grid_torus(ranks):
+    """The SpMMError.cpp program run by the unmodified reference on sqrt(ranks) x sqrt(ranks) processes; returns its report line."""
+    return [l for l in _run_grid(["torus"], ranks).splitlines() if l.startswith("torus")][0]
+
+
+def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1):
+    """The unmodified reference on a sqrt(ranks) x sqrt(ranks) process grid (oracle/_ref/cbref_grid: one process per rank over
+    the shared-memory MPI stand-in).  via: 0 Mult_AnXBn_Synch, 1 k x SpMV, 2 _DoubleBuff, 3 _Overlap.
+    Returns (Y, seconds, stdout)."""
+    import tempfile
+    X = np.ascontiguousarray(X)
+    Xb = X.view(np.uint8) if X.dtype == np.bool_ else X
+    xd = CODE_OF[Xb.dtype]
+    if V is None:
+        ad, Vb = PATTERN, None
+    else:
+        Vb = np.ascontiguousarray(V)
+        Vb = Vb.view(np.uint8) if Vb.dtype == np.bool_ else Vb
+        ad = CODE_OF[Vb.dtype]
+    k = Xb.shape[1]
+    with tempfile.TemporaryDirectory(prefix="cbref_grid_") as d:
+        with open(os.path.join(d, "meta.txt"), "w") as f:
+            f.write(f"{m} {n} {len(I)} {k} {0 if Vb is None else 1}\n")
+        np.ascontiguousarray(I, np.int64).tofile(os.path.join(d, "I.bin"))
+        np.ascontiguousarray(J, np.int64).tofile(os.path.join(d, "J.bin"))
+        if Vb is not None:
+            Vb.tofile(os.path.join(d, "V.bin"))
+        Xb.tofile(os.path.join(d, "X.bin"))
+        out = _run_grid(["spmm", ref_key(semiring, ad, xd), str(via), d], ranks, threads)
+        Y = np.empty((m, k), Xb.dtype)
+        seen = np.zeros((m, k), bool)
+        for r in range(ranks):
+            raw = np.fromfile(os.path.join(d, f"Y_{r}.bin"), np.uint8)
+            r0, c0, rows, cols = (int(v) for v in raw[:32].view(np.int64))
+            Y[r0:r0 + rows, c0:c0 + cols] = raw[32:].view(Xb.dtype).reshape(rows, cols)
+            seen[r0:r0 + rows, c0:c0 + cols] = True
+        assert seen.all(), "cbref_grid: the ranks' blocks do not tile Y"
+    sec = float([l for l in out.splitlines() if l.startswith("multiply seconds")][0].split()[2])
+    return Y, sec, out
+
+
 def ref_read_mm(path):
     R = ref()
     m, n, nnz = c_int64(), c_int64(), c_int64()

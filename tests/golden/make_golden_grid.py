@@ -1,0 +1,66 @@
+"""Generates tests/golden/grid_ref.npz by RUNNING THE UNMODIFIED REFERENCE ON A PROCESS GRID (oracle/_ref/cbref_grid:
+/root/reference compiled against the process-per-rank MPI stand-in oracle/mpi_multi; `make -C oracle ref`).
+Run in the build container only:
+
+    python tests/golden/make_golden_grid.py
+
+Contents (results of the reference's own multi-process multiply, stored instead of recomputed):
+  torus_4 / torus_9 / torus_16   the report line of the SpMMError.cpp program on 2x2, 3x3, 4x4 processes
+  <case>_p4 / <case>_p9          Y of Mult_AnXBn_Synch on 2x2 / 3x3 processes for the operands of tests/summa_worker.py
+                                 (R-MAT scale 9, edge factor 8, seed 3, ragged m = n-5, n = n-3, k = 13)
+  <case>_p4_spmv                 the same product through k x SpMV<SR>(A, FullyDistVec) on 2x2 processes
+Only numeric outputs are stored; inputs are regenerated from the counter-based generators at test time.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+SCALE, K = 9, 13
+CASES = {  # the cases of tests/summa_worker.py
+    "minplus_i32": (O.MIN_PLUS, np.int32, np.int32, "x_minplus"),
+    "pt_f64": (O.PLUS_TIMES, np.float64, np.float64, "value"),
+    "pt_f32": (O.PLUS_TIMES, np.float32, np.float32, "value"),
+    "pt_pat_i64": (O.PLUS_TIMES, None, np.int64, "value"),
+    "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"),
+    "or_and": (O.OR_AND, None, np.uint8, "value"),
+}
+
+
+def operands(case, scale=SCALE, k=K):
+    """(semiring, m, n, I, J, V, X) exactly as tests/summa_worker.py builds them with --ragged 1."""
+    sr, adt, xdt, kind = CASES[case]
+    n, I, J = O.rmat_matrix(scale, 8, seed=3)
+    m, n = n - 5, n - 3
+    keep = (I < m) & (J < n)
+    I, J = I[keep], J[keep]
+    V = None if adt is None else O.matrix_values(I, J, n, 7, adt)
+    X = O.dense_operand(n, k, 9, xdt, kind)
+    return sr, m, n, I, J, V, X
+
+
+def main():
+    if not O.ref_grid_available():
+        raise SystemExit("oracle/_ref/cbref_grid missing: run `make -C oracle ref` first")
+    out = {}
+    for p in (4, 9, 16):
+        out[f"torus_{p}"] = np.array(O.ref_grid_torus(p))
+    for case in CASES:
+        sr, m, n, I, J, V, X = operands(case)
+        for p in (4, 9):
+            Y, _, log = O.ref_grid_spmm(sr, p, m, n, I, J, V, X, via=0)
+            assert "agrees with the reference constructor" in log
+            out[f"{case}_p{p}"] = Y
+        if X.dtype != np.uint8:
+            out[f"{case}_p4_spmv"] = O.ref_grid_spmm(sr, 4, m, n, I, J, V, X, via=1)[0]
+    np.savez_compressed(os.path.join(OUT, "grid_ref.npz"), **out)
+    print("wrote grid_ref.npz:", ", ".join(sorted(out)))
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--k", type=int, default=13)
     ap.add_argument("--cases", default="minplus_i32,pt_f64")
     ap.add_argument("--ragged", type=int, default=1, help="drop trailing rows/cols so nothing divides evenly")
+    ap.add_argument("--golden", default="", help="npz of the reference's own multi-process results (tests/golden/grid_ref.npz): "
+                    "also compare the gathered Y with the entry <case>_p<world>")
     ap.add_argument("--no-cache-a", action="store_true", help="re-broadcast the A parts on every multiply (reference behaviour)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -125,6 +127,15 @@ def main():
                 ok = bool((np.abs(Y - ref) <= tol * np.maximum(np.abs(ref), 1e-300)).all())
             else:
                 ok = bool(np.array_equal(Y, ref))
+            if a.golden:
+                # the unmodified reference run on pr x pc processes (tests/golden/make_golden_grid.py)
+                gold = np.load(a.golden)[f"{case}_p{world}"]
+                if np.issubdtype(ref.dtype, np.floating):
+                    gok = bool((np.abs(Y - gold) <= tol * np.maximum(np.abs(gold.astype(np.float64)), 1e-300)).all())
+                else:
+                    gok = bool(np.array_equal(Y, gold))
+                print(f"[summa {a.mode} {pr}x{pc}] {case} vs reference on {world} processes: {'same' if gok else 'DIFFERENT'}", flush=True)
+                ok = ok and gok
             print(f"[summa {a.mode} {pr}x{pc}] {case}: {'ok' if ok else 'MISMATCH'}", flush=True)
             failures += 0 if ok else 1
     flag = torch.tensor([failures], device=f"cuda:{local}" if a.mode == "gpu" else "cpu")

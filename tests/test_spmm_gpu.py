@@ -59,6 +59,17 @@ def test_torus_known_answer(ctx):
     assert np.array_equal(Y, g["Ydense"]) and (Y != 0).sum() == 112
 
 
+@pytest.mark.parametrize("case", ["minplus_i32", "pt_f64", "pt_f32", "pt_pat_i64", "selmax_i32", "or_and"])
+def test_matches_reference_run_on_process_grids(ctx, case):
+    # tests/golden/grid_ref.npz: the unmodified reference's own 2x2- and 3x3-process multiplies
+    from tests.golden.make_golden_grid import operands
+    g = np.load(os.path.join(G, "grid_ref.npz"))
+    sr, m, n, I, J, V, X = operands(case)
+    Y = gpu_spmm(ctx, m, n, I, J, V, X, sr)
+    for p in (4, 9):
+        check(Y, g[f"{case}_p{p}"])
+
+
 @pytest.mark.parametrize("how", ["coo", "dcsc", "csc"])
 def test_hepth_config_c1(ctx, how):
     g = np.load(os.path.join(G, "hepth.npz"))

@@ -45,6 +45,17 @@ def test_summa_4gpu(pr, pc):
     assert r.returncode == 0 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_summa_2x2_matches_reference_run_on_2x2_processes():
+    # the product on a 2x2 GPU grid against the stored results of the unmodified reference on a 2x2 PROCESS grid
+    # (tests/golden/grid_ref.npz, made by oracle/_ref/cbref_grid): same distribution, same stages
+    need(4)
+    import os
+    from tests.golden.make_golden_grid import K, SCALE
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid_ref.npz")
+    r = torchrun(4, ["--mode", "gpu", "--pr", "2", "--pc", "2", "--cases", ALL, "--scale", str(SCALE), "--k", str(K), "--golden", gold])
+    assert r.returncode == 0 and r.stdout.count("processes: same") == 6 and r.stdout.count(": ok") == 6, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("pr,pc", [(2, 4), (4, 2)])
 def test_summa_8gpu(pr, pc):
     need(8)
