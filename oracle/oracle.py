@@ -235,8 +235,8 @@ def ref_grid_available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "cbref_grid"))
 
 
-def _run_grid(args, ranks, threads=1, timeout=900):
-    env = dict(os.environ, CBMPI_NP=str(ranks), OMP_NUM_THREADS=str(threads), CBMPI_TIMEOUT=str(timeout))
+def _run_grid(args, ranks, threads=1, timeout=900, extra_env=None):
+    env = dict(os.environ, CBMPI_NP=str(ranks), OMP_NUM_THREADS=str(threads), CBMPI_TIMEOUT=str(timeout), **(extra_env or {}))
     r = subprocess.run([os.path.join(HERE, "_ref", "cbref_grid")] + args, env=env, capture_output=True, text=True, timeout=timeout + 30)
     if r.returncode:
         raise RuntimeError(f"cbref_grid {args} on {ranks} ranks: rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
@@ -248,7 +248,7 @@ def ref_grid_torus(ranks):
     return [l for l in _run_grid(["torus"], ranks).splitlines() if l.startswith("torus")][0]
 
 
-def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1):
+def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_distribution=True):
     """The unmodified reference on a sqrt(ranks) x sqrt(ranks) process grid (oracle/_ref/cbref_grid: one process per rank over
     the shared-memory MPI stand-in).  via: 0 Mult_AnXBn_Synch, 1 k x SpMV, 2 _DoubleBuff, 3 _Overlap.
     Returns (Y, seconds, stdout)."""
@@ -271,7 +271,8 @@ def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1):
         if Vb is not None:
             Vb.tofile(os.path.join(d, "V.bin"))
         Xb.tofile(os.path.join(d, "X.bin"))
-        out = _run_grid(["spmm", ref_key(semiring, ad, xd), str(via), d], ranks, threads)
+        out = _run_grid(["spmm", ref_key(semiring, ad, xd), str(via), d], ranks, threads,
+                        extra_env=None if check_distribution else {"CBREF_SKIP_DISTCHECK": "1"})
         Y = np.empty((m, k), Xb.dtype)
         seen = np.zeros((m, k), bool)
         for r in range(ranks):
@@ -282,6 +283,24 @@ def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1):
         assert seen.all(), "cbref_grid: the ranks' blocks do not tile Y"
     sec = float([l for l in out.splitlines() if l.startswith("multiply seconds")][0].split()[2])
     return Y, sec, out
+
+
+def ref_best_time(semiring, m, n, I, J, V, X, cores, reps=1):
+    """Seconds of the fastest configuration of the unmodified reference on `cores` host cores: 1 process x cores OpenMP
+    threads (libcbref.so) or a 2x2 process grid x cores/4 threads (cbref_grid) - its MPI+OpenMP design is faster with
+    processes.  Returns (seconds, description); used by bench.py's cpu_baseline / --impl reference legs only."""
+    best = None
+    for _ in range(max(1, reps)):
+        _, sec = ref_spmm(semiring, m, n, I, J, V, X, via=0, threads=cores)
+        if best is None or sec < best[0]:
+            best = (sec, f"1 process x {cores} OpenMP threads")
+    if ref_grid_available() and cores >= 4:
+        th = max(1, cores // 4)
+        for _ in range(max(1, reps)):
+            _, sec, _ = ref_grid_spmm(semiring, 4, m, n, I, J, V, X, via=0, threads=th, check_distribution=False)
+            if sec < best[0]:
+                best = (sec, f"2x2 processes x {th} OpenMP threads")
+    return best
 
 
 def ref_read_mm(path):
