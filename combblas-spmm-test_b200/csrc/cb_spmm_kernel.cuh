@@ -170,20 +170,45 @@ __device__ __forceinline__ void st16_stream(void* p, const Vec16<T>& v) {
     __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&v));
 }
 
-// FULL: the panel row is exactly VW*R vectors wide (every lane owns real columns) - no lane predicates are generated
-template <class Op, int VW, int R, int U, int MINB, bool FULL>
-__global__ void __launch_bounds__(256, MINB)
-cb_spmm_kernel(const SpmmArgs a) {
+#ifndef CB_CLUSTER_INTRINSICS     // the CPU warp emulator (tests/emul) supplies host versions of these
+// 16 bytes from shared memory of CTA `cta` of this cluster (distributed shared memory); addr is a shared-window address
+__device__ __forceinline__ uint4 cb_ld_cluster16(uint32_t addr, uint32_t cta) {
+    uint32_t remote;
+    uint4 u;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(remote));
+    return u;
+}
+#endif
+
+// Hub-row source of the hub variant (cb_spmm_hub_kernel.cuh); the plain kernel passes an empty one and compiles none of it.
+struct HubSrc {
+    const uint16_t* __restrict__ hubslot;   // per nonzero: rank of its column among the tile's hub columns, 0xffff = not a hub
+    int nhub;                               // ranks < nhub are resident in (distributed) shared memory
+    uint32_t smem;                          // shared-window address of this CTA's slot 0, plus this lane's vector offset
+    uint32_t slot_bytes;                    // bytes between slots
+    uint32_t cta_mask, cta_shift;           // rank -> (CTA of the cluster, local slot): rank & mask, rank >> shift
+};
+
+template <typename T>
+__device__ __forceinline__ Vec16<T> ld_hub16(const HubSrc& hub, uint32_t rank, int byte_off) {
+    Vec16<T> r;
+    *reinterpret_cast<uint4*>(&r) = cb_ld_cluster16(hub.smem + (rank >> hub.cta_shift) * hub.slot_bytes + (uint32_t)byte_off, rank & hub.cta_mask);
+    return r;
+}
+
+// One virtual warp walks chunk `chunk` of the tile front to back (all virtual warps of the hardware warp in lock step).
+// FULL: the panel row is exactly VW*R vectors wide (every lane owns real columns) - no lane predicates are generated.
+// HUB : rows of hub columns come from shared memory of the cluster instead of global memory.
+template <class Op, int VW, int R, int U, bool FULL, bool HUB>
+__device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t chunk, const HubSrc& hub) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     constexpr int EPL = 16 / sizeof(T);
-    constexpr int NV = 32 / VW;                       // virtual warps per warp
     constexpr bool HASVAL = Op::akind != A_PATTERN;
     const int lane = threadIdx.x & 31;
     const int vl = lane & (VW - 1);
     const int vshift = lane & ~(VW - 1);              // first lane of this virtual warp
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t chunk = warp * NV + (lane / VW);
     const bool live = chunk < a.nchunks;
 
     // this slab's columns
@@ -260,9 +285,11 @@ cb_spmm_kernel(const SpmmArgs a) {
         const int rem = e - (s + base);                 // nonzeros this virtual warp still owns (may be <= 0)
         int cf = 0;
         TA av = TA();
+        int hs = 0xffff;
         if (vl < rem) {
             cf = ld_stream(a.colflag + s + base + vl);
             if (HASVAL) av = ld_stream_val<TA>(vals + s + base + vl);
+            if (HUB) hs = (int)__ldcs(hub.hubslot + s + base + vl);
         }
         // end-of-row flags of this virtual warp's VW entries, one bit each
         const uint32_t fm = (__ballot_sync(0xffffffffu, cf < 0) >> vshift) & (VW == 32 ? 0xffffffffu : ((1u << VW) - 1u));
@@ -279,18 +306,26 @@ cb_spmm_kernel(const SpmmArgs a) {
                 for (int u = 0; u < U; ++u) {
                     const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
                     const char* xr = xbase + (uint64_t)c * ldx;
+                    const int h = HUB ? __shfl_sync(0xffffffffu, hs, j0 + u, VW) : 0xffff;
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        if (lane_on[r]) x[u].v[r] = ldg16<T>(xr + r * VW * 16);      // lane-constant predicate (panel narrower than VW*R vectors)
+                        if (lane_on[r]) {                                            // lane-constant predicate (panel narrower than VW*R vectors)
+                            if (HUB && h < hub.nhub) x[u].v[r] = ld_hub16<T>(hub, (uint32_t)h, r * VW * 16);
+                            else x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                        }
                 }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
                     const char* xr = xbase + (uint64_t)c * ldx;
+                    const int h = HUB ? __shfl_sync(0xffffffffu, hs, j0 + u, VW) : 0xffff;
 #pragma unroll
                     for (int r = 0; r < R; ++r)
-                        if (j0 + u < rem && lane_on[r]) x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                        if (j0 + u < rem && lane_on[r]) {
+                            if (HUB && h < hub.nhub) x[u].v[r] = ld_hub16<T>(hub, (uint32_t)h, r * VW * 16);
+                            else x[u].v[r] = ldg16<T>(xr + r * VW * 16);
+                        }
                 }
             }
 #pragma unroll
@@ -318,6 +353,15 @@ cb_spmm_kernel(const SpmmArgs a) {
         for (int r = 0; r < R; ++r)
             if (lane_on[r]) st16<T>(dst + (vl + r * VW) * 16, acc.v[r]);
     }
+}
+
+// K2: one chunk per virtual warp, grid sized to the chunk count
+template <class Op, int VW, int R, int U, int MINB, bool FULL>
+__global__ void __launch_bounds__(256, MINB)
+cb_spmm_kernel(const SpmmArgs a) {
+    constexpr int NV = 32 / VW;                       // virtual warps per warp
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    cb_spmm_walk<Op, VW, R, U, FULL, false>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
 }
 
 // Combine the pieces of split rows in chunk order: Y[row] = tail[c0] (+) head[c0+1] (+) ... (+) head[c1].
