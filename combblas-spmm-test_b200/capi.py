@@ -22,7 +22,8 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_timer_start", "cb_timer_stop", "cb_tile_upload_csc", "cb_tile_upload_coo", "cb_tile_from_device_coo",
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
-           "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense"]
+           "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host"]
 
 
 class CBError(RuntimeError):
@@ -100,6 +101,9 @@ def lib():
         L.cb_gen_rmat_tile.argtypes = [c_void_p, c_int, c_int, c_uint64, POINTER(c_double), c_int, c_int64, c_int64,
                                        c_int64, c_int64, c_int, c_uint64, POINTER(c_void_p)]
         L.cb_gen_dense.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int64, c_int]
+        L.cb_spmm_hub_config.argtypes = [c_void_p, c_int, c_int, c_int]
+        L.cb_spmm_hub_info.argtypes = [c_void_p, POINTER(c_int64)]
+        L.cb_hub_select_host.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
         _lib = L
     return _lib
 
@@ -124,6 +128,17 @@ def summa_plan(pr, pc, gn):
     ac, xr, ns = (c_int * (pr + pc))(), (c_int * (pr + pc))(), c_int()
     _check(lib().cb_summa_plan(pr, pc, gn, seg, ac, xr, byref(ns)))
     return list(seg[:ns.value + 1]), list(ac[:ns.value]), list(xr[:ns.value])
+
+
+def hub_select(counts, max_hubs):
+    """The hub selection rule of the hub variant (cb_hub.cu): -> (hub columns by rank, cumulative nonzero counts); host arithmetic only."""
+    counts = np.ascontiguousarray(counts, np.int32)
+    cols = np.empty(max(max_hubs, 1), np.int32)
+    cum = np.empty(max(max_hubs, 1), np.int64)
+    n = lib().cb_hub_select_host(_ptr(counts), len(counts), max_hubs, _ptr(cols), _ptr(cum))
+    if n < 0:
+        raise CBError(n, "cb_hub_select_host: bad arguments")
+    return cols[:n].copy(), cum[:n].copy()
 
 
 def block_range(total, nb, b):
@@ -260,6 +275,10 @@ class Context:
     def spmm_summa(self, tile, X, Y, semiring, gm, gn, gk):
         _check(lib().cb_spmm_summa(self.h, tile.h, X.h, Y.h, semiring, gm, gn, gk), self.h)
 
+    def hub_config(self, enable, cluster=0, slab_bytes=0):
+        """Opt into the hub variant of the local multiply (K2H); enable=-1 follows CB_SPMM_HUB."""
+        _check(lib().cb_spmm_hub_config(self.h, int(enable), int(cluster), int(slab_bytes)), self.h)
+
     def summa_cache_a(self, on=True):
         _check(lib().cb_summa_cache_a(self.h, int(on)), self.h)
 
@@ -300,6 +319,12 @@ class Tile:
         if self.h:
             lib().cb_tile_free(self.h)
             self.h = c_void_p()
+
+    def hub_info(self):
+        """{built, hub columns known, hub rows resident in the last multiply, share of nonzeros they serve}"""
+        info = (c_int64 * 4)()
+        _check(lib().cb_spmm_hub_info(self.h, info))
+        return {"built": bool(info[0]), "known": info[1], "resident": info[2], "cover": info[3] / 1e6}
 
     def pattern_view(self):
         v = c_void_p()

@@ -38,6 +38,8 @@ struct cb_ctx {
     cudaStream_t h2d = nullptr, d2h = nullptr;               // column slabs of host panels flow up / down on these
     cudaEvent_t slab_up[8] = {nullptr}, slab_done[8] = {nullptr}, host_begin = nullptr;
     void* summa_state = nullptr;      // receive buffers + events, owned by cb_summa.cu
+    // hub variant of K2 (cb_hub.cu): -1 / 0 = follow the CB_SPMM_HUB* environment, otherwise set by cb_spmm_hub_config
+    int hub_enable = -1, hub_cluster = 0, hub_slab_bytes = 0;
     std::string err;
 };
 
@@ -69,6 +71,7 @@ static inline cb_tile_layout cb_layout(const cb_tile_meta& t) {
 }
 
 // Device tile: doubly compressed rows (the row-major mirror of Dcsc, dcsc.h:124-131) plus a work partition.
+struct cb_hub;
 struct cb_tile {
     cb_ctx* ctx = nullptr;
     uint64_t uid = 0;         // unique per built tile (0 for views onto received buffers)
@@ -108,6 +111,8 @@ struct cb_tile {
     // my whole block-row of A regrouped by the X row block it multiplies (one tile per processor row), built from the
     // own + cached parts at the second multiply; entries stay NULL where a single existing part already is that tile
     std::vector<cb_tile*> summa_merged;
+    // most frequent columns and the per-nonzero hub ranks, built at the first hub multiply (cb_hub.cu); owned tiles only
+    cb_hub* hub = nullptr;
 };
 
 static inline cb_tile_meta cb_tile_get_meta(const cb_tile* t) {

@@ -1,0 +1,23 @@
+// Shared declarations of the hub variant of K2 (cb_hub.cu, cb_spmm_hub_kernel.cuh, cb_spmm_dispatch.cuh).
+#pragma once
+#include "cb_common.cuh"
+
+#define CB_HUB_MAX_RANKS 65535      // ranks are 16-bit, 0xffff = "not a hub"
+#define CB_HUB_MAX_SLABS 8192
+
+namespace cbk {
+// shape of one hub launch, decided by cb_hub_plan; nhub == 0 means "run plain K2"
+struct HubPlan {
+    int cluster = 1;                  // CTAs per cluster pooling their shared memory
+    int slab_bytes = 0;               // bytes of a panel row handled per column slab: 128, 256 or 512
+    int nhub = 0;                     // hub ranks resident on the SMs
+    size_t smem_bytes = 0;            // dynamic shared memory per CTA
+    const uint16_t* hubslot = nullptr;
+    const int32_t* hubcols = nullptr;
+    unsigned* counters = nullptr;
+};
+}  // namespace cbk
+
+int cb_hub_plan(cb_ctx* ctx, const cb_tile* tile, int64_t row_bytes, cudaStream_t stream, cbk::HubPlan* plan);
+void cb_hub_release(cb_tile* tile);
+extern "C" int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs, int32_t* hubcols, int64_t* cum);

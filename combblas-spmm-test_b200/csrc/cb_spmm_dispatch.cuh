@@ -1,6 +1,7 @@
 // Host-side launch of K2 (+ fix-up) for one semiring functor: picks the virtual-warp layout from the row width.
 #pragma once
-#include "cb_spmm_kernel.cuh"
+#include "cb_hub.cuh"
+#include "cb_spmm_hub_kernel.cuh"
 
 #ifndef CB_WIDE_U
 #define CB_WIDE_U 4
@@ -16,6 +17,14 @@
 #define CB_DEEP_U 8
 #define CB_DEEP_B 4
 #endif
+// hub variant: one persistent CTA of CB_HUB_BT threads per SM, CB_HUB_U row gathers in flight per lane.  1024 threads cap
+// the kernel at 64 registers, which U=4 fits without spills for every element type (U=8 spills 16-200 bytes on 4-byte types)
+#ifndef CB_HUB_BT
+#define CB_HUB_BT 1024
+#endif
+#ifndef CB_HUB_U
+#define CB_HUB_U 4
+#endif
 
 namespace cbk {
 
@@ -29,7 +38,10 @@ struct LaunchParams {
     int64_t ldy_bytes;
     int total_row_bytes;      // padded to 16
     int accumulate;
+    const HubPlan* hub = nullptr;   // non-null: run the hub variant (K2H) with this shape
 };
+
+enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
 template <class Op, int VW, int R, int U, int MINB, bool FULL>
 static int launch_layout_f(const LaunchParams& p) {
@@ -70,23 +82,103 @@ static int launch_layout(const LaunchParams& p) {
     return launch_layout_f<Op, VW, R, U, MINB, false>(p);
 }
 
+// K2H: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
+template <class Op, int VW, bool FULL>
+static int launch_hub_layout(const LaunchParams& p) {
+    constexpr int BT = CB_HUB_BT;                                      // one CTA owns the SM
+    constexpr int U = CB_HUB_U;
+    const cb_tile* t = p.t;
+    const HubPlan& hp = *p.hub;
+    SpmmArgs a;
+    a.colflag = t->colflag;
+    a.vals = t->vals;
+    a.nzrows = t->nzrows;
+    a.chunk_start = t->chunk_start;
+    a.chunk_row = t->chunk_row;
+    a.nchunks = t->nchunks;
+    a.X = (const char*)p.X;
+    a.Y = (char*)p.Y;
+    a.ldx_bytes = p.ldx_bytes;
+    a.ldy_bytes = p.ldy_bytes;
+    a.slab_bytes = VW * 16;
+    a.row_bytes = a.slab_bytes;
+    a.total_row_bytes = p.total_row_bytes;
+    a.carry = (char*)t->carry;
+    a.carry_stride = p.total_row_bytes;
+    a.accumulate = p.accumulate;
+    HubArgs h;
+    h.hubslot = hp.hubslot;
+    h.hubcols = hp.hubcols;
+    h.nhub = hp.nhub;
+    h.counter = hp.counters;
+    auto kernel = cb_spmm_hub_kernel<Op, VW, 1, U, BT, FULL>;
+    const unsigned nslabs = (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes);
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes) != cudaSuccess) { cudaGetLastError(); return CB_HUB_FALLBACK; }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)hp.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)hp.cluster, nslabs, 1);
+    cfg.blockDim = dim3(BT, 1, 1);
+    cfg.dynamicSmemBytes = hp.smem_bytes;
+    cfg.stream = p.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return CB_HUB_FALLBACK; }
+    // no more CTAs than there is work for: one warp takes 32/VW chunks at a time
+    const int64_t warps_needed = (t->nchunks + (32 / VW) - 1) / (32 / VW);
+    const int64_t clusters_needed = (warps_needed + (int64_t)hp.cluster * (BT / 32) - 1) / ((int64_t)hp.cluster * (BT / 32));
+    if ((int64_t)nclusters > clusters_needed) nclusters = (int)clusters_needed;
+    cfg.gridDim.x = (unsigned)(nclusters * hp.cluster);
+    CB_CUDA(p.ctx, cudaMemsetAsync(hp.counters, 0, nslabs * sizeof(unsigned), p.stream));
+    {
+        cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
+        CB_CUDA(p.ctx, cudaLaunchKernelEx(&cfg, kernel, a, h));
+    }
+    CB_LAUNCHED(p.ctx);
+    CB_CUDA(p.ctx, cudaGetLastError());
+    return CB_OK;
+}
+
+template <class Op, int VW>
+static int launch_hub_vw(const LaunchParams& p) {
+    if (p.total_row_bytes % (VW * 16) == 0) return launch_hub_layout<Op, VW, true>(p);
+    return launch_hub_layout<Op, VW, false>(p);
+}
+
+template <class Op>
+static int launch_hub(const LaunchParams& p) {
+    switch (p.hub->slab_bytes) {
+        case 128: return launch_hub_vw<Op, 8>(p);
+        case 256: return launch_hub_vw<Op, 16>(p);
+        case 512: return launch_hub_vw<Op, 32>(p);
+    }
+    return CB_HUB_FALLBACK;
+}
+
 template <class Op>
 static int launch_op(const LaunchParams& p) {
     const cb_tile* t = p.t;
     if (t->nnz > 0) {
         const int nvec = p.total_row_bytes / 16;
-        int s;
-        // X rows this tile touches: mostly L2-resident (R-MAT scale <= 22 class) or streaming from DRAM?
-        static const int force = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;      // 0 deep, 1 wide (experiments)
-        const bool wide = force >= 0 ? force == 1 : (nvec <= 16 && (double)t->nzc * (double)p.total_row_bytes < 1.0e9);
-        // 64-bit element types need more registers per gathered vector's arithmetic: one CTA per SM fewer
-        constexpr int WB = sizeof(typename Op::T) == 8 ? CB_WIDE_B64 : CB_WIDE_B;
-        constexpr int DB = sizeof(typename Op::T) == 8 ? CB_DEEP_B64 : CB_DEEP_B;
-        if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
-        else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 8, 1, CB_DEEP_U, DB>(p);
-        else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 16, 1, CB_DEEP_U, DB>(p);
-        else if (nvec <= 32) s = wide ? launch_layout<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 32, 1, CB_DEEP_U, DB>(p);
-        else s = launch_layout<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
+        int s = CB_HUB_FALLBACK;
+        if (p.hub) s = launch_hub<Op>(p);
+        if (s == CB_HUB_FALLBACK) {
+            // X rows this tile touches: mostly L2-resident (R-MAT scale <= 22 class) or streaming from DRAM?
+            static const int force = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;      // 0 deep, 1 wide (experiments)
+            const bool wide = force >= 0 ? force == 1 : (nvec <= 16 && (double)t->nzc * (double)p.total_row_bytes < 1.0e9);
+            // 64-bit element types need more registers per gathered vector's arithmetic: one CTA per SM fewer
+            constexpr int WB = sizeof(typename Op::T) == 8 ? CB_WIDE_B64 : CB_WIDE_B;
+            constexpr int DB = sizeof(typename Op::T) == 8 ? CB_DEEP_B64 : CB_DEEP_B;
+            if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
+            else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 8, 1, CB_DEEP_U, DB>(p);
+            else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 16, 1, CB_DEEP_U, DB>(p);
+            else if (nvec <= 32) s = wide ? launch_layout<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 32, 1, CB_DEEP_U, DB>(p);
+            else s = launch_layout<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
+        }
         if (s != CB_OK) return s;
         if (t->nsplit > 0) {
             FixupArgs f;

@@ -9,6 +9,7 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 #include "cb_common.cuh"
+#include "cb_hub.cuh"
 
 namespace {
 
@@ -353,6 +354,7 @@ int cb_tile_free(cb_tile* t) {
     if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->compute); cudaStreamSynchronize(t->ctx->comm); }
     if (t->owns_slab) cudaFree(t->slab);
     cudaFree(t->carry);
+    cb_hub_release(t);
     for (cb_tile* sub : t->summa_parts) cb_tile_free(sub);
     for (cb_tile* sub : t->summa_remote) cb_tile_free(sub);
     for (cb_tile* sub : t->summa_merged) cb_tile_free(sub);

@@ -173,6 +173,23 @@ int cb_summa_plan(int pr, int pc, int64_t gn, int64_t* seg, int* a_owner_col, in
 int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy,
                  int64_t k, int dtype, int semiring);
 
+/* Hub variant of the local multiply (K2H, csrc/cb_spmm_hub_kernel.cuh) - OPT-IN, off by default.
+ * For tiles whose columns are very unevenly used (R-MAT / power-law inputs) the panel rows of the most frequent columns
+ * are kept in the shared memory of thread-block clusters for the whole multiply, so that share of the row gathers no
+ * longer crosses the L2 slices.  Results are bit-identical to the default kernel (same walk, same fold order).  It has no
+ * counterpart in the reference: it is a faster LocalHybridSpGEMM-with-dense-rhs (include/CombBLAS/mtSpGEMM.h:213-460).
+ *   enable     : 1 on, 0 off, -1 follow the environment (CB_SPMM_HUB=1)
+ *   cluster    : CTAs pooling their shared memory: 1, 2, 4, 8, or 0 for the default (CB_SPMM_HUB_CLUSTER, 4)
+ *   slab_bytes : bytes of a panel row handled per column slab: 128, 256, 512, or 0 to choose by row width
+ * cb_spmm_hub_info: {hub data built, hub columns known, hub rows resident in the last multiply, share of the tile's
+ * nonzeros they serve x 1e6}. */
+int cb_spmm_hub_config(cb_ctx* ctx, int enable, int cluster, int slab_bytes);
+int cb_spmm_hub_info(const cb_tile* tile, int64_t info[4]);
+/* The hub selection rule as pure host arithmetic (no device needed): the max_hubs most frequent columns with at least
+ * two nonzeros, most frequent first, ties by ascending column; cum[r] = nonzeros in the columns of rank <= r.
+ * Returns the number of hubs written, or -1 on bad arguments. */
+int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs, int32_t* hubcols, int64_t* cum);
+
 /* number of kernels this library has launched on the ctx since creation (bench.py's gpu_launches) */
 int64_t cb_launch_count(const cb_ctx* ctx);
 /* per-kernel device timing: while enabled every K3 (identity fill) / K2 (multiply) / fix-up launch on the

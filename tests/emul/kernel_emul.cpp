@@ -5,7 +5,7 @@
 #include "cuda_emul.h"
 #include <cstdio>
 #include <random>
-#include "cb_spmm_kernel.cuh"
+#include "cb_spmm_hub_kernel.cuh"
 
 using namespace cbk;
 
@@ -47,10 +47,12 @@ template <class T> static T rnd_val(std::mt19937& g) { return (T)(1 + g() % 9); 
 template <> float rnd_val<float>(std::mt19937& g) { return (float)(1 + g() % 64) / 8.0f; }
 template <> double rnd_val<double>(std::mt19937& g) { return (double)(1 + g() % 1024) / 32.0; }
 
-// one multiply on the emulator; returns the number of mismatching elements
+// one multiply on the emulator; returns the number of mismatching elements.  hub_cs > 0 runs the hub variant (K2H) in
+// clusters of hub_cs CTAs with the `nhub` most frequent columns resident in (distributed) shared memory and also
+// requires its result to be bit-identical to plain K2's.
 template <class Op, int VW, int R, int U, bool FULL>
 static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elements of Op::T per panel row */, int32_t L, int hub, unsigned seed,
-                     bool accumulate) {
+                     bool accumulate, int hub_cs = 0, int nhub = 0) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     std::mt19937 g(seed);
@@ -101,7 +103,37 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
     a.carry = carry.data(); a.carry_stride = row_bytes; a.accumulate = accumulate ? 1 : 0;
     constexpr int NV = 32 / VW;
     dim3 grid((unsigned)((t.nchunks + 8 * NV - 1) / (8 * NV)), (unsigned)((row_bytes + a.slab_bytes - 1) / a.slab_bytes));
-    const long long syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
+    long long syncs = 0;
+    std::vector<T> Yplain;
+    if (hub_cs > 0) {
+        // plain K2 on a copy first: K2H must reproduce it bit for bit (same walk, same fold order)
+        std::vector<T> Ysave = Y;
+        emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
+        Yplain = Y;
+        Y = Ysave;
+        a.Y = (char*)Y.data();
+        std::fill(carry.begin(), carry.end(), (char)0x77);
+        // hub ranks: columns by descending count, ties by ascending column (cb_hub_select_host)
+        std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
+        for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
+        for (int64_t c = 0; c < n; ++c) order[c] = (int32_t)c;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cnt[x] > cnt[y]; });
+        int have = 0;
+        while (have < n && cnt[order[have]] > 0) ++have;
+        nhub = std::min(nhub, have);
+        std::vector<int32_t> hubcols(order.begin(), order.begin() + nhub);               // exactly nhub entries: reading rank >= nhub is an ASan report
+        std::vector<uint16_t> rank_of((size_t)n, 0xffff), hubslot((size_t)t.nnz);
+        for (int r = 0; r < have && r < 0xffff; ++r) rank_of[order[r]] = (uint16_t)r;    // ranks beyond nhub exist too: the kernel must ignore them
+        for (int64_t p = 0; p < t.nnz; ++p) hubslot[p] = rank_of[t.colflag[p] & 0x7fffffff];
+        std::vector<unsigned> counters(grid.y, 0u);
+        HubArgs h{};
+        h.hubslot = hubslot.data(); h.hubcols = hubcols.data(); h.nhub = nhub; h.counter = counters.data();
+        const size_t smem = (size_t)((nhub + hub_cs - 1) / hub_cs) * a.slab_bytes;
+        emul::launch_cluster(dim3((unsigned)(2 * hub_cs), grid.y), dim3(64), (unsigned)hub_cs, smem ? smem : 16,
+                             [&] { cb_spmm_hub_kernel<Op, VW, R, U, 64, FULL>(a, h); });
+    } else {
+        syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
+    }
     if (t.nsplit) {
         FixupArgs f{};
         f.split_row = t.split_row.data(); f.nsplit = t.nsplit; f.nzrows = t.nzrows.data(); f.rowptr = t.rowptr.data();
@@ -110,6 +142,16 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         emul::launch(dim3((unsigned)((t.nsplit + 7) / 8)), dim3(256), [&] { cb_fixup_kernel<Op>(f); });
     }
     long bad = 0;
+    if (hub_cs > 0) {
+        if (t.nsplit) {      // fix-up of the plain run, so the two results are comparable row for row
+            FixupArgs f{};
+            f.split_row = t.split_row.data(); f.nsplit = t.nsplit; f.nzrows = t.nzrows.data(); f.rowptr = t.rowptr.data();
+            f.chunk_len = t.L; f.carry = carry.data(); f.carry_stride = row_bytes; f.Y = (char*)Yplain.data(); f.ldy_bytes = row_bytes;
+            f.total_row_bytes = row_bytes; f.accumulate = accumulate ? 1 : 0;
+            emul::launch(dim3((unsigned)((t.nsplit + 7) / 8)), dim3(256), [&] { cb_fixup_kernel<Op>(f); });
+        }
+        if (std::memcmp(Yplain.data(), Y.data(), Y.size() * sizeof(T)) != 0) { ++bad; std::printf("%-28s K2H differs from K2\n", name); }
+    }
     for (size_t q = 0; q < Y.size(); ++q) {
         const double x = (double)Y[q], y = (double)Yref[q];
         if (std::is_floating_point<T>::value ? std::abs(x - y) > 1e-5 * std::max(1.0, std::abs(y)) : Y[q] != Yref[q]) ++bad;
@@ -141,6 +183,15 @@ int main(int argc, char** argv) {
     // a larger tile: several blocks, chunk length 64, hub rows of ~11 chunks
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pt_f32 VW16 larger", 400, 900, 64, 64, 700, 11 + sd, false);
     bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("minplus_i64 VW16 larger acc", 300, 500, 32, 64, 400, 12 + sd, true);
+    // K2H, the hub variant: persistent CTAs, dynamic chunks, hub rows in the shared memory of a 1/2/4-CTA cluster
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs1", 61, 97, 64, 32, 150, 21 + sd, false, 1, 20);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs2 acc", 61, 97, 64, 32, 150, 22 + sd, true, 2, 33);
+    bad += run_case<PlusTimes<float, A_PATTERN>, 32, 1, 8, false>("hub pt_f32 pat 3 slabs cs4", 33, 60, 300, 32, 55, 23 + sd, false, 4, 60);   // every column a hub
+    bad += run_case<PlusTimes<double, A_BOOL>, 32, 1, 8, false>("hub pt_f64 boolA ragged cs2", 30, 80, 50, 32, 70, 24 + sd, true, 2, 7);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("hub minplus_i32 VW8 cs4", 70, 64, 32, 32, 60, 25 + sd, false, 4, 30);
+    bad += run_case<SelectMax<int64_t>, 8, 1, 8, false>("hub selectmax_i64 k=13 cs1", 45, 50, 13, 32, 45, 26 + sd, false, 1, 1);
+    bad += run_case<OrAnd<A_PATTERN>, 8, 1, 8, false>("hub or_and VW8 cs2 nhub=0", 50, 40, 24, 32, 38, 27 + sd, false, 2, 0);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 larger cs4", 400, 900, 64, 64, 700, 28 + sd, false, 4, 200);
     }
     std::printf(bad ? "EMULATION FAILED\n" : "emulation ok\n");
     return bad ? 1 : 0;

@@ -127,3 +127,21 @@ def test_unsupported_semiring_is_a_compile_time_error(tmp_path):
     ok.write_text(src.read_text().replace("MaxTimesSRing<double, double>>(A, X)", "MinPlusSRing<double, double>>(A, X)"))
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-Wno-int-in-bool-context"] + inc + [str(ok)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_hub_selection_rule():
+    # cb_hub_select_host (csrc/cb_hub.cu): most frequent columns first, ties by ascending column, columns with < 2 nonzeros never
+    import cbb200_loader
+    cb = cbb200_loader.load_package()
+    counts = np.array([5, 0, 9, 1, 9, 2, 2, 7], np.int32)
+    cols, cum = cb.capi.hub_select(counts, 16)
+    assert cols.tolist() == [2, 4, 7, 0, 5, 6] and cum.tolist() == [9, 18, 25, 30, 32, 34]
+    cols, cum = cb.capi.hub_select(counts, 3)
+    assert cols.tolist() == [2, 4, 7] and cum.tolist() == [9, 18, 25]
+    assert cb.capi.hub_select(np.zeros(10, np.int32), 4)[0].size == 0
+    rng = np.random.default_rng(0)
+    counts = rng.zipf(1.3, 5000).clip(0, 100000).astype(np.int32)
+    cols, cum = cb.capi.hub_select(counts, 300)
+    order = np.lexsort((np.arange(len(counts)), -counts.astype(np.int64)))
+    order = order[counts[order] >= 2][:300]
+    assert np.array_equal(cols, order) and np.array_equal(cum, np.cumsum(counts[order].astype(np.int64)))

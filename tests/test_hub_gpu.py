@@ -1,0 +1,84 @@
+"""The hub variant of the local multiply (K2H, csrc/cb_spmm_hub_kernel.cuh) on the GPU, through the C ABI.
+
+STATUS: K2H has been validated on the CPU warp/cluster emulator only (tests/test_kernel_emul_cpu.py); no GPU time was
+left in the round that wrote it.  It is opt-in in the product (cb_spmm_hub_config / CB_SPMM_HUB=1) and these tests are
+opt-in too: they run with CB_TEST_HUB=1 and are skipped otherwise, so an untested kernel cannot turn the validated suite
+red.  First thing to run on hardware next round:
+
+    CB_TEST_HUB=1 python -m pytest tests/test_hub_gpu.py -x -q
+
+Each case runs in its own process (own CUDA context, hard timeout): a fault or a hang of the new kernel stays contained.
+The bar is stronger than parity: K2H walks chunks exactly like K2, so its result must equal K2's BIT FOR BIT for every
+semiring, floating point included, and equal the oracle within the usual tolerances."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CB_TEST_HUB") != "1", reason="hub variant not yet validated on hardware: set CB_TEST_HUB=1")]
+
+WORKER = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import cbb200_loader
+from oracle import oracle as O
+cb = cbb200_loader.load_package()
+case, cluster, slab, scale, k = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+CASES = {"pt_f32": (O.PLUS_TIMES, np.float32, np.float32, "value"), "pt_f64": (O.PLUS_TIMES, np.float64, np.float64, "value"),
+         "minplus_i32": (O.MIN_PLUS, np.int32, np.int32, "x_minplus"), "pt_pat_i64": (O.PLUS_TIMES, None, np.int64, "value"),
+         "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"), "or_and": (O.OR_AND, None, np.uint8, "value")}
+sr, adt, xdt, kind = CASES[case]
+n, I, J = O.rmat_matrix(scale, 16, seed=0)
+V = None if adt is None else O.matrix_values(I, J, n, 1, adt)
+X = O.dense_operand(n, k, 42, xdt, kind)
+with cb.Context(0) as ctx:
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    Xd, Y0, Y1, Y2 = ctx.dense_from(X), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt)
+    for acc in (False, True):                               # plain K2: overwrite, then accumulate on top
+        ctx.spmm_local(t, Xd, Y0, sr, accumulate=acc)
+    ctx.hub_config(1, cluster, slab)
+    for acc in (False, True):                               # K2H: the same two calls
+        ctx.spmm_local(t, Xd, Y1, sr, accumulate=acc)
+    ctx.spmm_local(t, Xd, Y2, sr)
+    info = t.hub_info()
+    ctx.hub_config(0)
+    a, a1, b = Y0.download(), Y1.download(), Y2.download()
+    ref = O.spmm(sr, n, n, I, J, V, X)
+    assert info["built"] and info["resident"] > 0, f"the hub kernel did not run: {info}"
+    assert a.tobytes() == a1.tobytes(), "K2H differs from K2"
+    if np.issubdtype(ref.dtype, np.floating):
+        tol = 1e-5 if ref.dtype == np.float32 else 1e-12
+        assert (np.abs(b - ref) <= tol * np.maximum(np.abs(ref), 1e-300)).all()
+    else:
+        assert np.array_equal(b, ref)
+    print("hub ok", case, "cluster", cluster, "slab", slab, info)
+'''
+
+
+def run(case, cluster, slab, scale=12, k=64):
+    env = dict(os.environ, CB_SPMM_HUB_MIN_COVER_PCT="0")          # small test matrices: never fall back for low coverage
+    r = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}, case, str(cluster), str(slab), str(scale), str(k)],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "hub ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_hub_matches_k2_bitwise_fp32(cluster):
+    run("pt_f32", cluster, 0)
+
+
+@pytest.mark.parametrize("case", ["pt_f64", "minplus_i32", "pt_pat_i64", "selmax_i32", "or_and"])
+def test_hub_every_semiring(case):
+    run(case, 4, 0, k=64 if case != "or_and" else 256)          # boolean panels: 256 one-byte columns = 256-byte rows
+
+
+@pytest.mark.parametrize("slab,k", [(128, 64), (256, 100), (512, 300), (128, 33)])
+def test_hub_column_slabs_and_ragged_widths(slab, k):
+    run("pt_f32", 2, slab, k=k)
+
+
+def test_hub_larger_matrix_many_chunks():
+    run("minplus_i32", 4, 128, scale=16, k=32)

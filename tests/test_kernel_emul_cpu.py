@@ -1,7 +1,9 @@
-"""Memory safety and warp convergence of the hot kernel without a GPU: csrc/cb_spmm_kernel.cuh is compiled UNMODIFIED for the
-host against a lock-step warp emulator (tests/emul/cuda_emul.h: 32 lanes = 32 threads, *_sync intrinsics are rendezvous
-points) and run under AddressSanitizer + UBSan on small tiles with hub rows, empty rows, ragged widths, column slabs and the
-accumulate mode, against a scalar loop over the same functors.  (compute-sanitizer is closed on the GPU pool.)"""
+"""Memory safety and warp convergence of the hot kernels without a GPU: csrc/cb_spmm_kernel.cuh and cb_spmm_hub_kernel.cuh are
+compiled UNMODIFIED for the host against a lock-step warp emulator (tests/emul/cuda_emul.h: 32 lanes = 32 threads, *_sync
+intrinsics are rendezvous points; CTAs, clusters, shared memory and reads of a neighbour CTA's shared memory for the hub
+variant) and run under AddressSanitizer + UBSan on small tiles with hub rows, empty rows, ragged widths, column slabs and the
+accumulate mode, against a scalar loop over the same functors.  The hub variant (K2H) must also reproduce plain K2 bit for
+bit.  (compute-sanitizer is closed on the GPU pool.)"""
 import os
 import subprocess
 
@@ -17,4 +19,4 @@ def test_k2_and_fixup_on_the_warp_emulator_under_asan(tmp_path):
     r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)      # a dead-locked warp = diverged *_sync = timeout
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "emulation ok" in r.stdout and "mismatches=0" in r.stdout and "runtime error" not in r.stderr
-    assert r.stdout.count("mismatches=0") == 24
+    assert r.stdout.count("mismatches=0") == 40 and "K2H differs" not in r.stdout

@@ -35,6 +35,6 @@ for name in a.workloads:
     print(json.dumps(dict(w=name, k=k, nnz=t.nnz, ms_step=round(ms, 4), k2_ms=round(k2, 4), fill_ms=round(pm["fill"] / max(pn["fill"], 1), 4),
                           fix_ms=round(pm["fixup"] / max(pn["fixup"], 1), 4), tflops=round(2 * t.nnz * k / ms / 1e9, 2),
                           alg_gbs=round(b / k2 / 1e6, 1), frac=round(b / k2 / 1e6 / 6542.1, 4), gather_tbs=round(g / k2 / 1e9, 2),
-                          chunks=t.nchunks, split=t.nsplit)), flush=True)
+                          chunks=t.nchunks, split=t.nsplit, hub=t.hub_info())), flush=True)
     for h in (t, X, Y): h.free()
 ctx.close()
