@@ -285,6 +285,28 @@ def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_dis
     return Y, sec, out
 
 
+def ref_grid_mm(path, ranks, X):
+    """BASELINE config C1 on sqrt(ranks)^2 processes: the reference reads the Matrix Market file itself (ParallelReadMM) and
+    multiplies by X (n x k float64) with Mult_AnXBn_Synch.  Returns (Y, report line)."""
+    import tempfile
+    X = np.ascontiguousarray(X, np.float64)
+    n, k = X.shape
+    with tempfile.TemporaryDirectory(prefix="cbref_grid_") as d:
+        X.tofile(os.path.join(d, "X.bin"))
+        out = _run_grid(["mm", path, str(k), d], ranks)
+        blocks = []
+        for r in range(ranks):
+            raw = np.fromfile(os.path.join(d, f"Y_{r}.bin"), np.uint8)
+            r0, c0, rows, cols = (int(v) for v in raw[:32].view(np.int64))
+            blocks.append((r0, c0, raw[32:].view(np.float64).reshape(rows, cols)))
+    m = max(r0 + b.shape[0] for r0, _, b in blocks)
+    Y = np.full((m, k), np.nan)
+    for r0, c0, b in blocks:
+        Y[r0:r0 + b.shape[0], c0:c0 + b.shape[1]] = b
+    assert not np.isnan(Y).any()
+    return Y, [l for l in out.splitlines() if l.startswith("A:")][0]
+
+
 def ref_best_time(semiring, m, n, I, J, V, X, cores, reps=1):
     """Seconds of the fastest configuration of the unmodified reference on `cores` host cores: 1 process x cores OpenMP
     threads (libcbref.so) or a 2x2 process grid x cores/4 threads (cbref_grid) - its MPI+OpenMP design is faster with

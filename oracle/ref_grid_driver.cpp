@@ -11,6 +11,8 @@
 //   cbref_grid torus
 //       the program of Applications/SpMMError.cpp (that file no longer compiles against its own headers: it omits the
 //       NUO/UDERO template arguments, ParFriends.h:1004-1005); same steps with the arguments spelled out.
+//   cbref_grid mm <file.mtx> <k> <dir>
+//       BASELINE config C1 on a grid: ParallelReadMM by the reference itself, then x dense k columns fp64 (X from <dir>/X.bin)
 //   cbref_grid spmm <key> <via> <dir>
 //       reads <dir>/meta.txt ("m n nnz k hasV"), I.bin J.bin (int64), V.bin (A's value type), X.bin (n x k row-major),
 //       writes <dir>/Y_<rank>.bin = int64 header {row0, col0, rows, cols} + the rank's dense block of Y (T_promote),
@@ -203,6 +205,40 @@ int run_spmm(int via, const std::string& dir) {
     return 0;
 }
 
+// BASELINE config C1 on a process grid: the reference reads the Matrix Market file itself (ParallelReadMM: every rank
+// parses its byte range of the file, symmetric expansion, Alltoallv redistribution, SpParMat.cpp:3978-4115), then
+// Y = A x X(k, fp64) through Mult_AnXBn_Synch.  X comes from <dir>/X.bin (n x k doubles); writes <dir>/Y_<rank>.bin.
+int run_mm(const std::string& file, int64_t k, const std::string& dir) {
+    typedef SpDCCols<int64_t, double> DD;
+    typedef PlusTimesSRing<double, double> SR;
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+    const int pr = grid->GetGridRows(), pc = grid->GetGridCols();
+    const int myrow = grid->GetRankInProcCol(), mycol = grid->GetRankInProcRow(), rank = grid->GetRank();
+    SpParMat<int64_t, double, DD> A(grid);
+    A.ParallelReadMM(file, true, maximum<double>());
+    const int64_t m = A.getnrow(), n = A.getncol(), nnz = A.getnnz();
+    std::vector<double> X = slurp<double>(dir + "/X.bin", (size_t)(n * k));
+    const Block ar = block_of(m, pr, myrow), xr = block_of(n, pr, myrow), xc = block_of(k, pc, mycol);
+    std::vector<std::tuple<int64_t, int64_t, double>> xt;
+    for (int64_t i = 0; i < xr.len; ++i)
+        for (int64_t j = 0; j < xc.len; ++j) xt.push_back(std::make_tuple(i, j, X[(size_t)((xr.lo + i) * k + xc.lo + j)]));
+    SpParMat<int64_t, double, DD> Xs(local_tile<double>(xr.len, xc.len, xt), grid);
+    SpParMat<int64_t, double, DD> C = Mult_AnXBn_Synch<SR, double, DD>(A, Xs);
+    std::vector<double> out((size_t)(ar.len * xc.len), 0.0);
+    Dcsc<int64_t, double>* d = C.seq().GetDCSC();
+    if (d)
+        for (int64_t c = 0; c < d->nzc; ++c)
+            for (int64_t p = d->cp[c]; p < d->cp[c + 1]; ++p) out[(size_t)(d->ir[p] * xc.len + d->jc[c])] = d->numx[p];
+    const int64_t hdr[4] = {ar.lo, xc.lo, ar.len, xc.len};
+    FILE* f = std::fopen((dir + "/Y_" + std::to_string(rank) + ".bin").c_str(), "wb");
+    std::fwrite(hdr, sizeof(int64_t), 4, f);
+    std::fwrite(out.data(), sizeof(double), out.size(), f);
+    std::fclose(f);
+    const int64_t cnnz = C.getnnz();
+    if (rank == 0) std::printf("A: %lld x %lld, %lld nonzeros on a %d x %d grid; C: %lld stored entries\n", (long long)m, (long long)n, (long long)nnz, pr, pc, (long long)cnnz);
+    return 0;
+}
+
 int run_torus() {
     typedef int64_t ValueType;
     typedef SpDCCols<int64_t, ValueType> DCColsType;
@@ -240,6 +276,7 @@ int main(int argc, char* argv[]) {
     {
         const std::string mode = argc > 1 ? argv[1] : "";
         if (mode == "torus") rc = run_torus();
+        else if (mode == "mm" && argc >= 5) rc = run_mm(argv[2], std::atoll(argv[3]), argv[4]);
         else if (mode == "spmm" && argc >= 5) {
             const std::string s = argv[2], dir = argv[4];
             const int via = std::atoi(argv[3]);
@@ -261,7 +298,7 @@ int main(int argc, char* argv[]) {
             CASE("select_max:bool:i64", SelectMaxSRing, bool, int64_t)
 #undef CASE
             if (rc == 2) std::fprintf(stderr, "cbref_grid: unknown key %s\n", s.c_str());
-        } else if (!mode.empty()) std::fprintf(stderr, "usage: cbref_grid torus | spmm <key> <via> <dir>\n");
+        } else if (!mode.empty()) std::fprintf(stderr, "usage: cbref_grid torus | mm <file.mtx> <k> <dir> | spmm <key> <via> <dir>\n");
     }
     MPI_Finalize();
     return rc;

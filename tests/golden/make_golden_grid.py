@@ -9,6 +9,8 @@ Contents (results of the reference's own multi-proce
   <case>_p4 / <case>_p9          Y of Mult_AnXBn_Synch on 2x2 / 3x3 processes for the operands of tests/summa_worker.py
                                  (R-MAT scale 9, edge factor 8, seed 3, ragged m = n-5, n = n-3, k = 13)
   <case>_p4_spmv                 the same product through k x SpMV<SR>(A, FullyDistVec) on 2x2 processes
+  hepth_p4, hepth_p4_report      BASELINE config C1 on 2x2 processes: Applications/hep-th.mtx read by the reference's own
+                                 ParallelReadMM on four ranks, x X(k=16, fp64, seed 42) through Mult_AnXBn_Synch
 Only numeric outputs are stored; inputs are regenerated from the counter-based generators at test time.
 """
 import os
@@ -58,6 +60,9 @@ def main():
             out[f"{case}_p{p}"] = Y
         if X.dtype != np.uint8:
             out[f"{case}_p4_spmv"] = O.ref_grid_spmm(sr, 4, m, n, I, J, V, X, via=1)[0]
+    hep = np.load(os.path.join(OUT, "hepth.npz"))
+    Y, report = O.ref_grid_mm("/root/reference/Applications/hep-th.mtx", 4, O.dense_operand(int(hep["n"]), 16, 42, np.float64))
+    out["hepth_p4"], out["hepth_p4_report"] = Y, np.array(report)
     np.savez_compressed(os.path.join(OUT, "grid_ref.npz"), **out)
     print("wrote grid_ref.npz:", ", ".join(sorted(out)))
 

@@ -56,6 +56,21 @@ def test_restatement_matches_reference_run_on_process_grids(case):
         assert close(one, g[f"{case}_p4_spmv"])
 
 
+def test_hepth_config_c1_on_2x2_processes():
+    # the reference's own ParallelReadMM on four ranks + Mult_AnXBn_Synch, against our Matrix Market reader + the restatement
+    g, hep = np.load(GOLD), np.load(os.path.join(ROOT, "tests", "golden", "hepth.npz"))
+    assert "8361 x 8361, 31502 nonzeros on a 2 x 2 grid; C: 121760 stored entries" in str(g["hepth_p4_report"])   # hep-th-p4.txt:9
+    m, n = int(hep["m"]), int(hep["n"])
+    X = O.dense_operand(n, 16, 42, np.float64)
+    gold = g["hepth_p4"]
+    assert close(O.spmm(O.PLUS_TIMES, m, n, hep["I"], hep["J"], hep["V"], X), gold)
+    # same stages; inside a stage the reference takes its heap branch for columns with flops/nnz < 2 (mtSpGEMM.h:336-347), whose
+    # summation order is not ascending, so a few percent of the entries differ in the last bit
+    em = O.spmm_summa(O.PLUS_TIMES, 2, 2, m, n, hep["I"], hep["J"], hep["V"], X)
+    assert close(em, gold) and (em == gold).mean() > 0.9
+    assert close(hep["Y"], gold)                                                                              # 1 process vs 4 processes
+
+
 def test_host_stage_loop_matches_reference_run_2x2():
     r = torchrun(4, ["--mode", "cpu", "--pr", "2", "--pc", "2", "--scale", str(SCALE), "--k", str(K), "--golden", GOLD,
                      "--cases", "minplus_i32,pt_f64,or_and"])

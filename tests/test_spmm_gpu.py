@@ -79,6 +79,8 @@ def test_hepth_config_c1(ctx, how):
     check(Y, g["Y"])
     # rows that are not cut by the work partition follow the reference's summation order exactly
     assert (Y == g["Y"]).mean() > 0.95
+    # ... and the reference's own 2x2-process run of the same configuration (ParallelReadMM on four ranks, grid_ref.npz)
+    check(Y, np.load(os.path.join(G, "grid_ref.npz"))["hepth_p4"])
 
 
 @pytest.mark.parametrize("name", ["seven", "nonsym", "large"])
