@@ -4,6 +4,7 @@
 //   host_logic_test mm <file.mtx>                -> triples after Matrix Market expansion
 //   host_logic_test semirings                    -> functor tables
 //   host_logic_test owner <pr> <pc> <m> <n> <r> <c>
+//   host_logic_test fdv <glen> <pr> <pc>         -> the FullyDistVec layout: per process (LengthUntil, MyLocLength), owners of all indices
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -114,6 +115,23 @@ int main(int argc, char** argv) {
         std::cout << "lastblock " << s << ' ' << l << '\n';
         return 0;
     }
-    std::cerr << "usage: host_logic_test tile|mm|semirings|owner ...\n";
+    if (mode == "fdv" && argc > 4) {
+        const int64_t glen = std::atoll(argv[2]);
+        const int pr = std::atoi(argv[3]), pc = std::atoi(argv[4]);
+        FullyDistLayout<int64_t> L(glen, pr, pc);
+        std::vector<int64_t> until, len, owner, lind;
+        for (int i = 0; i < pr; ++i)
+            for (int j = 0; j < pc; ++j) { until.push_back(L.LengthUntil(i, j)); len.push_back(L.LocLength(i, j)); }
+        for (int64_t g = 0; g < glen; ++g) {
+            int a, b;
+            int64_t l;
+            L.Owner(g, a, b, l);
+            owner.push_back(a * pc + b);
+            lind.push_back(l);
+        }
+        dump("until", until); dump("len", len); dump("owner", owner); dump("lind", lind);
+        return 0;
+    }
+    std::cerr << "usage: host_logic_test tile|mm|semirings|owner|fdv ...\n";
     return 2;
 }

@@ -4,6 +4,8 @@
 //   spmm_driver mtx  <file.mtx> <k> [ydump.bin]          fp64 PlusTimes on a Matrix Market file (BASELINE config C1)
 //   spmm_driver rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]   Kronecker matrix generated on the GPU
 //   spmm_driver torus                                    the sparse x sparse program of Applications/SpMMError.cpp
+//   spmm_driver spmv <scale> [pr pc]                     dense SpMV<SR>(A, FullyDistVec) under three semirings, DenseParMat::Reduce,
+//                                                        DenseParMat += SpParMat and SpParMat::EWiseScale (the steps around the multiply)
 //
 // Single process, or one process per GPU under a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK
 // (python -m torch.distributed.run --no-python ./spmm_driver ...).  Verification replays the multiply with the
@@ -12,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <limits>
 #include "CombBLAS/CombBLAS.h"
 
 using namespace combblas;
@@ -91,7 +94,7 @@ int RunRmat(int scale, int64_t k, int pr, int pc, double tol, bool values) {
 int main(int argc, char* argv[]) {
     MPI_Init(&argc, &argv);
     int rc = 0;
-    if (argc < 4 && !(argc >= 2 && std::string(argv[1]) == "torus")) {
+    if (argc < 4 && !(argc >= 2 && std::string(argv[1]) == "torus") && !(argc >= 3 && std::string(argv[1]) == "spmv")) {
         SpParHelper::Print("Usage: spmm_driver mtx <file.mtx> <k> [ydump.bin] | rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]\n");
         MPI_Finalize();
         return 2;
@@ -175,6 +178,79 @@ int main(int argc, char* argv[]) {
                 if (bad == 0 && want == c.getnnz()) SpParHelper::Print("SpGEMM (sparse x sparse) working correctly\n");
                 else { SpParHelper::Print("ERROR in SpGEMM, go fix it!\n"); rc = 1; }
             }
+        } else if (mode == "spmv") {
+            // y = A x through the dense SpMV interface (reference ParFriends.h:1924-1996), checked against k = 1 SpMM and
+            // against a host replay on one process; then the DenseParMat / SpParMat epilogues of SURVEY.md section 8 row f3
+            typedef SpParMat<int64_t, int64_t, SpDCCols<int64_t, int64_t>> Mat;
+            typedef SpParMat<int64_t, bool, SpDCCols<int64_t, bool>> BMat;
+            const int scale = std::atoi(argv[2]);
+            const int pr = argc > 4 ? std::atoi(argv[3]) : 0, pc = argc > 4 ? std::atoi(argv[4]) : 0;
+            std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, pr, pc));
+            Mat A(grid);
+            A.GenGraph500(scale, 8, true, 0, true, 1);
+            A.PrintInfo();
+            const int64_t n = A.getncol(), m = A.getnrow();
+            bool ok = true;
+            // (1) MinPlus: vector of hashed weights with a few "infinite" entries
+            FullyDistVec<int64_t, int64_t> x(grid, n, 0);
+            for (int64_t i = 0; i < x.LocArrSize(); ++i) {
+                const uint64_t h = splitmix64((uint64_t)(x.LengthUntil() + i) ^ 0xC0FFEEULL);
+                x.SetLocalElement(i, h % 97 == 0 ? std::numeric_limits<int64_t>::max() : (int64_t)(1 + h % 100));
+            }
+            FullyDistVec<int64_t, int64_t> y = SpMV<MinPlusSRing<int64_t, int64_t>>(A, x);
+            ok = ok && y.TotalLength() == m;
+            // the same product as an n x 1 panel
+            DenseParMat<int64_t, int64_t> X1 = DenseParMat<int64_t, int64_t>::Global(0, grid, n, 1);
+            {
+                const std::vector<int64_t> xw = x.Gather();
+                int64_t r0, c0;
+                X1.GetPlaceInGlobalGrid(n, 1, r0, c0);
+                for (int64_t i = 0; i < X1.getlocalrows(); ++i)
+                    for (int64_t j = 0; j < X1.getlocalcols(); ++j) X1(i, j) = xw[(size_t)(r0 + i)];
+            }
+            DenseParMat<int64_t, int64_t> Y1 = SpMM<MinPlusSRing<int64_t, int64_t>>(A, X1);
+            FullyDistVec<int64_t, int64_t> yr = Y1.Reduce(Row, [](int64_t a, int64_t b) { return std::min(a, b); }, std::numeric_limits<int64_t>::max());
+            ok = ok && (yr == y);
+            const int64_t reached = y.Count([](int64_t v) { return v != std::numeric_limits<int64_t>::max(); });
+            if (grid->GetRank() == 0) std::cout << "SpMV MinPlus: " << reached << " of " << m << " rows reached" << std::endl;
+            // (2) PlusTimes with an all-ones vector = row degrees weighted by A; Reduce(Row, +) of A as dense must agree
+            FullyDistVec<int64_t, int64_t> ones(grid, n, 1);
+            FullyDistVec<int64_t, int64_t> deg = SpMV<PlusTimesSRing<int64_t, int64_t>>(A, ones);
+            const int64_t total = deg.Reduce(std::plus<int64_t>(), (int64_t)0);
+            int64_t local = 0;
+            for (int64_t v : A.seq().numx) local += v;
+            ok = ok && total == grid->SumWorld(local);
+            // (3) SelectMax<bool,T> with values below the identity -1: SpMV starts from id(), so they are clipped (axpy semantics)
+            BMat P(grid);
+            P.GenGraph500(scale, 8, true, 0, false, 1);
+            FullyDistVec<int64_t, int64_t> neg(grid, n, -5);
+            FullyDistVec<int64_t, int64_t> sel = SpMV<SelectMaxSRing<bool, int64_t>>(P, neg);
+            ok = ok && sel.Count([](int64_t v) { return v != -1; }) == 0;
+            // (4) epilogues on one process grid cell: D += A, then A.EWiseScale(D) squares the stored values
+            DenseParMat<int64_t, int64_t> D(0, grid, A.getlocalrows(), A.getlocalcols());
+            D += A;
+            FullyDistVec<int64_t, int64_t> rowsum = D.Reduce(Row, std::plus<int64_t>(), (int64_t)0);
+            ok = ok && (rowsum == deg);
+            FullyDistVec<int64_t, int64_t> colsum = D.Reduce(Column, std::plus<int64_t>(), (int64_t)0);
+            ok = ok && colsum.TotalLength() == n && colsum.Reduce(std::plus<int64_t>(), (int64_t)0) == total;
+            Mat A2(A);
+            A2.EWiseScale(D);
+            FullyDistVec<int64_t, int64_t> sq = SpMV<PlusTimesSRing<int64_t, int64_t>>(A2, ones);
+            int64_t localsq = 0;
+            for (int64_t v : A.seq().numx) localsq += v * v;
+            ok = ok && sq.Reduce(std::plus<int64_t>(), (int64_t)0) == grid->SumWorld(localsq);
+            if (grid->GetSize() == 1) {
+                // host replay of (1) with the semiring's own functors
+                const SpDCCols<int64_t, int64_t>& t = A.seq();
+                std::vector<int64_t> ref((size_t)m, MinPlusSRing<int64_t, int64_t>::id());
+                for (size_t c = 0; c < t.jc.size(); ++c)
+                    for (int64_t p = t.cp[c]; p < t.cp[c + 1]; ++p)
+                        MinPlusSRing<int64_t, int64_t>::axpy(t.numx[(size_t)p], x.GetLocArr()[t.jc[c]], ref[(size_t)t.ir[(size_t)p]]);
+                for (int64_t i = 0; i < m; ++i) ok = ok && ref[(size_t)i] == y.GetLocArr()[i];
+            }
+            ok = grid->MinWorld(ok ? 1 : 0) == 1;
+            if (ok) SpParHelper::Print("SpMV and dense epilogues working correctly\n");
+            else { SpParHelper::Print("ERROR in SpMV / epilogues, go fix it!\n"); rc = 1; }
         } else if (mode == "mtx") {
             typedef SpParMat<int64_t, double, SpDCCols<int64_t, double>> PSpMat_Double;
             std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));

@@ -7,6 +7,7 @@
 #include "Semirings.h"
 #include "CommGrid.h"
 #include "SpTuples.h"
+#include "FullyDistVec.h"
 #include "SpParMat.h"
 #include "DenseParMat.h"
 #include "ParFriends.h"

@@ -12,9 +12,13 @@
 #include <memory>
 #include <vector>
 #include "CommGrid.h"
+#include "FullyDistVec.h"
 #include "promote.h"
 
 namespace combblas {
+
+template <class IU, class NU, class DER>
+class SpParMat;
 
 template <class IT, class NT>
 class DenseParMat {
@@ -45,6 +49,42 @@ public:
         Block(grows_, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), rowOffset, l);
         Block(gcols_, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), colOffset, l);
     }
+    // Fold along a dimension into a distributed vector (reference DenseParMat.cpp:36-130): dim == Row folds every row over
+    // its columns (result of length grows()), dim == Column folds every column over its rows (length gcols()).  Local
+    // fold first, then the partial vectors of the processes that share the rows (columns) in grid order, as the
+    // reference's MPI_Reduce_scatter does; the result is laid out as a FullyDistVec.  Host-side, like the reference.
+    template <typename _BinaryOperation>
+    FullyDistVec<IT, NT> Reduce(Dim dim, _BinaryOperation op, NT identity) const {
+        const int pr = commGrid->GetGridRows(), pc = commGrid->GetGridCols();
+        std::vector<ST> part(dim == Row ? (size_t)m : (size_t)n, (ST)identity);
+        for (IT i = 0; i < m; ++i)
+            for (IT j = 0; j < n; ++j) {
+                ST& dst = part[dim == Row ? (size_t)i : (size_t)j];
+                dst = (ST)op((NT)dst, (NT)(*this)(i, j));
+            }
+        std::vector<std::vector<char>> all;
+        cb_host_allgatherv(part.data(), part.size() * sizeof(ST), all);
+        const IT glen = dim == Row ? grows() : gcols();
+        std::vector<NT> whole((size_t)glen, identity);
+        IT off = 0;
+        for (int b = 0; b < (dim == Row ? pr : pc); ++b) {              // block b of the result = fold over the processes holding it
+            IT blen = 0;
+            for (int q = 0; q < (dim == Row ? pc : pr); ++q) {
+                const std::vector<char>& buf = all[(size_t)(dim == Row ? commGrid->GetRank(b, q) : commGrid->GetRank(q, b))];
+                blen = (IT)(buf.size() / sizeof(ST));
+                const ST* v = reinterpret_cast<const ST*>(buf.data());
+                for (IT i = 0; i < blen; ++i) whole[(size_t)(off + i)] = op(whole[(size_t)(off + i)], (NT)v[i]);
+            }
+            off += blen;
+        }
+        FullyDistVec<IT, NT> out(commGrid);
+        out.Scatter(whole);
+        return out;
+    }
+    // add a sparse matrix with the same distribution (reference DenseParMat.cpp:132-146, Dcsc::UpdateDense)
+    template <typename DER>
+    DenseParMat<IT, NT>& operator+=(const SpParMat<IT, NT, DER>& rhs);
+
     static void Block(IT total, int nb, int b, IT& start, IT& len) {
         const IT per = total / nb;
         start = (IT)b * per;

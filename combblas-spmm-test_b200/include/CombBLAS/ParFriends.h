@@ -10,6 +10,7 @@
 #define CB_PARFRIENDS_H
 
 #include "DenseParMat.h"
+#include "FullyDistVec.h"
 #include "Semirings.h"
 #include "SpParMat.h"
 
@@ -57,6 +58,61 @@ DenseParMat<IU, typename promote_trait<NUM, NUV>::T_promote> SpMM(const SpParMat
     cb_dense_free(dX);
     cb_dense_free(dY);
     return Y;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense SpMV: y = A (x).(+) x with a FullyDistVec operand and result, the reference's SpMV<SR>(A, x)
+// (include/CombBLAS/ParFriends.h:1924-1996).  The reference moves x to the transposed process (TransposeVector), gathers
+// it along the processor column, runs dcsc_gespmv on an id()-filled local y (SR::axpy, Friends.h:63-78) and reduces y along
+// the processor row.  Here the vector is handed to the SUMMA engine as an n x 1 panel (it lives on the last processor
+// column of the DenseParMat distribution), the multiply runs on the GPUs, and the result is cut back into FullyDistVec
+// pieces.  Starting from id() matters for one semiring: SelectMax<bool,T> yields max(-1, x) here, not x, for x < -1.
+template <typename IU, typename NUM, typename NUV, typename UDER>
+bool CheckSpMVCompliance(const SpParMat<IU, NUM, UDER>& A, const FullyDistVec<IU, NUV>& x) {         // ParFriends.h:1350-1366
+    if (*(A.getcommgrid()) != *(x.getcommgrid())) {
+        SpParHelper::Print("Grids are not comparable for SpMV\n");
+        MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+        return false;
+    }
+    const IU ncol = A.getncol(), len = x.TotalLength();
+    if (ncol != len) {
+        std::ostringstream outs;
+        outs << "Can not multiply, dimensions does not match" << std::endl << ncol << " != " << len << std::endl;
+        SpParHelper::Print(outs.str());
+        MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+        return false;
+    }
+    return true;
+}
+
+template <typename SR, typename IU, typename NUM, typename NUV, typename UDER>
+FullyDistVec<IU, typename promote_trait<NUM, NUV>::T_promote> SpMV(const SpParMat<IU, NUM, UDER>& A, const FullyDistVec<IU, NUV>& x) {
+    typedef typename promote_trait<NUM, NUV>::T_promote T_promote;
+    static_assert(std::is_same<T_promote, NUV>::value, "the vector must already have the promoted type");
+    CheckSpMVCompliance(A, x);
+    std::shared_ptr<CommGrid> grid = A.getcommgrid();
+    const IU gm = A.getnrow(), gn = A.getncol();
+    // x as an n x 1 panel: rows block myprocrow, the single column belongs to the last processor column
+    const std::vector<NUV> xw = x.Gather();
+    DenseParMat<IU, NUV> X = DenseParMat<IU, NUV>::Global(NUV(), grid, gn, 1);
+    IU r0, c0;
+    X.GetPlaceInGlobalGrid(gn, (IU)1, r0, c0);
+    if (X.getlocalcols() == 1)
+        for (IU i = 0; i < X.getlocalrows(); ++i) X(i, 0) = xw[(size_t)(r0 + i)];
+    DenseParMat<IU, T_promote> Y = SpMM<SR>(A, X);
+    // row blocks of y sit on the last processor column; everyone assembles the vector and keeps its FullyDistVec piece
+    std::vector<std::vector<char>> all;
+    cb_host_allgatherv(Y.data(), (size_t)Y.getlocalrows() * (size_t)Y.getlocalcols() * sizeof(T_promote), all);
+    std::vector<T_promote> yw;
+    yw.reserve((size_t)gm);
+    for (int i = 0; i < grid->GetGridRows(); ++i) {
+        const std::vector<char>& b = all[(size_t)grid->GetRank(i, grid->GetGridCols() - 1)];
+        const T_promote* v = reinterpret_cast<const T_promote*>(b.data());
+        for (size_t q = 0; q < b.size() / sizeof(T_promote); ++q) yw.push_back(SR::add(SR::id(), v[q]));     // y started as id()
+    }
+    FullyDistVec<IU, T_promote> y(grid);
+    y.Scatter(yw);
+    return y;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

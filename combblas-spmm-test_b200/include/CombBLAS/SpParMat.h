@@ -18,6 +18,7 @@
 #include <memory>
 #include <sstream>
 #include "CommGrid.h"
+#include "DenseParMat.h"
 #include "SpTuples.h"
 
 namespace combblas {
@@ -146,6 +147,27 @@ public:
         return commGrid->MinWorld(local) == 1;
     }
 
+    // scale every stored entry by the dense entry at its position (reference SpParMat.cpp:2817-2850, Dcsc::EWiseScale);
+    // the device mirror is rebuilt at the next multiply
+    void EWiseScale(const DenseParMat<IT, NT>& rhs) {
+        if (*commGrid != *rhs.getcommgrid()) {
+            SpParHelper::Print("Grids are not comparable elementwise multiplication\n");
+            MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+        }
+        DER& t = seq();
+        if ((IT)t.getnrow() != rhs.getlocalrows() || (IT)t.getncol() != rhs.getlocalcols()) {
+            SpParHelper::Print("Local dimensions do not match for EWiseScale\n");
+            MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+        }
+        SpTuples<LocalIT, NT> tup = TilesToTuples(t);
+        for (int64_t p = 0; p < tup.getnnz(); ++p)
+            std::get<2>(tup.tuples[(size_t)p]) = (NT)(tup.numvalue(p) * rhs(tup.rowindex(p), tup.colindex(p)));
+        DER* scaled = new DER(tup, false);
+        const IT keep_m = gm, keep_n = gn;
+        Release();
+        spSeq = scaled; gm = keep_m; gn = keep_n;
+    }
+
     // Owner of global entry (grow, gcol) and its local indices (SpParMat.cpp:5066-5096)
     template <typename LIT>
     int Owner(IT total_m, IT total_n, IT grow, IT gcol, LIT& lrow, LIT& lcol) const {
@@ -269,6 +291,23 @@ private:
     int64_t dnnz = 0;
     bool devvals = false;
 };
+
+template <class IT, class NT>
+template <typename DER>
+DenseParMat<IT, NT>& DenseParMat<IT, NT>::operator+=(const SpParMat<IT, NT, DER>& rhs) {
+    if (*commGrid != *rhs.getcommgrid()) {
+        SpParHelper::Print("Grids are not comparable elementwise addition\n");
+        MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+    }
+    const DER& t = rhs.seq();
+    if ((IT)t.getnrow() != m || (IT)t.getncol() != n) {
+        SpParHelper::Print("Local dimensions do not match for DenseParMat += SpParMat\n");
+        MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+    }
+    auto tup = TilesToTuples(t);
+    for (int64_t p = 0; p < tup.getnnz(); ++p) (*this)(tup.rowindex(p), tup.colindex(p)) += (ST)tup.numvalue(p);
+    return *this;
+}
 
 }  // namespace combblas
 #endif

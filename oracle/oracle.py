@@ -285,6 +285,17 @@ def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_dis
     return Y, sec, out
 
 
+def ref_grid_layout(glen, ranks):
+    """FullyDistVec layout of a length-glen vector as the reference computes it on sqrt(ranks)^2 processes:
+    dict of int arrays until[rank], len[rank], owner[index], lind[index]."""
+    out = {}
+    for line in _run_grid(["layout", str(glen)], ranks).splitlines():
+        key, *vals = line.split()
+        if key in ("until", "len", "owner", "lind"):
+            out[key] = np.array([int(v) for v in vals], np.int64)
+    return out
+
+
 def ref_grid_mm(path, ranks, X):
     """BASELINE config C1 on sqrt(ranks)^2 processes: the reference reads the Matrix Market file itself (ParallelReadMM) and
     multiplies by X (n x k float64) with Mult_AnXBn_Synch.  Returns (Y, report line)."""

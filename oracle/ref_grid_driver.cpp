@@ -11,6 +11,8 @@
 //   cbref_grid torus
 //       the program of Applications/SpMMError.cpp (that file no longer compiles against its own headers: it omits the
 //       NUO/UDERO template arguments, ParFriends.h:1004-1005); same steps with the arguments spelled out.
+//   cbref_grid layout <glen>
+//       the FullyDistVec distribution of a vector of that length: LengthUntil / MyLocLength per rank, Owner of every index
 //   cbref_grid mm <file.mtx> <k> <dir>
 //       BASELINE config C1 on a grid: ParallelReadMM by the reference itself, then x dense k columns fp64 (X from <dir>/X.bin)
 //   cbref_grid spmm <key> <via> <dir>
@@ -239,6 +241,31 @@ int run_mm(const std::string& file, int64_t k, const std::string& dir) {
     return 0;
 }
 
+// the FullyDistVec distribution as the reference computes it (FullyDist.h:107-260), for every rank and every index
+int run_layout(int64_t glen) {
+    std::shared_ptr<CommGrid> grid(new CommGrid(MPI_COMM_WORLD, 0, 0));
+    FullyDistVec<int64_t, int64_t> v(grid, glen, 0);
+    int rank, p;
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &p);
+    long long mine[2] = {(long long)v.LengthUntil(), (long long)v.MyLocLength()};
+    std::vector<long long> all((size_t)2 * p);
+    MPI_Allgather(mine, 2, MPI_LONG_LONG, all.data(), 2, MPI_LONG_LONG, MPI_COMM_WORLD);
+    if (rank == 0) {
+        std::printf("until");
+        for (int r = 0; r < p; ++r) std::printf(" %lld", all[2 * r]);
+        std::printf("\nlen");
+        for (int r = 0; r < p; ++r) std::printf(" %lld", all[2 * r + 1]);
+        std::printf("\nowner");
+        std::vector<int64_t> lind((size_t)glen);
+        for (int64_t g = 0; g < glen; ++g) std::printf(" %d", v.Owner(g, lind[(size_t)g]));
+        std::printf("\nlind");
+        for (int64_t g = 0; g < glen; ++g) std::printf(" %lld", (long long)lind[(size_t)g]);
+        std::printf("\n");
+    }
+    return 0;
+}
+
 int run_torus() {
     typedef int64_t ValueType;
     typedef SpDCCols<int64_t, ValueType> DCColsType;
@@ -276,6 +303,7 @@ int main(int argc, char* argv[]) {
     {
         const std::string mode = argc > 1 ? argv[1] : "";
         if (mode == "torus") rc = run_torus();
+        else if (mode == "layout" && argc >= 3) rc = run_layout(std::atoll(argv[2]));
         else if (mode == "mm" && argc >= 5) rc = run_mm(argv[2], std::atoll(argv[3]), argv[4]);
         else if (mode == "spmm" && argc >= 5) {
             const std::string s = argv[2], dir = argv[4];
@@ -298,7 +326,7 @@ int main(int argc, char* argv[]) {
             CASE("select_max:bool:i64", SelectMaxSRing, bool, int64_t)
 #undef CASE
             if (rc == 2) std::fprintf(stderr, "cbref_grid: unknown key %s\n", s.c_str());
-        } else if (!mode.empty()) std::fprintf(stderr, "usage: cbref_grid torus | mm <file.mtx> <k> <dir> | spmm <key> <via> <dir>\n");
+        } else if (!mode.empty()) std::fprintf(stderr, "usage: cbref_grid torus | layout <glen> | mm <file.mtx> <k> <dir> | spmm <key> <via> <dir>\n");
     }
     MPI_Finalize();
     return rc;

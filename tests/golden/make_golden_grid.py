@@ -9,6 +9,7 @@ Contents (results of the reference's own multi-proce
   <case>_p4 / <case>_p9          Y of Mult_AnXBn_Synch on 2x2 / 3x3 processes for the operands of tests/summa_worker.py
                                  (R-MAT scale 9, edge factor 8, seed 3, ragged m = n-5, n = n-3, k = 13)
   <case>_p4_spmv                 the same product through k x SpMV<SR>(A, FullyDistVec) on 2x2 processes
+  layout_<glen>_p<p>_{until,len,owner,lind}   the FullyDistVec distribution computed by the reference's FullyDist.h
   hepth_p4, hepth_p4_report      BASELINE config C1 on 2x2 processes: Applications/hep-th.mtx read by the reference's own
                                  ParallelReadMM on four ranks, x X(k=16, fp64, seed 42) through Mult_AnXBn_Synch
 Only numeric outputs are stored; inputs are regenerated from the counter-based generators at test time.
@@ -32,6 +33,11 @@ CASES = {  # the cases of tests/summa_worker.py
     "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"),
     "or_and": (O.OR_AND, None, np.uint8, "value"),
 }
+
+
+# FullyDistVec layouts stored from the reference: (global length, processes); short lengths hit the "everything on the last
+# processor row / column" branches of FullyDist::Owner (FullyDist.h:117-146)
+LAYOUTS = [(11, 4), (8361, 4), (100, 9), (5, 9), (2, 9), (1000, 16)]
 
 
 def operands(case, scale=SCALE, k=K):
@@ -60,6 +66,9 @@ def main():
             out[f"{case}_p{p}"] = Y
         if X.dtype != np.uint8:
             out[f"{case}_p4_spmv"] = O.ref_grid_spmm(sr, 4, m, n, I, J, V, X, via=1)[0]
+    for glen, p in LAYOUTS:
+        for key, val in O.ref_grid_layout(glen, p).items():
+            out[f"layout_{glen}_p{p}_{key}"] = val
     hep = np.load(os.path.join(OUT, "hepth.npz"))
     Y, report = O.ref_grid_mm("/root/reference/Applications/hep-th.mtx", 4, O.dense_operand(int(hep["n"]), 16, 42, np.float64))
     out["hepth_p4"], out["hepth_p4_report"] = Y, np.array(report)

@@ -1,0 +1,234 @@
+// TEST INFRASTRUCTURE ONLY: a host-memory stand-in for libcombblas_b200.so, so that the C++ HOST LAYER
+// (combblas-spmm-test_b200/include/CombBLAS/*.h: SpParMat, DenseParMat, FullyDistVec, SpMM, SpMV, Mult_AnXBn_Synch, ...)
+// and its driver can be exercised by the CPU test suite on a machine without a GPU.  tests/test_host_mock_cpu.py compiles
+// the driver against THIS library in a temporary directory; nothing in the product links, loads or ships it, and the real
+// library still has no CPU path (tests/test_abi_cpu.py).  Single process only (1 x 1 grid); multiplies are naive loops over
+// the semiring definitions of include/CombBLAS/Semirings.h - the driver's own replays and the GPU suite are the checkers of
+// arithmetic, this only has to be a faithful enough ABI for the host logic to run.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+#include "combblas_b200.h"
+
+struct cb_ctx { std::string err; int64_t launches = 0; };
+struct cb_tile {
+    int64_t m = 0, n = 0;
+    int val_dtype = CB_PATTERN;
+    std::vector<int64_t> rowptr, col;
+    std::vector<unsigned char> vals;       // nnz elements of val_dtype
+    bool view = false;
+};
+struct cb_dense { int64_t rows = 0, cols = 0; int dtype = CB_F32; std::vector<unsigned char> data; };
+
+static std::string g_err;
+static size_t esize(int dt) { return dt == CB_F32 || dt == CB_I32 ? 4 : dt == CB_F64 || dt == CB_I64 ? 8 : dt == CB_U8 ? 1 : 0; }
+static int fail(cb_ctx* c, int st, const std::string& msg) { g_err = msg; if (c) c->err = msg; return st; }
+
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+template <class T>
+static void put_value(std::vector<unsigned char>& out, uint64_t h) {
+    T v;
+    if (std::is_floating_point<T>::value) v = (T)((double)((h >> 11) | 1) / 9007199254740992.0);
+    else v = (T)(1 + (h >> 8) % 100);
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+    out.insert(out.end(), p, p + sizeof(T));
+}
+
+// rows of triples (r, c, value bytes) -> CSR with ascending columns
+static void build_csr(cb_tile* t, std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>>& trip) {
+    std::sort(trip.begin(), trip.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    t->rowptr.assign((size_t)t->m + 1, 0);
+    for (auto& e : trip) {
+        ++t->rowptr[(size_t)e.first.first + 1];
+        t->col.push_back(e.first.second);
+        t->vals.insert(t->vals.end(), e.second.begin(), e.second.end());
+    }
+    for (int64_t r = 0; r < t->m; ++r) t->rowptr[(size_t)r + 1] += t->rowptr[(size_t)r];
+}
+
+template <class T> static T sr_id(int sr) { return sr == CB_MIN_PLUS ? std::numeric_limits<T>::max() : sr == CB_MAX_SEL2ND ? (T)-1 : (T)0; }
+template <class T>
+static T sr_add(int sr, T a, T b) {
+    switch (sr) {
+        case CB_MIN_PLUS: return std::min(a, b);
+        case CB_MAX_SEL2ND: return std::max(a, b);
+        case CB_OR_AND: return (T)((a != 0) || (b != 0));
+        default: return (T)(a + b);
+    }
+}
+template <class T>
+static T sr_mul(int sr, bool has_a, T a, bool a_true, T x) {
+    switch (sr) {
+        case CB_MIN_PLUS: { const T inf = std::numeric_limits<T>::max(); return (a == inf || x == inf) ? inf : (T)(a + x); }
+        case CB_MAX_SEL2ND: return x;
+        case CB_OR_AND: return (T)(a_true && x != 0);
+        default: return has_a ? (T)(a * x) : (a_true ? x : (T)0);
+    }
+}
+
+template <class T>
+static void multiply(const cb_tile* t, const cb_dense* X, cb_dense* Y, int sr, bool accumulate) {
+    const T* x = reinterpret_cast<const T*>(X->data.data());
+    T* y = reinterpret_cast<T*>(Y->data.data());
+    const int64_t k = X->cols;
+    const bool same = t->val_dtype == X->dtype && t->val_dtype != CB_U8;
+    for (int64_t r = 0; r < t->m; ++r)
+        for (int64_t j = 0; j < k; ++j) {
+            bool first = true;
+            T acc = sr_id<T>(sr);
+            for (int64_t p = t->rowptr[(size_t)r]; p < t->rowptr[(size_t)r + 1]; ++p) {
+                T a = T();
+                bool a_true = true;
+                if (same) std::memcpy(&a, t->vals.data() + (size_t)p * sizeof(T), sizeof(T));
+                else if (t->val_dtype == CB_U8) a_true = t->vals[(size_t)p] != 0;
+                const T prod = sr_mul<T>(sr, same, a, a_true, x[(size_t)t->col[(size_t)p] * (size_t)k + (size_t)j]);
+                acc = first ? prod : sr_add<T>(sr, prod, acc);       // the first product is stored (mtSpGEMM.h:403-414)
+                first = false;
+            }
+            T& out = y[(size_t)r * (size_t)k + (size_t)j];
+            if (accumulate) { if (!first) out = sr_add<T>(sr, out, acc); }
+            else out = acc;
+        }
+}
+
+extern "C" {
+
+int cb_abi_version(void) { return CB_ABI_VERSION; }
+int cb_device_count(int* c) { *c = 1; return CB_OK; }
+int cb_comm_unique_id(void* id) { std::memset(id, 0, 128); return CB_OK; }
+int cb_ctx_create_grid(int, int rank, int nranks, int pr, int pc, const void*, cb_ctx** ctx) {
+    if (nranks != 1 || rank != 0 || pr != 1 || pc != 1) return fail(nullptr, CB_ERR_INVALIDPARAMS, "mock ABI: one process only");
+    *ctx = new cb_ctx();
+    return CB_OK;
+}
+int cb_ctx_create(int d, cb_ctx** ctx) { return cb_ctx_create_grid(d, 0, 1, 1, 1, nullptr, ctx); }
+int cb_ctx_destroy(cb_ctx* c) { delete c; return CB_OK; }
+int cb_ctx_grid(const cb_ctx*, int* rank, int* pr, int* pc, int* r, int* c) { *rank = 0; *pr = *pc = 1; *r = *c = 0; return CB_OK; }
+int cb_ctx_sync(cb_ctx*) { return CB_OK; }
+void* cb_ctx_stream(cb_ctx*) { return nullptr; }
+const char* cb_last_error(const cb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+const char* cb_status_string(int s) { return s == CB_OK ? "ok" : "mock ABI error"; }
+int cb_comm_allreduce_i64(cb_ctx*, int, int, int64_t*, int) { return CB_OK; }       // one process: the value is the result
+int64_t cb_launch_count(const cb_ctx* c) { return c->launches; }
+
+int cb_tile_upload_csc(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int64_t nzc, const void* cp, const void* jc, const void* ir,
+                       const void* numx, int idt, int vdt, cb_tile** tile) {
+    auto idx = [&](const void* a, int64_t i) { return idt == CB_I32 ? (int64_t)((const int32_t*)a)[i] : ((const int64_t*)a)[i]; };
+    cb_tile* t = new cb_tile();
+    t->m = m; t->n = n; t->val_dtype = vdt;
+    const size_t es = esize(vdt == CB_PATTERN ? CB_U8 : vdt);
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    const int64_t ncols = jc ? nzc : n;
+    for (int64_t c = 0; c < ncols; ++c)
+        for (int64_t p = idx(cp, c); p < idx(cp, c + 1); ++p) {
+            std::vector<unsigned char> v;
+            if (vdt != CB_PATTERN) v.assign((const unsigned char*)numx + (size_t)p * es, (const unsigned char*)numx + (size_t)(p + 1) * es);
+            trip.push_back({{idx(ir, p), jc ? idx(jc, c) : c}, v});
+        }
+    if ((int64_t)trip.size() != nz) { delete t; return fail(ctx, CB_ERR_INVALIDPARAMS, "mock ABI: nz does not match the column pointers"); }
+    build_csr(t, trip);
+    *tile = t;
+    return CB_OK;
+}
+int cb_tile_free(cb_tile* t) { delete t; return CB_OK; }
+int cb_tile_info(const cb_tile* t, int64_t info[8]) {
+    std::memset(info, 0, 8 * sizeof(int64_t));
+    info[0] = (int64_t)t->col.size(); info[1] = t->m; info[2] = t->n;
+    return CB_OK;
+}
+int cb_tile_pattern_view(const cb_tile* t, cb_tile** view) {
+    cb_tile* v = new cb_tile(*t);
+    v->val_dtype = CB_PATTERN; v->vals.clear(); v->view = true;
+    *view = v;
+    return CB_OK;
+}
+int cb_tile_download_csr(cb_tile* t, int64_t* rowptr, int64_t* colidx, void* vals) {
+    if (rowptr) std::copy(t->rowptr.begin(), t->rowptr.end(), rowptr);
+    if (colidx) std::copy(t->col.begin(), t->col.end(), colidx);
+    if (vals && !t->vals.empty()) std::memcpy(vals, t->vals.data(), t->vals.size());
+    return CB_OK;
+}
+int cb_gen_rmat_tile(cb_ctx*, int scale, int edgefactor, uint64_t seed, const double*, int symmetric, int64_t row0, int64_t m, int64_t col0,
+                     int64_t n, int val_dtype, uint64_t val_seed, cb_tile** tile) {
+    // NOT the product's generator: any skewed random graph will do for host-logic tests
+    const int64_t N = (int64_t)1 << scale;
+    std::map<std::pair<int64_t, int64_t>, int> seen;
+    for (int64_t e = 0; e < (int64_t)edgefactor * N; ++e) {
+        const uint64_t h = splitmix64(seed * 0x100000001B3ULL ^ (uint64_t)e);
+        int64_t i = (int64_t)((h & 0xffffffffu) % (uint64_t)N), j = (int64_t)((h >> 32) % (uint64_t)N);
+        if (h & 1) i = i % std::max<int64_t>(1, N / 8);      // a few heavy rows
+        if (i == j) continue;
+        seen[{i, j}] = 1;
+        if (symmetric) seen[{j, i}] = 1;
+    }
+    cb_tile* t = new cb_tile();
+    t->m = m; t->n = n; t->val_dtype = val_dtype;
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    for (auto& kv : seen) {
+        const int64_t i = kv.first.first, j = kv.first.second;
+        if (i < row0 || i >= row0 + m || j < col0 || j >= col0 + n) continue;
+        std::vector<unsigned char> v;
+        const uint64_t h = splitmix64(val_seed * 0x100000001B3ULL ^ (uint64_t)(i * N + j));
+        switch (val_dtype) {
+            case CB_F32: put_value<float>(v, h); break;
+            case CB_F64: put_value<double>(v, h); break;
+            case CB_I32: put_value<int32_t>(v, h); break;
+            case CB_I64: put_value<int64_t>(v, h); break;
+            case CB_U8: v.push_back(1); break;
+            default: break;
+        }
+        trip.push_back({{i - row0, j - col0}, v});
+    }
+    build_csr(t, trip);
+    *tile = t;
+    return CB_OK;
+}
+
+int cb_dense_alloc(cb_ctx*, int64_t rows, int64_t cols, int dtype, cb_dense** d) {
+    cb_dense* x = new cb_dense();
+    x->rows = rows; x->cols = cols; x->dtype = dtype;
+    x->data.assign((size_t)rows * (size_t)cols * esize(dtype), 0);
+    *d = x;
+    return CB_OK;
+}
+int cb_dense_free(cb_dense* d) { delete d; return CB_OK; }
+int cb_dense_upload(cb_dense* d, const void* host, int64_t ld) {
+    const size_t es = esize(d->dtype);
+    for (int64_t r = 0; r < d->rows; ++r) std::memcpy(d->data.data() + (size_t)r * (size_t)d->cols * es, (const char*)host + (size_t)r * (size_t)ld * es, (size_t)d->cols * es);
+    return CB_OK;
+}
+int cb_dense_download(cb_dense* d, void* host, int64_t ld) {
+    const size_t es = esize(d->dtype);
+    for (int64_t r = 0; r < d->rows; ++r) std::memcpy((char*)host + (size_t)r * (size_t)ld * es, d->data.data() + (size_t)r * (size_t)d->cols * es, (size_t)d->cols * es);
+    return CB_OK;
+}
+
+int cb_spmm_local(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int sr, int accumulate) {
+    if (X->rows != t->n || Y->rows != t->m || X->cols != Y->cols) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: dimension mismatch");
+    if (sr == CB_PLUS_TIMES && X->dtype == CB_U8) sr = CB_OR_AND;
+    ++ctx->launches;
+    switch (X->dtype) {
+        case CB_F32: multiply<float>(t, X, Y, sr, accumulate != 0); break;
+        case CB_F64: multiply<double>(t, X, Y, sr, accumulate != 0); break;
+        case CB_I32: multiply<int32_t>(t, X, Y, sr, accumulate != 0); break;
+        case CB_I64: multiply<int64_t>(t, X, Y, sr, accumulate != 0); break;
+        case CB_U8: multiply<uint8_t>(t, X, Y, sr, accumulate != 0); break;
+        default: return fail(ctx, CB_ERR_UNSUPPORTED, "mock ABI: dtype");
+    }
+    return CB_OK;
+}
+int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int sr, int64_t, int64_t, int64_t) {
+    return cb_spmm_local(ctx, t, X, Y, sr, 0);
+}
+
+}  // extern "C"

@@ -81,6 +81,30 @@ def test_driver_sparse_rhs_min_plus_structure_and_values():
 
 
 @pytest.mark.gpu
+def test_driver_spmv_fullydistvec_and_dense_epilogues():
+    # SpMV<SR>(A, FullyDistVec) under MinPlus / PlusTimes / SelectMax, DenseParMat::Reduce,
+    # DenseParMat += SpParMat, SpParMat::EWiseScale; every result checked inside the driver
+    build()
+    r = subprocess.run([DRIVER, "spmv", "12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SpMV and dense epilogues working correctly" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_spmv_on_a_process_grid():
+    import torch
+    from tests.test_summa_cpu import free_port
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    build()
+    n = 4 if torch.cuda.device_count() >= 4 else 2
+    grid = ["2", "2"] if n == 4 else ["1", "2"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), DRIVER, "spmv", "12"] + grid
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SpMV and dense epilogues working correctly" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_driver_spmmerror_program_on_a_2x2_grid():
     import torch
     from tests.test_summa_cpu import free_port

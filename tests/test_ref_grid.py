@@ -71,6 +71,23 @@ def test_hepth_config_c1_on_2x2_processes():
     assert close(hep["Y"], gold)                                                                              # 1 process vs 4 processes
 
 
+def test_fullydistvec_layout_matches_reference():
+    # the host layer's FullyDistLayout (include/CombBLAS/FullyDistVec.h) against LengthUntil / MyLocLength / Owner of the
+    # reference's FullyDist.h evaluated on real process grids
+    from tests.golden.make_golden_grid import LAYOUTS
+    exe = os.path.join(ROOT, "combblas-spmm-test_b200", "host", "host_logic_test")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "combblas-spmm-test_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    g = np.load(GOLD)
+    for glen, p in LAYOUTS:
+        q = int(round(p ** 0.5))
+        r = subprocess.run([exe, "fdv", str(glen), str(q), str(q)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        got = {l.split()[0]: np.array([int(v) for v in l.split()[1:]], np.int64) for l in r.stdout.splitlines()}
+        for key in ("until", "len", "owner", "lind"):
+            assert np.array_equal(got[key], g[f"layout_{glen}_p{p}_{key}"]), (glen, p, key)
+
+
 def test_host_stage_loop_matches_reference_run_2x2():
     r = torchrun(4, ["--mode", "cpu", "--pr", "2", "--pc", "2", "--scale", str(SCALE), "--k", str(K), "--golden", GOLD,
                      "--cases", "minplus_i32,pt_f64,or_and"])
