@@ -329,10 +329,13 @@ def ref_best_time(semiring, m, n, I, J, V, X, cores, reps=1):
             best = (sec, f"1 process x {cores} OpenMP threads")
     if ref_grid_available() and cores >= 4:
         th = max(1, cores // 4)
-        for _ in range(max(1, reps)):
-            _, sec, _ = ref_grid_spmm(semiring, 4, m, n, I, J, V, X, via=0, threads=th, check_distribution=False)
-            if sec < best[0]:
-                best = (sec, f"2x2 processes x {th} OpenMP threads")
+        try:
+            for _ in range(max(1, reps)):
+                _, sec, _ = ref_grid_spmm(semiring, 4, m, n, I, J, V, X, via=0, threads=th, check_distribution=False)
+                if sec < best[0]:
+                    best = (sec, f"2x2 processes x {th} OpenMP threads")
+        except Exception as ex:      # the multi-process run is an extra; the 1-process time stands if it cannot run on this box
+            best = (best[0], best[1] + f" (2x2-process run unavailable: {type(ex).__name__})")
     return best
 
 
