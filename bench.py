@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--grid", default=None, help="process grid as PRxPC (default: as square as possible, pr <= pc)")
     ap.add_argument("--no-cache-a", action="store_true", help="re-broadcast the A parts every multiply like the reference does")
+    ap.add_argument("--ring", type=int, default=0, help="opt into the ring-pipelined variant of the local multiply (K2R): depth 8; off by default")
     ap.add_argument("--hub", default=None, help="opt into the hub variant of the local multiply (K2H): CLUSTER[:SLAB_BYTES], e.g. 4 or 4:128; "
                                                "off by default (validated on the emulator only so far)")
     args = ap.parse_args()
@@ -204,6 +205,8 @@ def main():
     if args.hub:
         hub_cluster, _, hub_slab = args.hub.partition(":")
         ctx.hub_config(1, int(hub_cluster), int(hub_slab or 0))
+    if args.ring:
+        ctx.ring_config(args.ring)
     if args.no_cache_a:
         ctx.summa_cache_a(False)
 
@@ -364,7 +367,7 @@ def main():
                        "grid": f"{pr}x{pc}", "stages": stages, "l2_policy": "inputs larger than L2 (A+X+Y per GPU >> 126 MB), no flush",
                        "generator": "counter-based Kronecker (csrc/cb_gen.cu), seed 0", "setup_s": round(t_setup, 3),
                        "chunks": tile.nchunks, "split_rows": tile.nsplit,
-                       "a_parts_cached": (world > 1 and not args.no_cache_a), "local_kernel": ("K2H hub variant " + args.hub) if args.hub else "K2",
+                       "a_parts_cached": (world > 1 and not args.no_cache_a), "local_kernel": " + ".join(([f"K2H hub variant {args.hub}"] if args.hub else []) + ([f"K2R ring depth {args.ring}"] if args.ring else [])) or "K2",
                        "summa_last_call_ms": None if summa_ms is None else {"stage_loop": summa_ms[0], "comm_stream_busy": summa_ms[1]}},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
             "checksum_first_rows": checksum,

@@ -9,6 +9,7 @@ struct cb_hub {
     uint16_t* hubslot = nullptr;      // [nnz] device
     int32_t* hubcols = nullptr;       // [nhub_max] device, rank -> column
     unsigned* counters = nullptr;     // [CB_HUB_MAX_SLABS] device, dynamic chunk counters of a launch
+    bool built = false;               // hub columns selected (a ring-only launch creates the struct for its counters alone)
     int nhub_max = 0;
     std::vector<int64_t> cum;         // [nhub_max] nonzeros in the columns of rank <= r
     int last_nhub = 0;
@@ -59,6 +60,7 @@ extern "C" int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs
 static int hub_build(cb_ctx* ctx, cb_tile* t) {
     cb_hub* h = new cb_hub();
     t->hub = h;
+    h->built = true;
     cb_scratch sc;
     int* d_counts = nullptr;
     uint16_t* d_rank = nullptr;
@@ -82,7 +84,6 @@ static int hub_build(cb_ctx* ctx, cb_tile* t) {
     for (int r = 0; r < h->nhub_max; ++r) rank_of[(size_t)hubcols[r]] = (uint16_t)r;
     CB_CUDA(ctx, cudaMalloc(&h->hubslot, (size_t)t->nnz * sizeof(uint16_t)));
     CB_CUDA(ctx, cudaMalloc(&h->hubcols, (size_t)h->nhub_max * sizeof(int32_t)));
-    CB_CUDA(ctx, cudaMalloc(&h->counters, (size_t)CB_HUB_MAX_SLABS * sizeof(unsigned)));
     CB_CUDA(ctx, cudaMemcpyAsync(d_rank, rank_of.data(), (size_t)t->n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->compute));
     CB_CUDA(ctx, cudaMemcpyAsync(h->hubcols, hubcols.data(), (size_t)h->nhub_max * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->compute));
     cb_hub_slot_kernel<<<blocks, 256, 0, ctx->compute>>>(t->colflag, t->nnz, d_rank, h->hubslot);
@@ -97,37 +98,57 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// Decide whether this multiply runs the hub variant and with which shape.  CB_OK with plan->nhub == 0 means "use K2".
+// Decide whether this multiply runs a persistent variant (hub rows resident: K2H; gathers through a shared-memory ring:
+// K2R; or both) and with which shape.  CB_OK with plan->active == false means "use K2".
 int cb_hub_plan(cb_ctx* ctx, const cb_tile* tile, int64_t row_bytes, cudaStream_t stream, cbk::HubPlan* plan) {
+    plan->active = false;
     plan->nhub = 0;
     static const int env_on = env_int("CB_SPMM_HUB", 0), env_cluster = env_int("CB_SPMM_HUB_CLUSTER", 4), env_slab = env_int("CB_SPMM_HUB_SLAB", 0),
-                     env_smem_kb = env_int("CB_SPMM_HUB_SMEM_KB", 200), env_cover_pct = env_int("CB_SPMM_HUB_MIN_COVER_PCT", 15);
-    const int on = ctx->hub_enable >= 0 ? ctx->hub_enable : env_on;
-    if (!on || !tile->owns_slab || tile->nnz == 0 || tile->n >= (1LL << 31) || row_bytes < 128 || stream != ctx->compute) return CB_OK;
+                     env_smem_kb = env_int("CB_SPMM_HUB_SMEM_KB", 200), env_cover_pct = env_int("CB_SPMM_HUB_MIN_COVER_PCT", 15),
+                     env_ring = env_int("CB_SPMM_RING", 0);
+    const int hub_on = ctx->hub_enable >= 0 ? ctx->hub_enable : env_on;
+    const int ring = ctx->ring_depth >= 0 ? ctx->ring_depth : env_ring;
+    if (ring != 0 && ring != CB_RING_D) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "ring variant: depth %d (this build has 0 or %d)", ring, CB_RING_D);
+    if ((!hub_on && !ring) || tile->nnz == 0 || tile->n >= (1LL << 31) || row_bytes < 128 || stream != ctx->compute) return CB_OK;
     int cluster = ctx->hub_cluster > 0 ? ctx->hub_cluster : env_cluster;
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "hub variant: cluster size %d (1, 2, 4 or 8)", cluster);
     int slab = ctx->hub_slab_bytes > 0 ? ctx->hub_slab_bytes : env_slab;
     if (slab == 0) slab = row_bytes <= 128 ? 128 : row_bytes <= 256 ? 256 : 512;
     if (slab != 128 && slab != 256 && slab != 512) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "hub variant: slab of %d bytes (128, 256 or 512)", slab);
     if ((row_bytes + slab - 1) / slab > CB_HUB_MAX_SLABS) return CB_OK;
-    cb_tile* mt = const_cast<cb_tile*>(tile);                  // derived data of an immutable tile, built once
-    if (!mt->hub) CB_TRY(hub_build(ctx, mt));
-    cb_hub* h = mt->hub;
-    if (h->nhub_max == 0) return CB_OK;
     const int smem_kb = std::min(std::max(env_smem_kb, 16), 224);
-    const int64_t slots = (int64_t)smem_kb * 1024 / slab;
-    const int nhub = (int)std::min<int64_t>(h->nhub_max, slots * cluster);
-    const double cover = (double)h->cum[(size_t)nhub - 1] / (double)tile->nnz;
-    h->last_nhub = 0;
-    h->last_cover = cover;
-    if (cover * 100.0 < (double)env_cover_pct) return CB_OK;    // too few nonzeros would be served on the SMs: K2 is the better kernel
-    h->last_nhub = nhub;
-    plan->cluster = cluster;
+    const size_t ring_bytes = (size_t)CB_HUB_BT * (size_t)ring * 16;                  // one ring of `ring` slots per virtual warp
+    if (ring_bytes + (size_t)slab > (size_t)smem_kb * 1024) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "ring variant: %zu bytes of rings do not fit in %d KB", ring_bytes, smem_kb);
+    int nhub = 0;
+    cb_hub* h = nullptr;
+    // hub rows: derived data of an immutable, owned tile, built once (views onto receive buffers are rebound per stage)
+    if (hub_on && tile->owns_slab) {
+        cb_tile* mt = const_cast<cb_tile*>(tile);
+        if (!mt->hub || !mt->hub->built) { cb_hub_release(mt); CB_TRY(hub_build(ctx, mt)); }
+        h = mt->hub;
+        if (h->nhub_max > 0) {
+            const int64_t slots = ((int64_t)smem_kb * 1024 - (int64_t)ring_bytes) / slab;
+            nhub = (int)std::min<int64_t>(h->nhub_max, slots * cluster);
+            const double cover = nhub > 0 ? (double)h->cum[(size_t)nhub - 1] / (double)tile->nnz : 0.0;
+            h->last_cover = cover;
+            if (cover * 100.0 < (double)env_cover_pct) nhub = 0;      // too few nonzeros would be served on the SMs
+            h->last_nhub = nhub;
+        }
+    }
+    if (nhub == 0 && !ring) return CB_OK;                              // nothing to gain over K2
+    cb_tile* mt = const_cast<cb_tile*>(tile);
+    if (!mt->hub) { mt->hub = new cb_hub(); }                          // ring without hub data still needs the chunk counters
+    h = mt->hub;
+    if (!h->counters) CB_CUDA(ctx, cudaMalloc(&h->counters, (size_t)CB_HUB_MAX_SLABS * sizeof(unsigned)));
+    plan->active = true;
+    plan->cluster = nhub > 0 ? cluster : 1;
     plan->slab_bytes = slab;
     plan->nhub = nhub;
-    plan->smem_bytes = (size_t)((nhub + cluster - 1) / cluster) * (size_t)slab;
-    plan->hubslot = h->hubslot;
-    plan->hubcols = h->hubcols;
+    plan->ring = ring;
+    plan->smem_bytes = (size_t)((nhub + plan->cluster - 1) / plan->cluster) * (size_t)slab + ring_bytes;
+    if (plan->smem_bytes == 0) plan->smem_bytes = 16;
+    plan->hubslot = nhub > 0 ? h->hubslot : nullptr;
+    plan->hubcols = nhub > 0 ? h->hubcols : nullptr;
     plan->counters = h->counters;
     return CB_OK;
 }
@@ -144,9 +165,16 @@ int cb_spmm_hub_config(cb_ctx* ctx, int enable, int cluster, int slab_bytes) {
     return CB_OK;
 }
 
+int cb_spmm_ring_config(cb_ctx* ctx, int depth) {
+    if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_ring_config: null ctx");
+    if (depth > 0 && depth != CB_RING_D) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_ring_config: depth %d (this build has 0 or %d)", depth, CB_RING_D);
+    ctx->ring_depth = depth < 0 ? -1 : depth;
+    return CB_OK;
+}
+
 int cb_spmm_hub_info(const cb_tile* tile, int64_t info[4]) {
     if (!tile || !info) return cb_fail(nullptr, CB_ERR_INVALIDPARAMS, "cb_spmm_hub_info: null argument");
-    info[0] = tile->hub ? 1 : 0;
+    info[0] = tile->hub && tile->hub->built ? 1 : 0;
     info[1] = tile->hub ? tile->hub->nhub_max : 0;
     info[2] = tile->hub ? tile->hub->last_nhub : 0;
     info[3] = tile->hub ? (int64_t)(tile->hub->last_cover * 1e6) : 0;

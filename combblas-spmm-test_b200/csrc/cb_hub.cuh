@@ -4,13 +4,22 @@
 
 #define CB_HUB_MAX_RANKS 65535      // ranks are 16-bit, 0xffff = "not a hub"
 #define CB_HUB_MAX_SLABS 8192
+// persistent variants: one CTA of CB_HUB_BT threads per SM; CB_RING_D row copies in flight per lane in the ring variant
+#ifndef CB_HUB_BT
+#define CB_HUB_BT 1024
+#endif
+#ifndef CB_RING_D
+#define CB_RING_D 8
+#endif
 
 namespace cbk {
-// shape of one hub launch, decided by cb_hub_plan; nhub == 0 means "run plain K2"
+// shape of one launch of the persistent variants, decided by cb_hub_plan; active == false means "run plain K2"
 struct HubPlan {
     int cluster = 1;                  // CTAs per cluster pooling their shared memory
     int slab_bytes = 0;               // bytes of a panel row handled per column slab: 128, 256 or 512
-    int nhub = 0;                     // hub ranks resident on the SMs
+    bool active = false;              // run a persistent variant (K2H / K2R) instead of K2
+    int nhub = 0;                     // hub ranks resident on the SMs (0 = none: the ring variant on a tile without hubs)
+    int ring = 0;                     // ring depth of the pipelined variant K2R (0 = K2H, gathers through registers)
     size_t smem_bytes = 0;            // dynamic shared memory per CTA
     const uint16_t* hubslot = nullptr;
     const int32_t* hubcols = nullptr;

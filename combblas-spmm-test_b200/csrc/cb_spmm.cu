@@ -82,9 +82,9 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
     p.Y = Y; p.ldy_bytes = ldy * (int64_t)es;
     p.total_row_bytes = (int)row_bytes;
     p.accumulate = accumulate;
-    cbk::HubPlan hub_plan;                        // opt-in hub variant (cb_hub.cu); nhub == 0 -> plain K2
+    cbk::HubPlan hub_plan;                        // opt-in persistent variants K2H / K2R (cb_hub.cu); inactive -> plain K2
     CB_TRY(cb_hub_plan(ctx, t, row_bytes, stream, &hub_plan));
-    if (hub_plan.nhub > 0) p.hub = &hub_plan;
+    if (hub_plan.active) p.hub = &hub_plan;
     switch (semiring) {
         case CB_PLUS_TIMES:
             return (dtype == CB_F32 || dtype == CB_F64) ? cb_launch_plus_times_f(dtype, akind, p) : cb_launch_plus_times_i(dtype, akind, p);

@@ -19,9 +19,6 @@
 #endif
 // hub variant: one persistent CTA of CB_HUB_BT threads per SM, CB_HUB_U row gathers in flight per lane.  1024 threads cap
 // the kernel at 64 registers, which U=4 fits without spills for every element type (U=8 spills 16-200 bytes on 4-byte types)
-#ifndef CB_HUB_BT
-#define CB_HUB_BT 1024
-#endif
 #ifndef CB_HUB_U
 #define CB_HUB_U 4
 #endif
@@ -82,8 +79,8 @@ static int launch_layout(const LaunchParams& p) {
     return launch_layout_f<Op, VW, R, U, MINB, false>(p);
 }
 
-// K2H: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
-template <class Op, int VW, bool FULL>
+// K2H / K2R: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
+template <class Op, int VW, bool FULL, bool RING>
 static int launch_hub_layout(const LaunchParams& p) {
     constexpr int BT = CB_HUB_BT;                                      // one CTA owns the SM
     constexpr int U = CB_HUB_U;
@@ -111,7 +108,7 @@ static int launch_hub_layout(const LaunchParams& p) {
     h.hubcols = hp.hubcols;
     h.nhub = hp.nhub;
     h.counter = hp.counters;
-    auto kernel = cb_spmm_hub_kernel<Op, VW, 1, U, BT, FULL>;
+    auto kernel = RING ? cb_spmm_ring_kernel<Op, VW, (CB_RING_D <= VW ? CB_RING_D : VW), BT, FULL> : cb_spmm_hub_kernel<Op, VW, 1, U, BT, FULL>;
     const unsigned nslabs = (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes);
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp.smem_bytes) != cudaSuccess) { cudaGetLastError(); return CB_HUB_FALLBACK; }
     cudaLaunchAttribute attr[1];
@@ -145,8 +142,9 @@ static int launch_hub_layout(const LaunchParams& p) {
 
 template <class Op, int VW>
 static int launch_hub_vw(const LaunchParams& p) {
-    if (p.total_row_bytes % (VW * 16) == 0) return launch_hub_layout<Op, VW, true>(p);
-    return launch_hub_layout<Op, VW, false>(p);
+    const bool full = p.total_row_bytes % (VW * 16) == 0;
+    if (p.hub->ring) return full ? launch_hub_layout<Op, VW, true, true>(p) : launch_hub_layout<Op, VW, false, true>(p);
+    return full ? launch_hub_layout<Op, VW, true, false>(p) : launch_hub_layout<Op, VW, false, false>(p);
 }
 
 template <class Op>

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "cb_common.cuh"
+#include "cb_hub.cuh"
 
 // ------------------------------------------------------------------------------------------ NCCL, by hand
 namespace {
@@ -134,7 +135,7 @@ void cb_summa_release(cb_ctx* ctx) {
     if (!s) return;
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->slotA[i]); cudaFree(s->slotX[i]);
-        if (s->view[i]) { cudaFree(s->view[i]->carry); delete s->view[i]; }
+        if (s->view[i]) { cudaFree(s->view[i]->carry); cb_hub_release(s->view[i]); delete s->view[i]; }
         if (s->ready[i]) cudaEventDestroy(s->ready[i]);
         if (s->done[i]) cudaEventDestroy(s->done[i]);
     }

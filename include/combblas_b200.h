@@ -185,6 +185,11 @@ int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t l
  * nonzeros they serve x 1e6}. */
 int cb_spmm_hub_config(cb_ctx* ctx, int enable, int cluster, int slab_bytes);
 int cb_spmm_hub_info(const cb_tile* tile, int64_t info[4]);
+/* Ring variant of the local multiply (K2R, same file) - OPT-IN, off by default, combinable with the hub variant.
+ * The row gathers are pipelined through a per-virtual-warp ring in shared memory with cp.async (no destination registers),
+ * so an SM keeps threads x depth x 16 bytes of gathers in flight instead of what its register file allows.  Results are
+ * bit-identical to the default kernel.  depth: 8 on (the depth this build instantiates), 0 off, -1 follow CB_SPMM_RING. */
+int cb_spmm_ring_config(cb_ctx* ctx, int depth);
 /* The hub selection rule as pure host arithmetic (no device needed): the max_hubs most frequent columns with at least
  * two nonzeros, most frequent first, ties by ascending column; cum[r] = nonzeros in the columns of rank <= r.
  * Returns the number of hubs written, or -1 on bad arguments. */

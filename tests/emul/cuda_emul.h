@@ -102,6 +102,27 @@ inline uint4 cb_ld_cluster16(uint32_t addr, uint32_t cta) {
     return u;
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+// cp.async: copies are DEFERRED until a wait_group retires their group, so a kernel that reads a ring slot before waiting
+// for it sees the stale fill pattern (0x5a) and fails the comparison, exactly the bug class the hardware would hide at random
+namespace emul {
+struct AsyncCopy { uint32_t dst; const void* src; };
+static thread_local std::vector<std::vector<AsyncCopy>> t_groups;      // committed, oldest first
+static thread_local std::vector<AsyncCopy> t_open;
+}  // namespace emul
+inline void cb_cp_async16(uint32_t smem_addr, const void* gptr) { emul::t_open.push_back(emul::AsyncCopy{smem_addr, gptr}); }
+inline void cb_cp_async_commit() { emul::t_groups.push_back(emul::t_open); emul::t_open.clear(); }
+template <int N>
+inline void cb_cp_async_wait() {
+    while ((int)emul::t_groups.size() > N) {
+        for (const emul::AsyncCopy& c : emul::t_groups.front()) std::memcpy(&emul::t_cta->smem.at(c.dst + 15) - 15, c.src, 16);   // .at(): bounds
+        emul::t_groups.erase(emul::t_groups.begin());
+    }
+}
+inline uint4 cb_lds16(uint32_t smem_addr) {
+    uint4 u;
+    std::memcpy(&u, &emul::t_cta->smem.at(smem_addr + 15) - 15, 16);
+    return u;
+}
 
 namespace emul {
 // run `kernel()` for every thread of a grid launched in clusters of `cs` CTAs along x with `smem_bytes` of dynamic shared

@@ -52,7 +52,7 @@ template <> double rnd_val<double>(std::mt19937& g) { return (double)(1 + g() % 
 // requires its result to be bit-identical to plain K2's.
 template <class Op, int VW, int R, int U, bool FULL>
 static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elements of Op::T per panel row */, int32_t L, int hub, unsigned seed,
-                     bool accumulate, int hub_cs = 0, int nhub = 0) {
+                     bool accumulate, int hub_cs = 0, int nhub = 0, int ring = 0) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     std::mt19937 g(seed);
@@ -129,8 +129,17 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         HubArgs h{};
         h.hubslot = hubslot.data(); h.hubcols = hubcols.data(); h.nhub = nhub; h.counter = counters.data();
         const size_t smem = (size_t)((nhub + hub_cs - 1) / hub_cs) * a.slab_bytes;
-        emul::launch_cluster(dim3((unsigned)(2 * hub_cs), grid.y), dim3(64), (unsigned)hub_cs, smem ? smem : 16,
-                             [&] { cb_spmm_hub_kernel<Op, VW, R, U, 64, FULL>(a, h); });
+        if (ring == 0)
+            emul::launch_cluster(dim3((unsigned)(2 * hub_cs), grid.y), dim3(64), (unsigned)hub_cs, smem ? smem : 16,
+                                 [&] { cb_spmm_hub_kernel<Op, VW, R, U, 64, FULL>(a, h); });
+        else {
+            // K2R: U doubles as the ring depth D here; shared memory = hub slots + one ring of D slots per virtual warp, exactly
+            constexpr int D = U <= VW ? U : VW;
+            if (nhub == 0) { h.hubslot = nullptr; h.hubcols = nullptr; }             // ring without hub data must not touch it
+            const size_t ring_bytes = (size_t)(64 / 32) * NV * D * a.slab_bytes;
+            emul::launch_cluster(dim3((unsigned)(2 * hub_cs), grid.y), dim3(64), (unsigned)hub_cs, smem + ring_bytes,
+                                 [&] { cb_spmm_ring_kernel<Op, VW, D, 64, FULL>(a, h); });
+        }
     } else {
         syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
     }
@@ -192,6 +201,16 @@ int main(int argc, char** argv) {
     bad += run_case<SelectMax<int64_t>, 8, 1, 8, false>("hub selectmax_i64 k=13 cs1", 45, 50, 13, 32, 45, 26 + sd, false, 1, 1);
     bad += run_case<OrAnd<A_PATTERN>, 8, 1, 8, false>("hub or_and VW8 cs2 nhub=0", 50, 40, 24, 32, 38, 27 + sd, false, 2, 0);
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 larger cs4", 400, 900, 64, 64, 700, 28 + sd, false, 4, 200);
+    // K2R, the ring-pipelined variant (cp.async into a per-virtual-warp ring), with and without resident hub rows
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("ring pt_f32 VW16 D8 cs1", 61, 97, 64, 32, 150, 31 + sd, false, 1, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("ring pt_f32 VW16 D4 hubs cs2 acc", 61, 97, 64, 32, 150, 32 + sd, true, 2, 33, 1);
+    bad += run_case<PlusTimes<float, A_PATTERN>, 32, 1, 8, false>("ring pt_f32 pat 3 slabs cs4", 33, 60, 300, 32, 55, 33 + sd, false, 4, 60, 1);
+    bad += run_case<PlusTimes<double, A_BOOL>, 32, 1, 8, false>("ring pt_f64 boolA ragged cs2", 30, 80, 50, 32, 70, 34 + sd, true, 2, 7, 1);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("ring minplus_i32 VW8 D8 cs4", 70, 64, 32, 32, 60, 35 + sd, false, 4, 30, 1);
+    bad += run_case<SelectMax<int64_t>, 8, 1, 2, false>("ring selectmax_i64 k=13 D2", 45, 50, 13, 32, 45, 36 + sd, false, 1, 1, 1);
+    bad += run_case<OrAnd<A_PATTERN>, 8, 1, 4, false>("ring or_and VW8 D4 nhub=0", 50, 40, 24, 32, 38, 37 + sd, false, 2, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 16, true>("ring pt_f32 larger D16 cs4", 400, 900, 64, 64, 700, 38 + sd, false, 4, 200, 1);
+    bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("ring minplus_i64 larger acc", 300, 500, 32, 64, 400, 39 + sd, true, 1, 0, 1);
     }
     std::printf(bad ? "EMULATION FAILED\n" : "emulation ok\n");
     return bad ? 1 : 0;

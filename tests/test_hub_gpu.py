@@ -1,6 +1,7 @@
-"""The hub variant of the local multiply (K2H, csrc/cb_spmm_hub_kernel.cuh) on the GPU, through the C ABI.
+"""The persistent variants of the local multiply (csrc/cb_spmm_hub_kernel.cuh) on the GPU, through the C ABI: K2H (hub rows
+resident in cluster shared memory) and K2R (gathers pipelined through a shared-memory ring with cp.async).
 
-STATUS: K2H has been validated on the CPU warp/cluster emulator only (tests/test_kernel_emul_cpu.py); no GPU time was
+STATUS: both have been validated on the CPU warp/cluster emulator only (tests/test_kernel_emul_cpu.py); no GPU time was
 left in the round that wrote it.  It is opt-in in the product (cb_spmm_hub_config / CB_SPMM_HUB=1) and these tests are
 opt-in too: they run with CB_TEST_HUB=1 and are skipped otherwise, so an untested kernel cannot turn the validated suite
 red.  First thing to run on hardware next round:
@@ -26,7 +27,7 @@ sys.path.insert(0, %(root)r)
 import cbb200_loader
 from oracle import oracle as O
 cb = cbb200_loader.load_package()
-case, cluster, slab, scale, k = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+case, cluster, slab, scale, k, ring = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 CASES = {"pt_f32": (O.PLUS_TIMES, np.float32, np.float32, "value"), "pt_f64": (O.PLUS_TIMES, np.float64, np.float64, "value"),
          "minplus_i32": (O.MIN_PLUS, np.int32, np.int32, "x_minplus"), "pt_pat_i64": (O.PLUS_TIMES, None, np.int64, "value"),
          "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"), "or_and": (O.OR_AND, None, np.uint8, "value")}
@@ -39,28 +40,30 @@ with cb.Context(0) as ctx:
     Xd, Y0, Y1, Y2 = ctx.dense_from(X), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt)
     for acc in (False, True):                               # plain K2: overwrite, then accumulate on top
         ctx.spmm_local(t, Xd, Y0, sr, accumulate=acc)
-    ctx.hub_config(1, cluster, slab)
-    for acc in (False, True):                               # K2H: the same two calls
+    ctx.hub_config(1 if cluster > 0 else 0, max(cluster, 0), slab)
+    ctx.ring_config(ring)
+    for acc in (False, True):                               # K2H / K2R: the same two calls
         ctx.spmm_local(t, Xd, Y1, sr, accumulate=acc)
     ctx.spmm_local(t, Xd, Y2, sr)
     info = t.hub_info()
     ctx.hub_config(0)
+    ctx.ring_config(0)
     a, a1, b = Y0.download(), Y1.download(), Y2.download()
     ref = O.spmm(sr, n, n, I, J, V, X)
-    assert info["built"] and info["resident"] > 0, f"the hub kernel did not run: {info}"
+    assert cluster <= 0 or (info["built"] and info["resident"] > 0), f"the hub kernel did not run: {info}"
     assert a.tobytes() == a1.tobytes(), "K2H differs from K2"
     if np.issubdtype(ref.dtype, np.floating):
         tol = 1e-5 if ref.dtype == np.float32 else 1e-12
         assert (np.abs(b - ref) <= tol * np.maximum(np.abs(ref), 1e-300)).all()
     else:
         assert np.array_equal(b, ref)
-    print("hub ok", case, "cluster", cluster, "slab", slab, info)
+    print("hub ok", case, "cluster", cluster, "slab", slab, "ring", ring, info)
 '''
 
 
-def run(case, cluster, slab, scale=12, k=64):
+def run(case, cluster, slab, scale=12, k=64, ring=0):
     env = dict(os.environ, CB_SPMM_HUB_MIN_COVER_PCT="0")          # small test matrices: never fall back for low coverage
-    r = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}, case, str(cluster), str(slab), str(scale), str(k)],
+    r = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}, case, str(cluster), str(slab), str(scale), str(k), str(ring)],
                        capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0 and "hub ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
@@ -82,3 +85,19 @@ def test_hub_column_slabs_and_ragged_widths(slab, k):
 
 def test_hub_larger_matrix_many_chunks():
     run("minplus_i32", 4, 128, scale=16, k=32)
+
+
+# ---- K2R: gathers pipelined through a shared-memory ring (cp.async), alone (cluster 0 = no hub rows) and with hub rows
+@pytest.mark.parametrize("cluster", [0, 1, 4])
+def test_ring_matches_k2_bitwise_fp32(cluster):
+    run("pt_f32", cluster, 0, ring=8)
+
+
+@pytest.mark.parametrize("case", ["pt_f64", "minplus_i32", "pt_pat_i64", "selmax_i32", "or_and"])
+def test_ring_every_semiring(case):
+    run(case, 2, 0, k=64 if case != "or_and" else 256, ring=8)
+
+
+@pytest.mark.parametrize("slab,k", [(128, 64), (256, 100), (512, 300)])
+def test_ring_column_slabs_and_ragged_widths(slab, k):
+    run("pt_f32", 0, slab, k=k, ring=8)

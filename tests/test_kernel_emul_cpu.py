@@ -2,8 +2,9 @@
 compiled UNMODIFIED for the host against a lock-step warp emulator (tests/emul/cuda_emul.h: 32 lanes = 32 threads, *_sync
 intrinsics are rendezvous points; CTAs, clusters, shared memory and reads of a neighbour CTA's shared memory for the hub
 variant) and run under AddressSanitizer + UBSan on small tiles with hub rows, empty rows, ragged widths, column slabs and the
-accumulate mode, against a scalar loop over the same functors.  The hub variant (K2H) must also reproduce plain K2 bit for
-bit.  (compute-sanitizer is closed on the GPU pool.)"""
+accumulate mode, against a scalar loop over the same functors.  The hub variant (K2H) and the ring-pipelined variant (K2R,
+whose cp.async copies the emulator DEFERS until the matching wait_group, so a slot read too early shows stale bytes) must
+also reproduce plain K2 bit for bit.  (compute-sanitizer is closed on the GPU pool.)"""
 import os
 import subprocess
 
@@ -19,4 +20,4 @@ def test_k2_and_fixup_on_the_warp_emulator_under_asan(tmp_path):
     r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)      # a dead-locked warp = diverged *_sync = timeout
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "emulation ok" in r.stdout and "mismatches=0" in r.stdout and "runtime error" not in r.stderr
-    assert r.stdout.count("mismatches=0") == 40 and "K2H differs" not in r.stdout
+    assert r.stdout.count("mismatches=0") == 58 and "K2H differs" not in r.stdout      # 12 K2 + 8 K2H + 9 K2R cases, two seeds

@@ -9,3 +9,8 @@ for CS in 1 2 4 8; do
     CB_SPMM_HUB=1 CB_SPMM_HUB_CLUSTER=$CS CB_SPMM_HUB_SLAB=$SLAB timeout 600 python tools/kbench.py $W --steps 5 | cut -c1-220
   done
 done
+echo "== ring only (K2R, no hub rows)"; CB_SPMM_RING=8 timeout 600 python tools/kbench.py $W c3 --steps 5 | cut -c1-220
+for CS in 2 4; do
+  echo "== ring + hub cluster=$CS"
+  CB_SPMM_HUB=1 CB_SPMM_HUB_CLUSTER=$CS CB_SPMM_RING=8 timeout 600 python tools/kbench.py $W --steps 5 | cut -c1-220
+done
