@@ -101,3 +101,33 @@ def test_ring_every_semiring(case):
 @pytest.mark.parametrize("slab,k", [(128, 64), (256, 100), (512, 300)])
 def test_ring_column_slabs_and_ragged_widths(slab, k):
     run("pt_f32", 0, slab, k=k, ring=8)
+
+
+FULLSIZE = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import cbb200_loader
+cb = cbb200_loader.load_package()
+scale, k, what, cluster, ring = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
+dt, sr, vd, kind = {"pt_f32": (np.float32, cb.PLUS_TIMES, cb.F32, 0), "mp_i32": (np.int32, cb.MIN_PLUS, cb.I32, 1)}[what]
+n = 1 << scale
+with cb.Context(0) as ctx:
+    t = ctx.gen_rmat_tile(scale, 16, 0, val_dtype=vd, val_seed=1)
+    X = ctx.dense(n, k, dt); X.generate(42, 0, 0, k, kind)
+    Y0, Y1 = ctx.dense(n, k, dt), ctx.dense(n, k, dt)
+    ctx.spmm_local(t, X, Y0, sr)
+    ctx.hub_config(1 if cluster > 0 else 0, max(cluster, 0), 0); ctx.ring_config(ring)
+    ctx.spmm_local(t, X, Y1, sr)
+    info = t.hub_info()
+    assert Y0.download().tobytes() == Y1.download().tobytes(), "persistent variant differs from K2 at full size"
+    print("fullsize ok", what, scale, k, cluster, ring, info)
+'''
+
+
+@pytest.mark.parametrize("scale,k,what,cluster,ring", [(20, 64, "pt_f32", 4, 0), (20, 64, "pt_f32", 0, 8), (20, 64, "pt_f32", 4, 8),
+                                                       (22, 32, "mp_i32", 8, 0), (22, 32, "mp_i32", 2, 8)])
+def test_full_size_configs_bitwise_equal_to_k2(scale, k, what, cluster, ring):
+    # BASELINE configs C2 (R-MAT scale 20 x 64 fp32) and C5 (scale 22 x 32 int32 MinPlus) generated on the device
+    r = subprocess.run([sys.executable, "-c", FULLSIZE % {"root": ROOT}, str(scale), str(k), what, str(cluster), str(ring)],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "fullsize ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
