@@ -248,7 +248,7 @@ def ref_grid_torus(ranks):
     return [l for l in _run_grid(["torus"], ranks).splitlines() if l.startswith("torus")][0]
 
 
-def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_distribution=True):
+def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_distribution=True, timeout=900):
     """The unmodified reference on a sqrt(ranks) x sqrt(ranks) process grid (oracle/_ref/cbref_grid: one process per rank over
     the shared-memory MPI stand-in).  via: 0 Mult_AnXBn_Synch, 1 k x SpMV, 2 _DoubleBuff, 3 _Overlap.
     Returns (Y, seconds, stdout)."""
@@ -271,7 +271,7 @@ def ref_grid_spmm(semiring, ranks, m, n, I, J, V, X, via=0, threads=1, check_dis
         if Vb is not None:
             Vb.tofile(os.path.join(d, "V.bin"))
         Xb.tofile(os.path.join(d, "X.bin"))
-        out = _run_grid(["spmm", ref_key(semiring, ad, xd), str(via), d], ranks, threads,
+        out = _run_grid(["spmm", ref_key(semiring, ad, xd), str(via), d], ranks, threads, timeout=timeout,
                         extra_env=None if check_distribution else {"CBREF_SKIP_DISTCHECK": "1"})
         Y = np.empty((m, k), Xb.dtype)
         seen = np.zeros((m, k), bool)
@@ -331,7 +331,7 @@ def ref_best_time(semiring, m, n, I, J, V, X, cores, reps=1):
         th = max(1, cores // 4)
         try:
             for _ in range(max(1, reps)):
-                _, sec, _ = ref_grid_spmm(semiring, 4, m, n, I, J, V, X, via=0, threads=th, check_distribution=False)
+                _, sec, _ = ref_grid_spmm(semiring, 4, m, n, I, J, V, X, via=0, threads=th, check_distribution=False, timeout=240)
                 if sec < best[0]:
                     best = (sec, f"2x2 processes x {th} OpenMP threads")
         except Exception as ex:      # the multi-process run is an extra; the 1-process time stands if it cannot run on this box
