@@ -195,6 +195,17 @@ SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA>& A, SpParMat<
     return SpParMat<IU, NUO, UDERO>(new UDERO(ct, false), grid, gm, gk);
 }
 
+// Mult_AnXBn_DoubleBuff (ParFriends.h:798-997) and Mult_AnXBn_Overlap (:1110-1235) differ from _Synch only in how the
+// reference hides its broadcasts; here double buffering and overlap live inside cb_spmm_summa, so they are the same call.
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_DoubleBuff(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {
+    return Mult_AnXBn_Synch<SR, NUO, UDERO>(A, B, clearA, clearB);
+}
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_Overlap(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {
+    return Mult_AnXBn_Synch<SR, NUO, UDERO>(A, B, clearA, clearB);
+}
+
 template <typename SR, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
 SpParMat<IU, typename promote_trait<NU1, NU2>::T_promote, typename create_trait<UDERA, typename UDERA::LocalIT, typename promote_trait<NU1, NU2>::T_promote>::T_inferred>
 PSpGEMM(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {        // SpParMat.h:454-467

@@ -72,7 +72,8 @@ public:
         const bool hasbanner = banner.compare(0, 14, "%%matrixmarket") == 0;
         const bool pattern = hasbanner && banner.find("pattern") != std::string::npos;
         const bool symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
-        if (hasbanner) do { std::getline(in, line); } while (!line.empty() && line[0] == '%');
+        if (hasbanner) std::getline(in, line);
+        while (!line.empty() && line[0] == '%' && std::getline(in, line)) {}          // comment lines before the size line
         long long m_ = 0, n_ = 0, nz_ = 0;
         std::istringstream(line) >> m_ >> n_ >> nz_;
         tm = (IT)m_; tn = (IT)n_;
@@ -99,6 +100,34 @@ public:
             MPI_Abort(MPI_COMM_WORLD, NOFILE);
         }
         FromGlobalTriples(tm, tn, rows, cols, vals, true, binop);
+    }
+
+    // Triples file "m n nnz" + one "i j v" line per entry, one-based (reference SpParMat.cpp:4213-4400: the master reads and
+    // scatters; here every process reads the file and keeps what it owns).  nonum: no value column, every entry is 1.
+    // A missing file leaves an empty 0 x 0 matrix after the reference's message (SpParMat.cpp:4274-4279).
+    void ReadDistribute(const std::string& filename, int master, bool nonum = false, bool pario = false) {
+        (void)master; (void)pario;
+        std::ifstream in(filename);
+        if (!in) {
+            SpParHelper::Print("COMBBLAS: Input file doesn't exist\n");
+            FromGlobalTriples(0, 0, std::vector<IT>(), std::vector<IT>(), std::vector<NT>(), false);
+            return;
+        }
+        std::string line;
+        do { std::getline(in, line); } while (in && !line.empty() && line[0] == '%');
+        long long tm = 0, tn = 0, tnz = 0;
+        std::istringstream(line) >> tm >> tn >> tnz;
+        std::vector<IT> rows, cols;
+        std::vector<NT> vals;
+        long long ii, jj;
+        double vv = 1;
+        while (std::getline(in, line)) {
+            std::istringstream ls(line);
+            if (!(ls >> ii >> jj)) continue;
+            if (!nonum) ls >> vv;
+            rows.push_back((IT)(ii - 1)); cols.push_back((IT)(jj - 1)); vals.push_back((NT)vv);
+        }
+        FromGlobalTriples((IT)tm, (IT)tn, rows, cols, vals, false);
     }
 
     // Graph500-style Kronecker matrix generated on the device (GenWriteMatrix.cpp:96-131 recipe).  The local tile never

@@ -105,6 +105,36 @@ def test_driver_spmv_on_a_process_grid():
 
 
 @pytest.mark.gpu
+def test_reference_multtiming_driver_unmodified_on_the_gpu(tmp_path):
+    # oracle/_ref/MultTiming_b200 = the reference's own ReleaseTests/MultTiming.cpp compiled UNMODIFIED against this host layer
+    # and libcombblas_b200.so in the build container (host/Makefile target reference_drivers); it travels prebuilt
+    exe = os.path.join(ROOT, "oracle", "_ref", "MultTiming_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/MultTiming_b200 was not built (needs the reference tree)")
+    from tests.test_host_mock_cpu import write_triples
+    rng = np.random.default_rng(3)
+    m, kd, n = 600, 450, 64
+
+    def rand(mm, nn, nz):
+        I, J = rng.integers(0, mm, nz), rng.integers(0, nn, nz)
+        keep = np.unique(I * nn + J, return_index=True)[1]
+        return I[keep].astype(np.int64), J[keep].astype(np.int64), rng.integers(1, 9, len(keep)).astype(np.int64)
+    AI, AJ, AV = rand(m, kd, 6000)
+    BI, BJ, BV = rand(kd, n, 900)
+    a, b = str(tmp_path / "A.txt"), str(tmp_path / "B.txt")
+    write_triples(a, m, kd, AI, AJ, AV)
+    write_triples(b, kd, n, BI, BJ, BV)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, a, b], capture_output=True, text=True, timeout=300, env=env)
+    A = np.zeros((m, kd), np.int64); A[AI, AJ] = 1
+    B = np.zeros((kd, n), np.int64); B[BI, BJ] = 1
+    want = int(((A @ B) > 0).sum())
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"C has a total of {want} nonzeros" in r.stderr + r.stdout and r.stdout.count(f"and {want} nonzeros") == 2
+    assert "Synchronous multiplications finished" in r.stdout
+
+
+@pytest.mark.gpu
 def test_driver_spmmerror_program_on_a_2x2_grid():
     import torch
     from tests.test_summa_cpu import free_port

@@ -65,3 +65,46 @@ def test_matrix_market_config_c1(driver, tmp_path):
     assert "31502 nonzeros" in r.stdout and "SpMM working correctly" in r.stderr
     Y = np.fromfile(dump, np.float64).reshape(m, 16)
     assert (np.abs(Y - g["Y"]) <= 1e-12 * np.maximum(np.abs(g["Y"]), 1e-300)).all()     # host layer + reader vs the reference's golden
+
+
+REF_DRIVER = "/root/reference/ReleaseTests/MultTiming.cpp"
+
+
+def write_triples(path, m, n, I, J, V):
+    with open(path, "w") as f:
+        f.write(f"{m} {n} {len(I)}\n")
+        for i, j, v in zip(I, J, V):
+            f.write(f"{i + 1} {j + 1} {float(v)!r}\n")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="the reference tree is not mounted here")
+def test_reference_multtiming_driver_compiles_unmodified_and_runs(tmp_path_factory, driver, tmp_path):
+    # source-level drop-in: the reference's own ReleaseTests/MultTiming.cpp (ReadDistribute, Mult_AnXBn_DoubleBuff, Mult_AnXBn_Synch,
+    # PrintInfo, getnnz, MPI_Pcontrol) compiled as it is against the host layer; nnz(C) checked against the reference library itself
+    from oracle import oracle as O
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "MultTiming_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, REF_DRIVER, f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"], timeout=600)
+    rng = np.random.default_rng(3)
+    m, kd, n = 60, 45, 30
+    def rand(mm, nn, nz):
+        I, J = rng.integers(0, mm, nz), rng.integers(0, nn, nz)
+        keep = np.unique(I * nn + J, return_index=True)[1]
+        return I[keep].astype(np.int64), J[keep].astype(np.int64), rng.integers(1, 9, len(keep)).astype(np.int64)
+    AI, AJ, AV = rand(m, kd, 300)
+    BI, BJ, BV = rand(kd, n, 200)
+    a, b = str(tmp_path / "A.txt"), str(tmp_path / "B.txt")
+    write_triples(a, m, kd, AI, AJ, AV)
+    write_triples(b, kd, n, BI, BJ, BV)
+    r = run(exe, a, b)
+    if O.ref_available():
+        CI, CJ, CV = O.ref_spgemm_i64(m, kd, n, AI, AJ, AV, BI, BJ, BV)
+        want = len(CI)
+    else:
+        A = np.zeros((m, kd), np.int64); A[AI, AJ] = 1
+        B = np.zeros((kd, n), np.int64); B[BI, BJ] = 1
+        want = int(((A @ B) > 0).sum())
+    assert f"C has a total of {want} nonzeros" in r.stderr + r.stdout
+    assert r.stdout.count(f"and {want} nonzeros") == 2                      # C.PrintInfo() after DoubleBuff and after Synch
+    assert "Double buffered multiplications finished" in r.stdout and "Synchronous multiplications finished" in r.stdout
