@@ -1,7 +1,8 @@
 // spmm_driver - a driver in the style of the reference's ReleaseTests/MultTest.cpp / MultTiming.cpp, written against
 // the B200 host layer: declare the SpParMat typedefs, build a grid, read or generate A, multiply, PrintInfo, verify.
 //
-//   spmm_driver mtx  <file.mtx> <k> [ydump.bin]          fp64 PlusTimes on a Matrix Market file (BASELINE config C1)
+//   spmm_driver mtx  <file.mtx> <k> [ydump.bin [copy.mtx]]   fp64 PlusTimes on a Matrix Market file (BASELINE config C1); optional
+//                                                        ParallelWriteMM -> ParallelReadMM round trip through copy.mtx
 //   spmm_driver rmat <scale> <k> <pt_f32|mp_i32|sel_i64|bool> [pr pc]   Kronecker matrix generated on the GPU
 //   spmm_driver torus                                    the sparse x sparse program of Applications/SpMMError.cpp
 //   spmm_driver spmv <scale> [pr pc]                     dense SpMV<SR>(A, FullyDistVec) under three semirings, DenseParMat::Reduce,
@@ -260,6 +261,14 @@ int main(int argc, char* argv[]) {
             const int64_t k = std::atoll(argv[3]);
             DenseParMat<int64_t, double> X = MakeX<int64_t, double>(grid, A.getncol(), k);
             DenseParMat<int64_t, double> Y = SpMM<PlusTimesSRing<double, double>>(A, X);
+            if (argc > 5) {
+                // ParallelWriteMM -> ParallelReadMM round trip (reference SpParMat.cpp:4118-4210 / :3978-4115)
+                A.ParallelWriteMM(argv[5], true);
+                PSpMat_Double A2(grid);
+                A2.ParallelReadMM(argv[5], true, maximum<double>());
+                if (A2 == A) SpParHelper::Print("Matrix Market round trip working correctly\n");
+                else { SpParHelper::Print("ERROR in the Matrix Market round trip, go fix it!\n"); rc = 1; }
+            }
             if (grid->GetSize() == 1) {
                 if (VerifyLocal<PlusTimesSRing<double, double>>(A, X, Y, 1e-12)) SpParHelper::Print("SpMM working correctly\n");
                 else { SpParHelper::Print("ERROR in SpMM, go fix it!\n"); rc = 1; }

@@ -130,6 +130,32 @@ public:
         FromGlobalTriples((IT)tm, (IT)tn, rows, cols, vals, false);
     }
 
+    // Matrix Market coordinate file of the whole matrix, every process contributing its tile in rank order, column by
+    // column inside a tile - the text the reference's ParallelWriteMM produces (SpParMat.cpp:4118-4210: header by rank 0,
+    // "row<TAB>col<TAB>value" lines).  Round-trips through ParallelReadMM; used for archived results.
+    void ParallelWriteMM(const std::string& filename, bool onebased) const {
+        const IT totalm = getnrow(), totaln = getncol(), totnnz = getnnz();
+        IT roffset = 0, coffset = 0, len = 0;
+        BlockRange(totalm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), roffset, len);
+        BlockRange(totaln, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), coffset, len);
+        if (onebased) { roffset += 1; coffset += 1; }
+        std::ostringstream ss;
+        ss.precision(17);
+        if (commGrid->GetRank() == 0) ss << "%%MatrixMarket matrix coordinate real general\n" << totalm << " " << totaln << " " << totnnz << "\n";
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq());
+        for (int64_t p = 0; p < tup.getnnz(); ++p)
+            ss << (IT)tup.rowindex(p) + roffset << '\t' << (IT)tup.colindex(p) + coffset << '\t' << +tup.numvalue(p) << '\n';
+        const std::string text = ss.str();
+        for (int q = 0; q < commGrid->GetSize(); ++q) {                        // one writer at a time, in rank order
+            if (q == commGrid->GetRank()) {
+                std::ofstream out(filename, q == 0 ? std::ios::trunc : std::ios::app);
+                out << text;
+            }
+            if (commGrid->GetSize() > 1) MPI_Barrier(commGrid->GetWorld());
+        }
+    }
+    void SaveGathered(const std::string& filename) const { ParallelWriteMM(filename, true); }
+
     // Graph500-style Kronecker matrix generated on the device (GenWriteMatrix.cpp:96-131 recipe).  The local tile never
     // exists on the host; seq() downloads it on first use.
     void GenGraph500(int scale, int edgefactor, bool symmetric = true, uint64_t seed = 0, bool values = false, uint64_t val_seed = 1,

@@ -47,9 +47,9 @@ def test_driver_hepth_matches_reference_golden(tmp_path):
     m, n = int(g["m"]), int(g["n"])
     mtx, dump = str(tmp_path / "hepth.mtx"), str(tmp_path / "y.bin")
     write_mtx(mtx, m, n, g["I"], g["J"], g["V"])
-    r = subprocess.run([DRIVER, "mtx", mtx, "16", dump], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([DRIVER, "mtx", mtx, "16", dump, str(tmp_path / "copy.mtx")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "31502 nonzeros" in r.stdout and "SpMM working correctly" in r.stderr
+    assert "31502 nonzeros" in r.stdout and "SpMM working correctly" in r.stderr and "Matrix Market round trip working correctly" in r.stderr
     Y = np.fromfile(dump, np.float64).reshape(m, 16)
     ref = g["Y"]
     assert (np.abs(Y - ref) <= 1e-12 * np.maximum(np.abs(ref), 1e-300)).all()

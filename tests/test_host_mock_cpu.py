@@ -61,8 +61,10 @@ def test_matrix_market_config_c1(driver, tmp_path):
     m, n = int(g["m"]), int(g["n"])
     mtx, dump = str(tmp_path / "hepth.mtx"), str(tmp_path / "y.bin")
     write_mtx(mtx, m, n, g["I"], g["J"], g["V"])
-    r = run(driver, "mtx", mtx, 16, dump)
-    assert "31502 nonzeros" in r.stdout and "SpMM working correctly" in r.stderr
+    r = run(driver, "mtx", mtx, 16, dump, str(tmp_path / "copy.mtx"))
+    assert "31502 nonzeros" in r.stdout and "SpMM working correctly" in r.stderr and "Matrix Market round trip working correctly" in r.stderr
+    with open(tmp_path / "copy.mtx") as f:
+        assert f.readline().startswith("%%MatrixMarket matrix coordinate real general") and f.readline().split() == ["8361", "8361", "31502"]
     Y = np.fromfile(dump, np.float64).reshape(m, 16)
     assert (np.abs(Y - g["Y"]) <= 1e-12 * np.maximum(np.abs(g["Y"]), 1e-300)).all()     # host layer + reader vs the reference's golden
 
