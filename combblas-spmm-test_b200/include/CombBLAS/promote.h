@@ -30,6 +30,10 @@ CB_DECLARE_PROMOTE(double, int64_t, double)
 CB_DECLARE_PROMOTE(int64_t, double, double)
 #undef CB_DECLARE_PROMOTE
 
+// user-side extension point with the reference's name (promote.h:56-60; Applications/SpMMError.cpp:28-29 uses it)
+#define DECLARE_PROMOTE(A, B, C) \
+    template <> struct promote_trait<A, B> { typedef C T_promote; };
+
 // element type -> cb_dtype code of the C ABI
 template <class T> struct cb_dtype_of;
 template <> struct cb_dtype_of<float> { static const int value = 0; };
