@@ -53,7 +53,7 @@ inline void cb_host_allgatherv(const void* mine, size_t bytes, std::vector<std::
     MPI_Comm_size(MPI_COMM_WORLD, &p);
     MPI_Comm_rank(MPI_COMM_WORLD, &r);
     all.assign((size_t)p, std::vector<char>());
-    if (p == 1) { all[0].assign((const char*)mine, (const char*)mine + bytes); return; }
+    if (p == 1) { if (bytes) all[0].assign((const char*)mine, (const char*)mine + bytes); return; }
 #ifdef CB_HAVE_MPI
     std::vector<long long> sizes((size_t)p);
     long long mysz = (long long)bytes;
@@ -72,7 +72,8 @@ inline void cb_host_allgatherv(const void* mine, size_t bytes, std::vector<std::
     std::vector<uint64_t> sz((size_t)p);
     for (int q = 0; q < p; ++q) { std::memcpy(&sz[q], sizes.data() + sizeof(uint64_t) * (size_t)q, sizeof(uint64_t)); mx = std::max(mx, sz[q]); }
     std::vector<char> padded((size_t)mx, 0), buf;
-    std::memcpy(padded.data(), mine, bytes);
+    if (bytes) std::memcpy(padded.data(), mine, bytes);
+    if (mx == 0) return;                                   // nobody has anything
     cb_rt::allgather_bytes(padded.data(), (size_t)mx, buf);
     for (int q = 0; q < p; ++q) all[q].assign(buf.begin() + (size_t)mx * (size_t)q, buf.begin() + (size_t)mx * (size_t)q + (size_t)sz[q]);
 #endif

@@ -2,19 +2,72 @@
 // (combblas-spmm-test_b200/include/CombBLAS/*.h: SpParMat, DenseParMat, FullyDistVec, SpMM, SpMV, Mult_AnXBn_Synch, ...)
 // and its driver can be exercised by the CPU test suite on a machine without a GPU.  tests/test_host_mock_cpu.py compiles
 // the driver against THIS library in a temporary directory; nothing in the product links, loads or ships it, and the real
-// library still has no CPU path (tests/test_abi_cpu.py).  Single process only (1 x 1 grid); multiplies are naive loops over
+// library still has no CPU path (tests/test_abi_cpu.py).  Multiplies are naive loops over
 // the semiring definitions of include/CombBLAS/Semirings.h - the driver's own replays and the GPU suite are the checkers of
 // arithmetic, this only has to be a faithful enough ABI for the host logic to run.
+// Process grids: with RANK / WORLD_SIZE set (one OS process per rank, as under torch.distributed.run) the mock exchanges tiles
+// and panels through files in CB_RENDEZVOUS_DIR, so the host layer's multi-process paths (distribution, FullyDistVec pieces,
+// SpMV, Reduce, ParallelWriteMM ordering) run on CPU too; cb_spmm_summa gathers the whole product's operands on every rank and
+// computes the caller's block.
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 #include "combblas_b200.h"
 
-struct cb_ctx { std::string err; int64_t launches = 0; };
+struct cb_ctx { std::string err; int64_t launches = 0; int rank = 0, nranks = 1, pr = 1, pc = 1; };
+
+// every rank contributes a byte string; afterwards everyone holds all of them (files "mock<seq>.r<rank>" in the rendezvous directory)
+static void mock_allgatherv(const cb_ctx* c, const std::vector<unsigned char>& mine, std::vector<std::vector<unsigned char>>& all) {
+    all.assign((size_t)c->nranks, std::vector<unsigned char>());
+    if (c->nranks == 1) { all[0] = mine; return; }
+    static long seq = 0;
+    const char* d = std::getenv("CB_RENDEZVOUS_DIR");
+    const std::string dir = d ? d : "/tmp/cb_mock_rdv";
+    mkdir(dir.c_str(), 0700);
+    const std::string base = dir + "/mock" + std::to_string(seq++) + ".r";
+    {
+        const std::string tmp = base + std::to_string(c->rank) + ".tmp", fin = base + std::to_string(c->rank);
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        const uint64_t n = mine.size();
+        std::fwrite(&n, sizeof n, 1, f);
+        if (n) std::fwrite(mine.data(), 1, mine.size(), f);
+        std::fclose(f);
+        std::rename(tmp.c_str(), fin.c_str());
+    }
+    for (int q = 0; q < c->nranks; ++q)
+        for (int tries = 0;; ++tries) {
+            FILE* f = std::fopen((base + std::to_string(q)).c_str(), "rb");
+            if (f) {
+                uint64_t n = 0;
+                const bool ok = std::fread(&n, sizeof n, 1, f) == 1;
+                all[(size_t)q].resize((size_t)n);
+                const bool ok2 = ok && (n == 0 || std::fread(all[(size_t)q].data(), 1, (size_t)n, f) == n);
+                std::fclose(f);
+                if (ok2) break;
+            }
+            if (tries > 300000) { std::fprintf(stderr, "mock ABI: rank %d timed out waiting for rank %d\n", c->rank, q); std::exit(1); }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+}
+template <class T>
+static void put(std::vector<unsigned char>& b, const T& v) { const unsigned char* p = (const unsigned char*)&v; b.insert(b.end(), p, p + sizeof(T)); }
+template <class T>
+static T take(const std::vector<unsigned char>& b, size_t& off) { T v; std::memcpy(&v, b.data() + off, sizeof(T)); off += sizeof(T); return v; }
+static void block_range(int64_t total, int nb, int b, int64_t* start, int64_t* len) {
+    const int64_t per = total / nb;
+    *start = per * b;
+    *len = b == nb - 1 ? total - *start : per;
+}
 struct cb_tile {
     int64_t m = 0, n = 0;
     int val_dtype = CB_PATTERN;
@@ -107,18 +160,36 @@ int cb_abi_version(void) { return CB_ABI_VERSION; }
 int cb_device_count(int* c) { *c = 1; return CB_OK; }
 int cb_comm_unique_id(void* id) { std::memset(id, 0, 128); return CB_OK; }
 int cb_ctx_create_grid(int, int rank, int nranks, int pr, int pc, const void*, cb_ctx** ctx) {
-    if (nranks != 1 || rank != 0 || pr != 1 || pc != 1) return fail(nullptr, CB_ERR_INVALIDPARAMS, "mock ABI: one process only");
+    if (pr * pc != nranks || rank < 0 || rank >= nranks) return fail(nullptr, CB_ERR_INVALIDPARAMS, "mock ABI: grid does not match the rank count");
     *ctx = new cb_ctx();
+    (*ctx)->rank = rank; (*ctx)->nranks = nranks; (*ctx)->pr = pr; (*ctx)->pc = pc;
     return CB_OK;
 }
 int cb_ctx_create(int d, cb_ctx** ctx) { return cb_ctx_create_grid(d, 0, 1, 1, 1, nullptr, ctx); }
 int cb_ctx_destroy(cb_ctx* c) { delete c; return CB_OK; }
-int cb_ctx_grid(const cb_ctx*, int* rank, int* pr, int* pc, int* r, int* c) { *rank = 0; *pr = *pc = 1; *r = *c = 0; return CB_OK; }
+int cb_ctx_grid(const cb_ctx* x, int* rank, int* pr, int* pc, int* r, int* c) {
+    *rank = x->rank; *pr = x->pr; *pc = x->pc; *r = x->rank / x->pc; *c = x->rank % x->pc;
+    return CB_OK;
+}
 int cb_ctx_sync(cb_ctx*) { return CB_OK; }
 void* cb_ctx_stream(cb_ctx*) { return nullptr; }
 const char* cb_last_error(const cb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 const char* cb_status_string(int s) { return s == CB_OK ? "ok" : "mock ABI error"; }
-int cb_comm_allreduce_i64(cb_ctx*, int, int, int64_t*, int) { return CB_OK; }       // one process: the value is the result
+int cb_comm_allreduce_i64(cb_ctx* c, int which, int op, int64_t* inout, int count) {
+    // which: 0 world, 1 my processor row, 2 my processor column; op: 0 sum, 1 max, 2 min
+    std::vector<unsigned char> mine((const unsigned char*)inout, (const unsigned char*)(inout + count));
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(c, mine, all);
+    const int myrow = c->rank / c->pc, mycol = c->rank % c->pc;
+    bool first = true;
+    for (int q = 0; q < c->nranks; ++q) {
+        if ((which == 1 && q / c->pc != myrow) || (which == 2 && q % c->pc != mycol)) continue;
+        const int64_t* v = (const int64_t*)all[(size_t)q].data();
+        for (int i = 0; i < count; ++i) inout[i] = first ? v[i] : op == 0 ? inout[i] + v[i] : op == 1 ? std::max(inout[i], v[i]) : std::min(inout[i], v[i]);
+        first = false;
+    }
+    return CB_OK;
+}
 int64_t cb_launch_count(const cb_ctx* c) { return c->launches; }
 
 int cb_tile_upload_csc(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int64_t nzc, const void* cp, const void* jc, const void* ir,
@@ -227,8 +298,52 @@ int cb_spmm_local(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y,
     }
     return CB_OK;
 }
-int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int sr, int64_t, int64_t, int64_t) {
-    return cb_spmm_local(ctx, t, X, Y, sr, 0);
+int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int sr, int64_t gm, int64_t gn, int64_t gk) {
+    if (ctx->nranks == 1) return cb_spmm_local(ctx, t, X, Y, sr, 0);
+    // every rank publishes its A tile (global coordinates) and its X tile; everyone rebuilds block-row myprocrow of A and
+    // block-column myproccol of X and multiplies them - the result the SUMMA stage loop accumulates
+    const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;
+    int64_t r0, rl, c0, cl, x0, xl, k0, kl;
+    block_range(gm, pr, myrow, &r0, &rl); block_range(gn, pc, mycol, &c0, &cl);
+    block_range(gn, pr, myrow, &x0, &xl); block_range(gk, pc, mycol, &k0, &kl);
+    if (t->m != rl || t->n != cl || X->rows != xl || X->cols != kl || Y->rows != rl || Y->cols != kl) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: summa block mismatch");
+    const size_t ves = esize(t->val_dtype == CB_PATTERN ? CB_U8 : t->val_dtype), xes = esize(X->dtype);
+    std::vector<unsigned char> mine;
+    put<int64_t>(mine, (int64_t)t->col.size());
+    for (int64_t r = 0; r < t->m; ++r)
+        for (int64_t p = t->rowptr[(size_t)r]; p < t->rowptr[(size_t)r + 1]; ++p) { put<int64_t>(mine, r0 + r); put<int64_t>(mine, c0 + t->col[(size_t)p]); }
+    if (t->val_dtype != CB_PATTERN) mine.insert(mine.end(), t->vals.begin(), t->vals.end());
+    put<int64_t>(mine, X->rows); put<int64_t>(mine, X->cols);
+    mine.insert(mine.end(), X->data.begin(), X->data.end());
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(ctx, mine, all);
+    cb_tile arow;                     // block-row myrow of A, all columns
+    arow.m = rl; arow.n = gn; arow.val_dtype = t->val_dtype;
+    cb_dense xcol;                    // all rows of X, block-column mycol
+    xcol.rows = gn; xcol.cols = kl; xcol.dtype = X->dtype;
+    xcol.data.assign((size_t)gn * (size_t)kl * xes, 0);
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    for (int q = 0; q < ctx->nranks; ++q) {
+        const std::vector<unsigned char>& b = all[(size_t)q];
+        size_t off = 0;
+        const int64_t nz = take<int64_t>(b, off);
+        std::vector<std::pair<int64_t, int64_t>> rc((size_t)nz);
+        for (int64_t p = 0; p < nz; ++p) { rc[(size_t)p].first = take<int64_t>(b, off); rc[(size_t)p].second = take<int64_t>(b, off); }
+        for (int64_t p = 0; p < nz; ++p) {
+            std::vector<unsigned char> v;
+            if (t->val_dtype != CB_PATTERN) { v.assign(b.begin() + off, b.begin() + off + ves); off += ves; }
+            if (q / pc == myrow) trip.push_back({{rc[(size_t)p].first - r0, rc[(size_t)p].second}, v});
+        }
+        const int64_t qr = take<int64_t>(b, off), qc = take<int64_t>(b, off);
+        if (q % pc == mycol) {
+            int64_t q0, ql;
+            block_range(gn, pr, q / pc, &q0, &ql);
+            if (qr != ql || qc != kl) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: X tile of a peer has the wrong shape");
+            if (qr > 0 && qc > 0) std::memcpy(xcol.data.data() + (size_t)q0 * (size_t)kl * xes, b.data() + off, (size_t)qr * (size_t)qc * xes);
+        }
+    }
+    build_csr(&arow, trip);
+    return cb_spmm_local(ctx, &arow, &xcol, Y, sr, 0);
 }
 
 }  // extern "C"

@@ -36,6 +36,43 @@ def run(exe, *args):
     return r
 
 
+def run_grid(exe, nproc, rdv, *args):
+    """one OS process per rank with the launcher environment the host layer reads (RANK / WORLD_SIZE / LOCAL_RANK)"""
+    procs = []
+    for r in range(nproc):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(nproc), LOCAL_RANK=str(r), CB_RENDEZVOUS_DIR=str(rdv))
+        procs.append(subprocess.Popen([exe, *[str(a) for a in args]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0 and "runtime error" not in se and "AddressSanitizer" not in se, so[-2000:] + se[-3000:]
+    return outs[0]
+
+
+@pytest.mark.parametrize("nproc,grid", [(4, ()), (2, (1, 2)), (2, (2, 1)), (6, (2, 3))])
+def test_spmv_fullydistvec_and_dense_epilogues_on_process_grids(driver, tmp_path, nproc, grid):
+    so, se = run_grid(driver, nproc, tmp_path, "spmv", 8, *grid)
+    assert "SpMV and dense epilogues working correctly" in se and "rows reached" in so
+
+
+def test_spmmerror_program_on_2x2_processes(driver, tmp_path):
+    so, se = run_grid(driver, 4, tmp_path, "torus")
+    assert so.count("112 nonzeros") == 3 and "SpGEMM (sparse x sparse) working correctly" in se
+
+
+def test_matrix_market_round_trip_on_2x2_processes(driver, tmp_path):
+    from tests.test_host_cpp import write_mtx
+    g = np.load(os.path.join(G, "small.npz"))
+    m, n = int(g["nonsym_m"]), int(g["nonsym_n"])
+    mtx = str(tmp_path / "a.mtx")
+    write_mtx(mtx, m, n, g["nonsym_I"], g["nonsym_J"], g["nonsym_V"])
+    so, se = run_grid(driver, 4, tmp_path / "rdv", "mtx", mtx, 8, str(tmp_path / "y.bin"), str(tmp_path / "copy.mtx"))
+    assert "Matrix Market round trip working correctly" in se
+    rows = [l.split() for l in open(tmp_path / "copy.mtx").read().splitlines()[2:]]
+    got = sorted((int(r[0]) - 1, int(r[1]) - 1, float(r[2])) for r in rows)
+    want = sorted(zip(g["nonsym_I"].tolist(), g["nonsym_J"].tolist(), g["nonsym_V"].tolist()))
+    assert len(got) == len(want) and all(a[:2] == b[:2] and abs(a[2] - b[2]) <= 1e-15 * abs(b[2]) for a, b in zip(got, want))
+
+
 def test_spmv_fullydistvec_and_dense_epilogues(driver):
     r = run(driver, "spmv", 8)
     assert "SpMV and dense epilogues working correctly" in r.stderr and "rows reached" in r.stdout
