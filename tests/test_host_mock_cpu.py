@@ -147,3 +147,6 @@ def test_reference_multtiming_driver_compiles_unmodified_and_runs(tmp_path_facto
     assert f"C has a total of {want} nonzeros" in r.stderr + r.stdout
     assert r.stdout.count(f"and {want} nonzeros") == 2                      # C.PrintInfo() after DoubleBuff and after Synch
     assert "Double buffered multiplications finished" in r.stdout and "Synchronous multiplications finished" in r.stdout
+    # the same unmodified program on 2 x 2 processes (ReadDistribute keeps what each process owns; two grids per process)
+    so, se = run_grid(exe, 4, tmp_path / "rdv", a, b)
+    assert f"C has a total of {want} nonzeros" in se + so and so.count(f"and {want} nonzeros") == 2
