@@ -1,7 +1,9 @@
-// Runs the product's K2 (cb_spmm_kernel), fix-up and K3 row fill - compiled UNMODIFIED from csrc/cb_spmm_kernel.cuh - on the
-// lock-step warp emulator, on small random tiles with hub rows, empty rows, ragged panel widths, column slabs and the
-// accumulate mode; compares with a scalar loop over the same semiring functors.  Built with -fsanitize=address,undefined:
-// every device buffer is an exactly-sized heap vector, so an out-of-bounds access of the kernel is an ASan report.
+// Runs the product's K2 (cb_spmm_kernel), its persistent variants K2H (hub rows in cluster shared memory) and K2R (gathers
+// through a cp.async ring) and the fix-up kernel - compiled UNMODIFIED from csrc/cb_spmm_kernel.cuh and
+// csrc/cb_spmm_hub_kernel.cuh - on the lock-step warp / cluster emulator, on small random tiles with hub rows, empty rows,
+// ragged panel widths, column slabs and the accumulate mode; compares with a scalar loop over the same semiring functors
+// and, for the variants, bit for bit with K2.  Built with -fsanitize=address,undefined: every device buffer and every CTA's
+// shared memory is an exactly-sized heap vector, so an out-of-bounds access of a kernel is an ASan report.
 #include "cuda_emul.h"
 #include <cstdio>
 #include <random>
