@@ -222,8 +222,12 @@ int main(int argc, char* argv[]) {
             for (int64_t v : A.seq().numx) local += v;
             ok = ok && total == grid->SumWorld(local);
             // (3) SelectMax<bool,T> with values below the identity -1: SpMV starts from id(), so they are clipped (axpy semantics)
-            BMat P(grid);
-            P.GenGraph500(scale, 8, true, 0, false, 1);
+            // the boolean matrix through the reference's construction path: DistEdgeList -> SpParMat (GenWriteMatrix.cpp:96-110)
+            double initiator[4] = {.57, .19, .19, .05};
+            DistEdgeList<int64_t> DEL(grid);
+            DEL.GenGraph500Data(initiator, scale, 8, true, true);
+            BMat P(DEL, false);
+            ok = ok && P.getnrow() == n && P.RemoveLoops() == 0;
             FullyDistVec<int64_t, int64_t> neg(grid, n, -5);
             FullyDistVec<int64_t, int64_t> sel = SpMV<SelectMaxSRing<bool, int64_t>>(P, neg);
             ok = ok && sel.Count([](int64_t v) { return v != -1; }) == 0;

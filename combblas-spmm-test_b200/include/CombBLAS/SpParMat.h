@@ -28,6 +28,31 @@ struct maximum { T operator()(const T& x, const T& y) const { return x < y ? y :
 template <class T>
 struct cb_sum { T operator()(const T& x, const T& y) const { return x + y; } };
 
+// DistEdgeList<IT>: the reference's distributed Graph500 edge list (include/CombBLAS/DistEdgeList.h:90-140).  Here it is a
+// recipe, not a container: GenGraph500Data records scale / edge factor / initiator, and SpParMat(const DistEdgeList&, bool)
+// has the device generator (csrc/cb_gen.cu) build the tiles directly in HBM - the edges never exist on the host.
+// Differences from the reference, by construction of that generator: vertex ids are always scrambled, self loops are always
+// dropped, duplicate edges are merged (values are hashed weights, not multiplicities).
+template <class IT>
+class DistEdgeList {
+public:
+    DistEdgeList() : commGrid(new CommGrid(MPI_COMM_WORLD, 0, 0)) {}
+    explicit DistEdgeList(std::shared_ptr<CommGrid> grid) : commGrid(grid) {}
+    void GenGraph500Data(double initiator[4], int log_numverts, int edgefactor, bool scramble = false, bool packed = false) {   // DistEdgeList.cpp:223-
+        (void)scramble; (void)packed;
+        for (int i = 0; i < 4; ++i) init[i] = initiator[i];
+        scale = log_numverts;
+        ef = edgefactor;
+        globalV = (IT)1 << log_numverts;
+    }
+    IT getGlobalV() const { return globalV; }
+    std::shared_ptr<CommGrid> getcommgrid() const { return commGrid; }
+    std::shared_ptr<CommGrid> commGrid;
+    double init[4] = {0.57, 0.19, 0.19, 0.05};
+    int scale = 0, ef = 16;
+    IT globalV = 0;
+};
+
 template <class IT, class NT, class DER>
 class SpParMat {
 public:
@@ -44,6 +69,12 @@ public:
              std::shared_ptr<CommGrid> grid, bool SumDuplicates = false)
         : commGrid(grid), spSeq(nullptr) {
         FromGlobalTriples(total_m, total_n, rows, cols, vals, SumDuplicates);
+    }
+    // conversion from a distributed edge list (reference SpParMat.cpp:3138-3254): generated on the device, see DistEdgeList
+    template <class DELIT>
+    SpParMat(const DistEdgeList<DELIT>& rhs, bool removeloops = true) : commGrid(rhs.commGrid), spSeq(nullptr) {
+        (void)removeloops;                                        // the device generator never emits self loops
+        GenGraph500(rhs.scale, rhs.ef, false, 0, !std::is_same<NT, bool>::value, 1, rhs.init);
     }
     SpParMat(const SpParMat& rhs) : commGrid(rhs.commGrid), spSeq(new DER(rhs.seq())), gm(rhs.gm), gn(rhs.gn) {}
     SpParMat& operator=(const SpParMat& rhs) {
@@ -221,6 +252,23 @@ public:
         const IT keep_m = gm, keep_n = gn;
         Release();
         spSeq = scaled; gm = keep_m; gn = keep_n;
+    }
+
+    // drop the entries on the global diagonal; returns how many there were (reference SpParMat.cpp RemoveLoops)
+    IT RemoveLoops() {
+        IT roff = 0, coff = 0;
+        GetPlaceInGlobalGrid(roff, coff);
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq()), kept(0, seq().getnrow(), seq().getncol());
+        for (int64_t p = 0; p < tup.getnnz(); ++p)
+            if ((IT)tup.rowindex(p) + roff != (IT)tup.colindex(p) + coff) kept.tuples.push_back(tup.tuples[(size_t)p]);
+        const int64_t removed = tup.getnnz() - kept.getnnz();
+        if (removed > 0) {
+            DER* fresh = new DER(kept, false);
+            const IT keep_m = gm, keep_n = gn;
+            Release();
+            spSeq = fresh; gm = keep_m; gn = keep_n;
+        }
+        return (IT)commGrid->SumWorld(removed);
     }
 
     // Owner of global entry (grow, gcol) and its local indices (SpParMat.cpp:5066-5096)
