@@ -171,7 +171,13 @@ static int launch_op(const LaunchParams& p) {
             // 64-bit element types need more registers per gathered vector's arithmetic: one CTA per SM fewer
             constexpr int WB = sizeof(typename Op::T) == 8 ? CB_WIDE_B64 : CB_WIDE_B;
             constexpr int DB = sizeof(typename Op::T) == 8 ? CB_DEEP_B64 : CB_DEEP_B;
-            if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
+            // narrow panels (rows of 16 or 32 bytes: SpMV, k <= 8 fp32, boolean k <= 32): with the 4-lane layout 3 or 2 of the 4
+            // lanes of a virtual warp carry no columns.  CB_K2_NARROW=1 runs them on 1- and 2-lane virtual warps (32 / 16 row
+            // walkers per warp) - the same walker, other template arguments; opt-in until it has been timed on hardware
+            static const bool narrow = getenv("CB_K2_NARROW") && atoi(getenv("CB_K2_NARROW")) != 0;
+            if (narrow && nvec == 1) s = launch_layout<Op, 1, 1, 1, 4>(p);
+            else if (narrow && nvec <= 2) s = launch_layout<Op, 2, 1, 2, 4>(p);
+            else if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
             else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 8, 1, CB_DEEP_U, DB>(p);
             else if (nvec <= 16) s = wide ? launch_layout<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 16, 1, CB_DEEP_U, DB>(p);
             else if (nvec <= 32) s = wide ? launch_layout<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 32, 1, CB_DEEP_U, DB>(p);

@@ -134,7 +134,7 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         if (ring == 0)
             emul::launch_cluster(dim3((unsigned)(2 * hub_cs), grid.y), dim3(64), (unsigned)hub_cs, smem ? smem : 16,
                                  [&] { cb_spmm_hub_kernel<Op, VW, R, U, 64, FULL>(a, h); });
-        else {
+        else if constexpr (VW >= 2 && U >= 2) {
             // K2R: U doubles as the ring depth D here; shared memory = hub slots + one ring of D slots per virtual warp, exactly
             constexpr int D = U <= VW ? U : VW;
             if (nhub == 0) { h.hubslot = nullptr; h.hubcols = nullptr; }             // ring without hub data must not touch it
@@ -194,6 +194,13 @@ int main(int argc, char** argv) {
     // a larger tile: several blocks, chunk length 64, hub rows of ~11 chunks
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pt_f32 VW16 larger", 400, 900, 64, 64, 700, 11 + sd, false);
     bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("minplus_i64 VW16 larger acc", 300, 500, 32, 64, 400, 12 + sd, true);
+    // narrow panels on 2- and 1-lane virtual warps (CB_K2_NARROW=1): 32- and 16-byte rows
+    bad += run_case<PlusTimes<float, A_SAME>, 2, 1, 2, true>("narrow pt_f32 VW2 k=8", 61, 97, 8, 32, 90, 41 + sd, false);
+    bad += run_case<PlusTimes<float, A_SAME>, 2, 1, 2, false>("narrow pt_f32 VW2 k=5 acc", 61, 97, 5, 32, 90, 42 + sd, true);
+    bad += run_case<MinPlus<int64_t>, 1, 1, 1, false>("narrow minplus_i64 VW1 k=1", 70, 64, 1, 32, 60, 43 + sd, false);
+    bad += run_case<PlusTimes<double, A_BOOL>, 1, 1, 1, true>("narrow pt_f64 boolA VW1 k=2", 45, 50, 2, 32, 45, 44 + sd, true);
+    bad += run_case<OrAnd<A_PATTERN>, 2, 1, 2, true>("narrow or_and VW2 k=32 bytes", 50, 40, 8, 32, 38, 45 + sd, false);
+    bad += run_case<SelectMax<int32_t>, 1, 1, 1, false>("narrow selectmax_i32 VW1 k=3", 45, 50, 3, 32, 45, 46 + sd, false);
     // K2H, the hub variant: persistent CTAs, dynamic chunks, hub rows in the shared memory of a 1/2/4-CTA cluster
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs1", 61, 97, 64, 32, 150, 21 + sd, false, 1, 20);
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs2 acc", 61, 97, 64, 32, 150, 22 + sd, true, 2, 33);

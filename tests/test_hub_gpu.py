@@ -131,3 +131,43 @@ def test_full_size_configs_bitwise_equal_to_k2(scale, k, what, cluster, ring):
     r = subprocess.run([sys.executable, "-c", FULLSIZE % {"root": ROOT}, str(scale), str(k), what, str(cluster), str(ring)],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "fullsize ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+# ---- narrow panels on 1- and 2-lane virtual warps (CB_K2_NARROW=1): K2's own walker with other template arguments
+NARROW = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import cbb200_loader
+from oracle import oracle as O
+cb = cbb200_loader.load_package()
+case, k = sys.argv[1], int(sys.argv[2])
+CASES = {"pt_f32": (O.PLUS_TIMES, np.float32, np.float32, "value"), "minplus_i64": (O.MIN_PLUS, np.int64, np.int64, "x_minplus"),
+         "or_and": (O.OR_AND, None, np.uint8, "value"), "selmax_i32": (O.MAX_SEL2ND, None, np.int32, "value"),
+         "pt_f64": (O.PLUS_TIMES, np.float64, np.float64, "value")}
+sr, adt, xdt, kind = CASES[case]
+n, I, J = O.rmat_matrix(13, 16, seed=0)
+V = None if adt is None else O.matrix_values(I, J, n, 1, adt)
+X = O.dense_operand(n, k, 42, xdt, kind)
+with cb.Context(0) as ctx:
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    Xd, Y = ctx.dense_from(X), ctx.dense(n, k, xdt)
+    for acc in (False, True):
+        ctx.spmm_local(t, Xd, Y, sr, accumulate=acc)
+    got = Y.download()
+ref = O.spmm(sr, n, n, I, J, V, X)
+ref2 = O.spmm(sr, n, n, I, J, V, X, accum_into=ref.copy())
+if np.issubdtype(ref2.dtype, np.floating):
+    tol = 1e-5 if ref2.dtype == np.float32 else 1e-12
+    assert (np.abs(got - ref2) <= tol * np.maximum(np.abs(ref2), 1e-300)).all()
+else:
+    assert np.array_equal(got, ref2)
+print("narrow ok", case, k, os.environ.get("CB_K2_NARROW"))
+'''
+
+
+@pytest.mark.parametrize("case,k", [("pt_f32", 1), ("pt_f32", 4), ("pt_f32", 8), ("pt_f32", 5), ("minplus_i64", 1), ("minplus_i64", 4),
+                                    ("or_and", 16), ("or_and", 32), ("selmax_i32", 3), ("pt_f64", 2), ("pt_f64", 3)])
+def test_narrow_layouts_match_the_oracle(case, k):
+    r = subprocess.run([sys.executable, "-c", NARROW % {"root": ROOT}, case, str(k)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, CB_K2_NARROW="1"), cwd=ROOT)
+    assert r.returncode == 0 and "narrow ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -14,3 +14,6 @@ for CS in 2 4; do
   echo "== ring + hub cluster=$CS"
   CB_SPMM_HUB=1 CB_SPMM_HUB_CLUSTER=$CS CB_SPMM_RING=8 timeout 600 python tools/kbench.py $W --steps 5 | cut -c1-220
 done
+echo "== narrow panels: 4-lane layout vs CB_K2_NARROW=1 (boolean k=32, SpMV-like k=1,4,8)"
+python tools/kbench.py c5b --steps 5 | cut -c1-220; CB_K2_NARROW=1 python tools/kbench.py c5b --steps 5 | cut -c1-220
+for K in 1 4 8; do python tools/kbench.py c2 --k $K --steps 5 | cut -c1-220; CB_K2_NARROW=1 python tools/kbench.py c2 --k $K --steps 5 | cut -c1-220; done
