@@ -9,7 +9,10 @@
  *        Applications/SpMMError.cpp:32-33,80; hep-th.mtx = 31502 nnz after expansion), and
  *   (ii) outputs of the unmodified reference itself (oracle/_ref/libcbref.so, built from
  *        /root/reference by oracle/Makefile) - live where /root/reference exists, and
- *        through the committed fixtures tests/golden/ (made by tests/golden/make_golden.py).
+ *        through the committed fixtures tests/golden/ (made by tests/golden/make_golden.py), and
+ *   (iii) outputs of the unmodified reference run on 2x2 / 3x3 PROCESS grids (oracle/_ref/cbref_grid =
+ *        the reference + the process-per-rank MPI stand-in oracle/mpi_multi): the emulated stage loop
+ *        below and the owner rule against tests/golden/grid_ref.npz (tests/test_ref_grid.py).
  *
  * What is restated, with the reference lines each function follows:
  *   semiring functors ............ include/CombBLAS/Semirings.h:40-47 (inf_plus), :191-210
