@@ -145,6 +145,7 @@ __device__ __forceinline__ void cb_spmm_walk_ring(const SpmmArgs& a, const int64
     int row = live ? a.nzrows[ridx] : 0;
     char* const carry_head = a.carry + (2 * chunk) * a.carry_stride + slab_off;
 
+    const bool has_hubs = hub.nhub > 0;
     // entries of one step: lane vl holds nonzero base + vl of the chunk
     struct Entry { int cf; TA av; int hs; };
     auto load_entries = [&](int base) {
@@ -153,14 +154,14 @@ __device__ __forceinline__ void cb_spmm_walk_ring(const SpmmArgs& a, const int64
         if (base + vl < len) {
             en.cf = ld_stream(a.colflag + s + base + vl);
             if (HASVAL) en.av = ld_stream_val<TA>(vals + s + base + vl);
-            if (hub.nhub > 0) en.hs = (int)__ldcs(hub.hubslot + s + base + vl);     // no hub data without resident hubs
+            if (has_hubs) en.hs = (int)__ldcs(hub.hubslot + s + base + vl);         // no hub data without resident hubs
         }
         return en;
     };
     // start the copy of the row of nonzero t (entry j of `en`) into its ring slot; always closes a group
     auto issue = [&](const Entry& en, int j, int t) {
         const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, en.cf, j, VW) & 0x7fffffffu;
-        const int h = __shfl_sync(0xffffffffu, en.hs, j, VW);
+        const int h = has_hubs ? __shfl_sync(0xffffffffu, en.hs, j, VW) : 0xffff;       // has_hubs is uniform over the grid
         if (t < len && lane_on && !(h < hub.nhub)) cb_cp_async16(ring + (uint32_t)(t & (D - 1)) * hub.slot_bytes, xbase + (uint64_t)c * ldx);
         cb_cp_async_commit();
     };
@@ -175,7 +176,7 @@ __device__ __forceinline__ void cb_spmm_walk_ring(const SpmmArgs& a, const int64
             const int t = base + j;
             cb_cp_async_wait<D - 1>();                       // my copies for nonzero t have landed
             const int cf = __shfl_sync(0xffffffffu, cur.cf, j, VW);
-            const int h = __shfl_sync(0xffffffffu, cur.hs, j, VW);
+            const int h = has_hubs ? __shfl_sync(0xffffffffu, cur.hs, j, VW) : 0xffff;
             const TA av = HASVAL ? (TA)__shfl_sync(0xffffffffu, cur.av, j, VW) : TA();
             if (t < len) {
                 if (lane_on) {
