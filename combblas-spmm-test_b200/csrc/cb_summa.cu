@@ -221,6 +221,69 @@ int slice_cols(cb_ctx* ctx, const cb_tile* t, int64_t c0, int64_t c1, cb_tile** 
     return cb_tile_build_from_keys(ctx, t->m, c1 - c0, nsel, keys_sel, (t->vals && nsel) ? vals_sel : nullptr, t->val_dtype, true, sc, out);
 }
 
+// the nonzeros of `t` whose column is marked in `keep_col` (one byte per column), as a new tile of the same shape: what a
+// sparse right-hand side leaves of A when most rows of B are empty (cb_tile_filter_columns).  Same steps as slice_cols.
+__global__ void filter_keys_kernel(const int32_t* __restrict__ colflag, const int32_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ nzrows, int64_t nzr, int64_t nz, const uint8_t* __restrict__ keep_col,
+                                   uint64_t* __restrict__ keys, uint8_t* __restrict__ keep) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t col = colflag[p] & 0x7fffffff;
+        const bool in = keep_col[col] != 0;
+        keep[p] = in ? 1 : 0;
+        if (in) {
+            int64_t lo = 0, hi = nzr;           // largest ridx with rowptr[ridx] <= p
+            while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rowptr[mid] <= p) lo = mid; else hi = mid; }
+            keys[p] = ((uint64_t)(uint32_t)nzrows[lo] << 32) | (uint64_t)(uint32_t)col;
+        } else {
+            keys[p] = ~0ULL;
+        }
+    }
+}
+
+template <typename V>
+int select_values(cb_ctx* ctx, cb_scratch& sc, const void* vals, const uint8_t* keep, void* out, int64_t* d_n, int64_t nz, cudaStream_t st) {
+    size_t b = 0;
+    void* tmp = nullptr;
+    CB_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, b, (const V*)vals, keep, (V*)out, d_n, (int)nz, st));
+    CB_CUDA(ctx, sc.alloc((char**)&tmp, b));
+    CB_CUDA(ctx, cub::DeviceSelect::Flagged(tmp, b, (const V*)vals, keep, (V*)out, d_n, (int)nz, st));
+    return CB_OK;
+}
+
+int filter_cols(cb_ctx* ctx, const cb_tile* t, const uint8_t* keep_col_host, cb_tile** out) {
+    cb_scratch sc;
+    cudaStream_t st = ctx->compute;
+    const int64_t nz = t->nnz;
+    uint64_t *keys = nullptr, *keys_sel = nullptr;
+    uint8_t *keep = nullptr, *keep_col = nullptr;
+    int64_t* d_n = nullptr;
+    void* vals_sel = nullptr;
+    const size_t vs = cb_dtype_size(t->val_dtype);
+    int64_t nsel = 0;
+    CB_CUDA(ctx, sc.alloc(&keys, (size_t)nz));
+    CB_CUDA(ctx, sc.alloc(&keys_sel, (size_t)nz));
+    if (nz > 0) {
+        CB_CUDA(ctx, sc.alloc(&keep, (size_t)nz));
+        CB_CUDA(ctx, sc.alloc(&keep_col, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_n, 1));
+        CB_CUDA(ctx, cudaMemcpyAsync(keep_col, keep_col_host, (size_t)t->n, cudaMemcpyHostToDevice, st));
+        filter_keys_kernel<<<grid_for(nz, ctx->sm_count), 256, 0, st>>>(t->colflag, t->rowptr, t->nzrows, t->nzr, nz, keep_col, keys, keep);
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+        CB_TRY(select_values<uint64_t>(ctx, sc, keys, keep, keys_sel, d_n, nz, st));
+        if (t->vals) {
+            CB_CUDA(ctx, sc.alloc((char**)&vals_sel, vs * (size_t)nz));
+            if (vs == 1) CB_TRY(select_values<uint8_t>(ctx, sc, t->vals, keep, vals_sel, d_n, nz, st));
+            else if (vs == 4) CB_TRY(select_values<uint32_t>(ctx, sc, t->vals, keep, vals_sel, d_n, nz, st));
+            else CB_TRY(select_values<uint64_t>(ctx, sc, t->vals, keep, vals_sel, d_n, nz, st));
+        }
+        ctx->launches += 4;
+        CB_CUDA(ctx, cudaMemcpyAsync(&nsel, d_n, sizeof nsel, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return cb_tile_build_from_keys(ctx, t->m, t->n, nsel, keys_sel, (t->vals && nsel) ? vals_sel : nullptr, t->val_dtype, true, sc, out);
+}
+
 // all nonzeros of `t` as keys row<<32 | (col + coloff), for concatenating column-disjoint parts of one block-row
 __global__ void emit_keys_kernel(const int32_t* __restrict__ colflag, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ nzrows, int64_t nzr, int64_t nz, int32_t coloff,
@@ -261,6 +324,12 @@ int merge_parts(cb_ctx* ctx, const std::vector<const cb_tile*>& parts, const std
 }  // namespace
 
 extern "C" {
+
+int cb_tile_filter_columns(cb_ctx* ctx, const cb_tile* tile, const uint8_t* keep_cols, cb_tile** out) {
+    if (!ctx || !tile || !keep_cols || !out) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_filter_columns: null argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return filter_cols(ctx, tile, keep_cols, out);
+}
 
 int cb_comm_unique_id(void* id128) {
     if (!nccl_load()) return cb_fail(nullptr, CB_ERR_NCCL, "NCCL unavailable: %s", nccl().error.c_str());

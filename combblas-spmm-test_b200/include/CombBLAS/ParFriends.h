@@ -9,6 +9,7 @@
 #ifndef CB_PARFRIENDS_H
 #define CB_PARFRIENDS_H
 
+#include <cstdlib>
 #include "DenseParMat.h"
 #include "FullyDistVec.h"
 #include "Semirings.h"
@@ -176,14 +177,48 @@ SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA>& A, SpParMat<
         cb_check(cb_dense_upload(dX, Xv.data(), kl), ctx, "cb_dense_upload");
         cb_check(cb_dense_upload(dS, Xs.data(), kl), ctx, "cb_dense_upload");
     }
-    cb_check(cb_spmm_summa(ctx, A.DeviceTile(), dX, dY, semiring_traits<SR>::op, gm, gn, gk), ctx, "cb_spmm_summa");
-    cb_check(cb_spmm_summa(ctx, A.DevicePatternTile(), dS, dM, CB_OR_AND, gm, gn, gk), ctx, "cb_spmm_summa (structure)");
+    // Sparse-aware option (CB_SPGEMM_FILTER=1): a column of A that meets only empty rows of B cannot contribute, and the
+    // reference's column-by-column SpGEMM never touches it (mtSpGEMM.h:292-441).  When fewer than half of B's rows hold
+    // anything, multiply with the tile that keeps only the other columns: the engine then costs what the product touches.
+    cb_tile *tileA = A.DeviceTile(), *tileP = nullptr, *filtered = nullptr, *filtered_pattern = nullptr;
+    static const bool want_filter = std::getenv("CB_SPGEMM_FILTER") && std::atoi(std::getenv("CB_SPGEMM_FILTER")) != 0;
+    if (want_filter) {
+        std::vector<uint8_t> mine((size_t)xl, 0);                  // rows of my B tile that hold anything
+        for (IU i = 0; i < xl; ++i)
+            for (IU j = 0; j < kl && !mine[(size_t)i]; ++j) mine[(size_t)i] = Xs(i, j) ? 1 : 0;
+        std::vector<std::vector<char>> all;
+        cb_host_allgatherv(mine.data(), mine.size(), all);
+        std::vector<uint8_t> active((size_t)gn, 0);                // B's row block i lives on the processes of processor row i
+        for (int i = 0; i < grid->GetGridRows(); ++i) {
+            IU r0, rl;
+            DenseParMat<IU, bool>::Block(gn, grid->GetGridRows(), i, r0, rl);
+            for (int j = 0; j < grid->GetGridCols(); ++j) {
+                const std::vector<char>& b = all[(size_t)grid->GetRank(i, j)];
+                for (size_t q = 0; q < b.size(); ++q) active[(size_t)r0 + q] |= (uint8_t)b[q];
+            }
+        }
+        size_t nactive = 0;
+        for (uint8_t a : active) nactive += a;
+        if (2 * nactive < (size_t)gn) {                            // the same decision on every process
+            IU c0, cl;
+            DenseParMat<IU, bool>::Block(gn, grid->GetGridCols(), grid->GetRankInProcRow(), c0, cl);
+            cb_check(cb_tile_filter_columns(ctx, tileA, active.data() + c0, &filtered), ctx, "cb_tile_filter_columns");
+            cb_check(cb_tile_pattern_view(filtered, &filtered_pattern), ctx, "cb_tile_pattern_view");
+            tileA = filtered;
+            tileP = filtered_pattern;
+        }
+    }
+    if (!tileP) tileP = A.DevicePatternTile();
+    cb_check(cb_spmm_summa(ctx, tileA, dX, dY, semiring_traits<SR>::op, gm, gn, gk), ctx, "cb_spmm_summa");
+    cb_check(cb_spmm_summa(ctx, tileP, dS, dM, CB_OR_AND, gm, gn, gk), ctx, "cb_spmm_summa (structure)");
     if (kl > 0) {
         cb_check(cb_dense_download(dY, Y.data(), kl), ctx, "cb_dense_download");
         cb_check(cb_dense_download(dM, M.data(), kl), ctx, "cb_dense_download");
     }
     cb_check(cb_ctx_sync(ctx), ctx, "cb_ctx_sync");
     cb_dense_free(dX); cb_dense_free(dY); cb_dense_free(dS); cb_dense_free(dM);
+    if (filtered_pattern) cb_tile_free(filtered_pattern);
+    if (filtered) cb_tile_free(filtered);
     // C tile: one entry per structural hit, column-major like every SpTuples the reference's local multiply returns
     typedef typename UDERO::LocalIT OIT;
     SpTuples<OIT, NUO> ct(0, (OIT)lm, (OIT)kl);

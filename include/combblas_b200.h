@@ -109,6 +109,12 @@ int cb_tile_info(const cb_tile* tile, int64_t info[8]);
  * matrix (used to compute the nonzero structure of a product with the boolean semiring).  The view borrows the
  * original's memory: free it before the original; freeing the view does not free the arrays. */
 int cb_tile_pattern_view(const cb_tile* tile, cb_tile** view);
+/* a new tile of the same shape holding only the nonzeros whose column c has keep_cols[c] != 0 (host array, one byte per
+ * column of the tile).  For products with a SPARSE right-hand side B (Mult_AnXBn_Synch with a sparse B,
+ * include/CombBLAS/ParFriends.h:1004-1108): columns of A that meet only empty rows of B cannot contribute, and the reference's
+ * column-by-column SpGEMM never touches them (mtSpGEMM.h:292-441); dropping them makes the dense-panel engine cost what the
+ * product touches instead of nnz(A) x k.  Opt-in in the host layer (CB_SPGEMM_FILTER=1). */
+int cb_tile_filter_columns(cb_ctx* ctx, const cb_tile* tile, const uint8_t* keep_cols, cb_tile** out);
 /* copy the device tile back as CSR (rowptr[m+1], colidx[nnz], vals) for inspection/tests; any pointer may be NULL */
 int cb_tile_download_csr(cb_tile* tile, int64_t* rowptr, int64_t* colidx, void* vals);
 

@@ -223,6 +223,22 @@ int cb_tile_pattern_view(const cb_tile* t, cb_tile** view) {
     *view = v;
     return CB_OK;
 }
+int cb_tile_filter_columns(cb_ctx*, const cb_tile* t, const uint8_t* keep, cb_tile** out) {
+    cb_tile* f = new cb_tile();
+    f->m = t->m; f->n = t->n; f->val_dtype = t->val_dtype;
+    const size_t es = esize(t->val_dtype == CB_PATTERN ? CB_U8 : t->val_dtype);
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    for (int64_t r = 0; r < t->m; ++r)
+        for (int64_t p = t->rowptr[(size_t)r]; p < t->rowptr[(size_t)r + 1]; ++p)
+            if (keep[t->col[(size_t)p]]) {
+                std::vector<unsigned char> v;
+                if (t->val_dtype != CB_PATTERN) v.assign(t->vals.begin() + (size_t)p * es, t->vals.begin() + (size_t)(p + 1) * es);
+                trip.push_back({{r, t->col[(size_t)p]}, v});
+            }
+    build_csr(f, trip);
+    *out = f;
+    return CB_OK;
+}
 int cb_tile_download_csr(cb_tile* t, int64_t* rowptr, int64_t* colidx, void* vals) {
     if (rowptr) std::copy(t->rowptr.begin(), t->rowptr.end(), rowptr);
     if (colidx) std::copy(t->col.begin(), t->col.end(), colidx);

@@ -92,6 +92,17 @@ def test_sparse_right_hand_side(driver):
     assert "SpGEMM (sparse x sparse) working correctly" in run(driver, "spgemm", 8, 20, 3).stderr
 
 
+def test_sparse_right_hand_side_with_column_filter(driver, tmp_path, monkeypatch):
+    # CB_SPGEMM_FILTER=1: A's columns that meet only empty rows of B are dropped before the multiply; same C, entry for entry
+    monkeypatch.setenv("CB_SPGEMM_FILTER", "1")
+    assert "SpGEMM (sparse x sparse) working correctly" in run(driver, "spgemm", 8, 20, 1).stderr      # 20 of 256 rows of B hold anything
+    assert "SpGEMM (sparse x sparse) working correctly" in run(driver, "torus").stderr                   # every row active: filter declines
+    one = run(driver, "spgemm", 8, 20, 1).stdout.splitlines()
+    so, se = run_grid(driver, 4, tmp_path, "spgemm", 8, 20, 1)                                           # and on 2 x 2 processes:
+    info = [l for l in so.splitlines() if l.startswith("As a whole")]
+    assert len(info) == 3 and info == [l for l in one if l.startswith("As a whole")]                     # same A, B and C sizes
+
+
 def test_matrix_market_config_c1(driver, tmp_path):
     from tests.test_host_cpp import write_mtx
     g = np.load(os.path.join(G, "hepth.npz"))

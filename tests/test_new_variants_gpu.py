@@ -3,10 +3,11 @@ resident in cluster shared memory) and K2R (gathers pipelined through a shared-m
 
 STATUS: both have been validated on the CPU warp/cluster emulator only (tests/test_kernel_emul_cpu.py); no GPU time was
 left in the round that wrote it.  It is opt-in in the product (cb_spmm_hub_config / CB_SPMM_HUB=1) and these tests are
-opt-in too: they run with CB_TEST_HUB=1 and are skipped otherwise, so an untested kernel cannot turn the validated suite
-red.  First thing to run on hardware next round:
+opt-in too: they run with CB_TEST_NEW=1 and are skipped otherwise, so an untested kernel cannot turn the validated suite
+red.  Also here: the narrow-panel layouts (CB_K2_NARROW=1) and the column filter for sparse right-hand sides
+(cb_tile_filter_columns / CB_SPGEMM_FILTER=1).  First thing to run on hardware next round:
 
-    CB_TEST_HUB=1 python -m pytest tests/test_hub_gpu.py -x -q
+    CB_TEST_NEW=1 python -m pytest tests/test_new_variants_gpu.py -x -q
 
 Each case runs in its own process (own CUDA context, hard timeout): a fault or a hang of the new kernel stays contained.
 The bar is stronger than parity: K2H walks chunks exactly like K2, so its result must equal K2's BIT FOR BIT for every
@@ -19,7 +20,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CB_TEST_HUB") != "1", reason="hub variant not yet validated on hardware: set CB_TEST_HUB=1")]
+              pytest.mark.skipif(os.environ.get("CB_TEST_NEW") != "1" and os.environ.get("CB_TEST_HUB") != "1",
+                                 reason="device code written without a GPU, not yet validated on hardware: set CB_TEST_NEW=1")]
 
 WORKER = r'''
 import sys, numpy as np
@@ -171,3 +173,46 @@ def test_narrow_layouts_match_the_oracle(case, k):
     r = subprocess.run([sys.executable, "-c", NARROW % {"root": ROOT}, case, str(k)], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, CB_K2_NARROW="1"), cwd=ROOT)
     assert r.returncode == 0 and "narrow ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+# ---- column filter for sparse right-hand sides (cb_tile_filter_columns, CB_SPGEMM_FILTER=1)
+FILTER = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import cbb200_loader
+from oracle import oracle as O
+cb = cbb200_loader.load_package()
+n, I, J = O.rmat_matrix(12, 16, seed=0)
+V = O.matrix_values(I, J, n, 1, np.float64)
+rng = np.random.default_rng(1)
+keep = (rng.random(n) < 0.1).astype(np.uint8)
+with cb.Context(0) as ctx:
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    f = t.filter_columns(keep)
+    rowptr, col, vals = f.to_csr(np.float64)
+    sel = keep[J] != 0
+    order = np.lexsort((J[sel], I[sel]))
+    assert f.nnz == int(sel.sum()) and f.m == n and f.n == n
+    assert np.array_equal(col, J[sel][order]) and np.array_equal(vals, V[sel][order])
+    assert np.array_equal(np.diff(rowptr), np.bincount(I[sel], minlength=n))
+    X = O.dense_operand(n, 24, 42, np.float64)
+    X[keep == 0] = 0.0                                       # rows a sparse B would not have
+    Xd, Y0, Y1 = ctx.dense_from(X), ctx.dense(n, 24, np.float64), ctx.dense(n, 24, np.float64)
+    ctx.spmm_local(t, Xd, Y0, cb.PLUS_TIMES)
+    ctx.spmm_local(f, Xd, Y1, cb.PLUS_TIMES)
+    a, b = Y0.download(), Y1.download()
+    assert (np.abs(a - b) <= 1e-12 * np.maximum(np.abs(a), 1e-300)).all()
+print("filter ok")
+'''
+
+
+def test_column_filter_keeps_exactly_the_marked_columns():
+    r = subprocess.run([sys.executable, "-c", FILTER % {"root": ROOT}], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "filter ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_driver_sparse_rhs_with_column_filter():
+    from tests.test_host_cpp import DRIVER, build
+    build()
+    r = subprocess.run([DRIVER, "spgemm", "11", "40", "1"], capture_output=True, text=True, timeout=300, env=dict(os.environ, CB_SPGEMM_FILTER="1"))
+    assert r.returncode == 0 and "SpGEMM (sparse x sparse) working correctly" in r.stderr, r.stdout + r.stderr

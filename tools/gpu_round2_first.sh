@@ -7,7 +7,7 @@ set -o pipefail
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r02_pytest_gpu.log
-CB_TEST_HUB=1 timeout 900 python -m pytest tests/test_hub_gpu.py -x -q 2>&1 | tail -25 | tee gpurun_out/r02_pytest_hub.log
+CB_TEST_NEW=1 timeout 900 python -m pytest tests/test_new_variants_gpu.py -x -q 2>&1 | tail -25 | tee gpurun_out/r02_pytest_hub.log
 if grep -q "passed" gpurun_out/r02_pytest_hub.log && ! grep -q "failed" gpurun_out/r02_pytest_hub.log; then
   timeout 1200 bash tools/tune_hub.sh "c2 c5 s24f32" 2>&1 | tee gpurun_out/r02_tune_hub.log
   CS=${HUB_CS:-4}; SLAB=${HUB_SLAB:-0}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Hub variant (K2H) against plain K2 on one GPU: cluster size x slab width sweep.  usage: tools/tune_hub.sh "<workloads>"
-# First hardware run of K2H: run `CB_TEST_HUB=1 python -m pytest tests/test_hub_gpu.py -x -q` before trusting any number.
+# First hardware run of K2H: run `CB_TEST_NEW=1 python -m pytest tests/test_new_variants_gpu.py -x -q` before trusting any number.
 W=${1:-"c2 c5 s24f32"}
 echo "== plain K2"; python tools/kbench.py $W --steps 5 | cut -c1-220
 for CS in 1 2 4 8; do
