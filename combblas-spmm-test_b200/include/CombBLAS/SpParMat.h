@@ -19,6 +19,7 @@
 #include <sstream>
 #include "CommGrid.h"
 #include "DenseParMat.h"
+#include "FullyDistVec.h"
 #include "SpTuples.h"
 
 namespace combblas {
@@ -271,6 +272,50 @@ public:
         return (IT)commGrid->SumWorld(removed);
     }
 
+    // A <- A^T (reference SpParMat.cpp Transpose: tiles swap between processes (i,j) and (j,i)).  Here every process
+    // publishes its triples in global coordinates and keeps the transposed ones it owns - host-side, like all ingestion.
+    void Transpose() {
+        const IT tm = getnrow(), tn = getncol();
+        IT roff = 0, coff = 0;
+        GetPlaceInGlobalGrid(roff, coff);
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq());
+        struct Trip { IT r, c; ST v; };
+        std::vector<Trip> mine((size_t)tup.getnnz());
+        for (int64_t p = 0; p < tup.getnnz(); ++p) mine[(size_t)p] = Trip{(IT)tup.rowindex(p) + roff, (IT)tup.colindex(p) + coff, (ST)tup.numvalue(p)};
+        std::vector<std::vector<char>> all;
+        cb_host_allgatherv(mine.data(), mine.size() * sizeof(Trip), all);
+        std::vector<IT> rows, cols;
+        std::vector<NT> vals;
+        const int me = commGrid->GetRank();
+        for (const std::vector<char>& b : all) {
+            const Trip* t = reinterpret_cast<const Trip*>(b.data());
+            for (size_t q = 0; q < b.size() / sizeof(Trip); ++q) {
+                LocalIT lr, lc;
+                if (Owner(tn, tm, t[q].c, t[q].r, lr, lc) == me) { rows.push_back(t[q].c); cols.push_back(t[q].r); vals.push_back((NT)t[q].v); }
+            }
+        }
+        FromGlobalTriplesOwned(tn, tm, rows, cols, vals);
+    }
+    // element-wise A += B for matrices with the same distribution (reference SpParMat.cpp operator+=: local tile addition)
+    SpParMat& operator+=(const SpParMat& rhs) {
+        if (*commGrid != *rhs.commGrid) {
+            SpParHelper::Print("Grids are not comparable for parallel addition (A+B)\n");
+            MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+        }
+        if (getnrow() != rhs.getnrow() || getncol() != rhs.getncol()) {
+            SpParHelper::Print("Dimensions do not match for parallel addition (A+B)\n");
+            MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+        }
+        SpTuples<LocalIT, NT> a = TilesToTuples(seq()), b = TilesToTuples(rhs.seq());
+        a.tuples.insert(a.tuples.end(), b.tuples.begin(), b.tuples.end());
+        a.RemoveDuplicates(cb_sum<NT>());
+        DER* sum = new DER(a, false);
+        const IT keep_m = getnrow(), keep_n = getncol();
+        Release();
+        spSeq = sum; gm = keep_m; gn = keep_n;
+        return *this;
+    }
+
     // Owner of global entry (grow, gcol) and its local indices (SpParMat.cpp:5066-5096)
     template <typename LIT>
     int Owner(IT total_m, IT total_n, IT grow, IT gcol, LIT& lrow, LIT& lcol) const {
@@ -342,6 +387,18 @@ private:
         }
         if (mergedups) mine.RemoveDuplicates(binop);     // SparseCommon, SpParMat.cpp:2962-2967
         else mine.SortColBased();
+        spSeq = new DER(mine, false);
+    }
+    // triples that are already known to belong to this process (global coordinates)
+    void FromGlobalTriplesOwned(IT total_m, IT total_n, const std::vector<IT>& rows, const std::vector<IT>& cols, const std::vector<NT>& vals) {
+        Release();
+        gm = total_m; gn = total_n;
+        IT r0, rl, c0, cl;
+        BlockRange(gm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), r0, rl);
+        BlockRange(gn, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), c0, cl);
+        SpTuples<LocalIT, NT> mine(0, (LocalIT)rl, (LocalIT)cl);
+        for (size_t i = 0; i < rows.size(); ++i) mine.tuples.emplace_back((LocalIT)(rows[i] - r0), (LocalIT)(cols[i] - c0), vals[i]);
+        mine.SortColBased();
         spSeq = new DER(mine, false);
     }
     void Upload(cb_ctx* ctx, const SpDCCols<LocalIT, NT>& t) {

@@ -135,6 +135,24 @@ def test_reference_multtiming_driver_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_genwritematrix_driver_unmodified_on_the_gpu(tmp_path):
+    # oracle/_ref/GenWriteMatrix_b200 = the reference's own ReleaseTests/GenWriteMatrix.cpp (its benchmark-input generator) compiled
+    # UNMODIFIED against this host layer: DistEdgeList -> SpParMat on the device generator, RemoveLoops, Transpose, +=, ParallelWriteMM
+    exe = os.path.join(ROOT, "oracle", "_ref", "GenWriteMatrix_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/GenWriteMatrix_b200 was not built (needs the reference tree)")
+    from tests.test_host_mock_cpu import read_mm_file
+    out = str(tmp_path / "scale10.mtx")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, "10", "16", "1", out], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Symmetricized" in r.stderr, r.stdout + r.stderr
+    m, n, ent = read_mm_file(out)
+    assert m == n == 1024 and len(ent) > 10000 and all(i != j for i, j, _ in ent)
+    pairs = {(i, j): v for i, j, v in ent}
+    assert all(pairs.get((j, i)) == v for (i, j), v in pairs.items())
+
+
+@pytest.mark.gpu
 def test_driver_spmmerror_program_on_a_2x2_grid():
     import torch
     from tests.test_summa_cpu import free_port

@@ -161,3 +161,33 @@ def test_reference_multtiming_driver_compiles_unmodified_and_runs(tmp_path_facto
     # the same unmodified program on 2 x 2 processes (ReadDistribute keeps what each process owns; two grids per process)
     so, se = run_grid(exe, 4, tmp_path / "rdv", a, b)
     assert f"C has a total of {want} nonzeros" in se + so and so.count(f"and {want} nonzeros") == 2
+
+
+def read_mm_file(path):
+    lines = open(path).read().splitlines()
+    assert lines[0].startswith("%%MatrixMarket matrix coordinate real general")
+    m, n, nnz = (int(v) for v in lines[1].split())
+    ent = sorted((int(a) - 1, int(b) - 1, float(c)) for a, b, c in (l.split() for l in lines[2:]))
+    assert len(ent) == nnz
+    return m, n, ent
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ReleaseTests/GenWriteMatrix.cpp"), reason="the reference tree is not mounted here")
+def test_reference_genwritematrix_driver_compiles_unmodified_and_runs(driver, tmp_path):
+    # the reference's generator of its benchmark inputs (CTest `GenWrMat 20 16 1 ...`, ReleaseTests/CMakeLists.txt:41): DistEdgeList,
+    # GenGraph500Data, SpParMat(DEL, false), RemoveLoops, Transpose, +=, LoadImbalance, ParallelWriteMM - compiled as it is
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "GenWriteMatrix_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, "/root/reference/ReleaseTests/GenWriteMatrix.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
+                          timeout=600)
+    one = str(tmp_path / "one.mtx")
+    r = run(exe, 7, 8, 1, one)
+    assert "Symmetricized" in r.stderr and "Removed 0 loops" in r.stderr
+    m, n, ent = read_mm_file(one)
+    assert m == n == 128 and all(i != j for i, j, _ in ent)
+    pairs = {(i, j): v for i, j, v in ent}
+    assert all(pairs.get((j, i)) == v for (i, j), v in pairs.items())             # A == A^T after Symmetricize
+    four = str(tmp_path / "four.mtx")
+    run_grid(exe, 4, tmp_path / "rdv", 7, 8, 1, four)
+    assert read_mm_file(four) == (m, n, ent)                                      # the same matrix from a 2 x 2 process grid
