@@ -135,6 +135,23 @@ def test_reference_multtiming_driver_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_transposetest_driver_unmodified_on_the_gpu(tmp_path):
+    # the reference's self-checking ReleaseTests/TransposeTest.cpp, compiled unmodified against this layer (oracle/_ref/TransposeTest_b200)
+    exe = os.path.join(ROOT, "oracle", "_ref", "TransposeTest_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/TransposeTest_b200 was not built (needs the reference tree)")
+    from tests.test_host_mock_cpu import write_triples
+    g = np.load(os.path.join(G, "small.npz"))
+    m, n = int(g["nonsym_m"]), int(g["nonsym_n"])
+    ones = np.ones(len(g["nonsym_I"]))
+    write_triples(str(tmp_path / "a.txt"), m, n, g["nonsym_I"], g["nonsym_J"], ones)
+    write_triples(str(tmp_path / "at.txt"), n, m, g["nonsym_J"], g["nonsym_I"], ones)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, str(tmp_path), "a.txt", "at.txt"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Transpose working correctly" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_reference_genwritematrix_driver_unmodified_on_the_gpu(tmp_path):
     # oracle/_ref/GenWriteMatrix_b200 = the reference's own ReleaseTests/GenWriteMatrix.cpp (its benchmark-input generator) compiled
     # UNMODIFIED against this host layer: DistEdgeList -> SpParMat on the device generator, RemoveLoops, Transpose, +=, ParallelWriteMM

@@ -191,3 +191,24 @@ def test_reference_genwritematrix_driver_compiles_unmodified_and_runs(driver, tm
     four = str(tmp_path / "four.mtx")
     run_grid(exe, 4, tmp_path / "rdv", 7, 8, 1, four)
     assert read_mm_file(four) == (m, n, ent)                                      # the same matrix from a 2 x 2 process grid
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ReleaseTests/TransposeTest.cpp"), reason="the reference tree is not mounted here")
+def test_reference_transposetest_driver_compiles_unmodified_and_passes(driver, tmp_path):
+    # the reference's own self-checking ReleaseTests/TransposeTest.cpp: ReadDistribute of a matrix and of its transpose (boolean
+    # SpParMat<int,bool,SpDCCols<int,bool>>), operator=, Transpose(), operator==
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "TransposeTest_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, "/root/reference/ReleaseTests/TransposeTest.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
+                          timeout=600)
+    g = np.load(os.path.join(G, "small.npz"))
+    m, n = int(g["nonsym_m"]), int(g["nonsym_n"])
+    ones = np.ones(len(g["nonsym_I"]))
+    write_triples(str(tmp_path / "a.txt"), m, n, g["nonsym_I"], g["nonsym_J"], ones)
+    write_triples(str(tmp_path / "at.txt"), n, m, g["nonsym_J"], g["nonsym_I"], ones)
+    assert "Transpose working correctly" in run(exe, tmp_path, "a.txt", "at.txt").stderr
+    so, se = run_grid(exe, 4, tmp_path / "rdv", tmp_path, "a.txt", "at.txt")
+    assert "Transpose working correctly" in se
+    write_triples(str(tmp_path / "bad.txt"), n, m, g["nonsym_J"][:-1], g["nonsym_I"][:-1], ones[:-1])       # one entry missing
+    assert "ERROR in transpose" in run(exe, tmp_path, "a.txt", "bad.txt").stderr
