@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <numeric>
 #include <vector>
@@ -152,9 +153,39 @@ public:
         const IT loc = (IT)std::count_if(arr.begin(), arr.end(), pred);
         return (IT)commGrid->SumWorld((int64_t)loc);
     }
-    bool operator==(const FullyDistVec<IT, NT>& rhs) const {               // FullyDistVec.cpp:369-377
-        int64_t same = (glen == rhs.glen && *commGrid == *rhs.commGrid && arr == rhs.arr) ? 1 : 0;
-        return commGrid->MinWorld(same) == 1;
+    bool operator==(const FullyDistVec<IT, NT>& rhs) const {               // FullyDistVec.cpp:369-377 with ErrorTolerantEqual (Compare.h:46-65)
+        bool same = glen == rhs.glen && *commGrid == *rhs.commGrid && arr.size() == rhs.arr.size();
+        for (size_t i = 0; same && i < arr.size(); ++i) {
+            if (std::is_floating_point<NT>::value) {
+                const double a = (double)arr[i], b = (double)rhs.arr[i], d = a > b ? a - b : b - a;
+                same = d < EPSILON || d < EPSILON * std::max(a < 0 ? -a : a, b < 0 ? -b : b);
+            } else {
+                same = arr[i] == rhs.arr[i];
+            }
+        }
+        return commGrid->MinWorld(same ? 1 : 0) == 1;
+    }
+    // "rows cols nnz" then one "row col value" line per entry, one-based; the vector index is the row for a column vector
+    // (cols == 1) and the column otherwise; absent entries are NT() (reference FullyDistVec.cpp:495-502 through
+    // FullyDistSpVec::ReadDistribute, FullyDistSpVec.cpp:1397-1500).  Every process reads the stream and keeps its piece.
+    std::ifstream& ReadDistribute(std::ifstream& infile, int master) {
+        (void)master;
+        long long numrows = 0, numcols = 0, total_nnz = 0;
+        std::vector<NT> whole;
+        if (infile.is_open()) {
+            infile.clear();
+            infile.seekg(0);
+            infile >> numrows >> numcols >> total_nnz;
+            whole.assign((size_t)(numcols == 1 ? numrows : numcols), NT());
+            long long r, c;
+            double v;
+            for (long long q = 0; q < total_nnz && (infile >> r >> c >> v); ++q) {
+                const long long ind = (numcols == 1 ? r : c) - 1;
+                if (ind >= 0 && ind < (long long)whole.size()) whole[(size_t)ind] = (NT)v;
+            }
+        }
+        Scatter(whole);
+        return infile;
     }
     // the whole vector on every process (the concatenation of the pieces in owner order)
     std::vector<NT> Gather() const {

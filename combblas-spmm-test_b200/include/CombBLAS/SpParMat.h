@@ -272,6 +272,44 @@ public:
         return (IT)commGrid->SumWorld(removed);
     }
 
+    // Fold the matrix along a dimension into a distributed vector (reference SpParMat.cpp:929-1100): dim == Row folds every
+    // row over its nonzeros (result of length getnrow()), dim == Column every column (length getncol()); the fold starts from
+    // `id`, applies `uop` to every value and combines with `op`; rows / columns without nonzeros hold `id`.  Local fold first,
+    // then the partial vectors of the processes that share the rows (columns), in grid order.  Host-side, as in the reference.
+    template <typename GIT, typename VT, typename _BinaryOperation, typename _UnaryOperation>
+    void Reduce(FullyDistVec<GIT, VT>& rvec, Dim dim, _BinaryOperation op, VT id, _UnaryOperation uop) const {
+        if (*rvec.getcommgrid() != *commGrid) {
+            SpParHelper::Print("Grids are not comparable, SpParMat::Reduce() fails!\n");
+            MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+        }
+        const int pr = commGrid->GetGridRows(), pc = commGrid->GetGridCols();
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq());
+        std::vector<VT> part(dim == Row ? (size_t)seq().getnrow() : (size_t)seq().getncol(), id);
+        for (int64_t p = 0; p < tup.getnnz(); ++p) {
+            VT& dst = part[dim == Row ? (size_t)tup.rowindex(p) : (size_t)tup.colindex(p)];
+            dst = op(dst, (VT)uop(tup.numvalue(p)));
+        }
+        std::vector<std::vector<char>> all;
+        cb_host_allgatherv(part.data(), part.size() * sizeof(VT), all);
+        std::vector<VT> whole((size_t)(dim == Row ? getnrow() : getncol()), id);
+        size_t off = 0;
+        for (int b = 0; b < (dim == Row ? pr : pc); ++b) {
+            size_t blen = 0;
+            for (int q = 0; q < (dim == Row ? pc : pr); ++q) {
+                const std::vector<char>& buf = all[(size_t)(dim == Row ? commGrid->GetRank(b, q) : commGrid->GetRank(q, b))];
+                blen = buf.size() / sizeof(VT);
+                const VT* v = reinterpret_cast<const VT*>(buf.data());
+                for (size_t i = 0; i < blen; ++i) whole[off + i] = op(whole[off + i], v[i]);
+            }
+            off += blen;
+        }
+        rvec.Scatter(whole);
+    }
+    template <typename GIT, typename VT, typename _BinaryOperation>
+    void Reduce(FullyDistVec<GIT, VT>& rvec, Dim dim, _BinaryOperation op, VT id) const {
+        Reduce(rvec, dim, op, id, [](NT v) { return v; });
+    }
+
     // A <- A^T (reference SpParMat.cpp Transpose: tiles swap between processes (i,j) and (j,i)).  Here every process
     // publishes its triples in global coordinates and keeps the transposed ones it owns - host-side, like all ingestion.
     void Transpose() {

@@ -152,6 +152,25 @@ def test_reference_transposetest_driver_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_reducetest_driver_unmodified_on_the_gpu(tmp_path):
+    # the reference's self-checking ReleaseTests/ReduceTest.cpp, compiled unmodified against this layer (oracle/_ref/ReduceTest_b200)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ReduceTest_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ReduceTest_b200 was not built (needs the reference tree)")
+    from tests.test_host_mock_cpu import write_triples, write_vector
+    g = np.load(os.path.join(G, "small.npz"))
+    m, n = int(g["nonsym_m"]), int(g["nonsym_n"])
+    I, J, V = g["nonsym_I"], g["nonsym_J"], g["nonsym_V"]
+    a, cs, rs = str(tmp_path / "a.txt"), str(tmp_path / "colsums.txt"), str(tmp_path / "rowsums.txt")
+    write_triples(a, m, n, I, J, V)
+    write_vector(cs, np.bincount(J, weights=V, minlength=n))
+    write_vector(rs, np.bincount(I, weights=V, minlength=m))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, a, cs, rs], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Reduction via summation working correctly" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_reference_genwritematrix_driver_unmodified_on_the_gpu(tmp_path):
     # oracle/_ref/GenWriteMatrix_b200 = the reference's own ReleaseTests/GenWriteMatrix.cpp (its benchmark-input generator) compiled
     # UNMODIFIED against this host layer: DistEdgeList -> SpParMat on the device generator, RemoveLoops, Transpose, +=, ParallelWriteMM

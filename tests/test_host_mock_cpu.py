@@ -212,3 +212,35 @@ def test_reference_transposetest_driver_compiles_unmodified_and_passes(driver, t
     assert "Transpose working correctly" in se
     write_triples(str(tmp_path / "bad.txt"), n, m, g["nonsym_J"][:-1], g["nonsym_I"][:-1], ones[:-1])       # one entry missing
     assert "ERROR in transpose" in run(exe, tmp_path, "a.txt", "bad.txt").stderr
+
+
+def write_vector(path, vals):
+    with open(path, "w") as f:
+        f.write(f"{len(vals)} 1 {len(vals)}\n")
+        for i, v in enumerate(vals):
+            f.write(f"{i + 1} 1 {float(v)!r}\n")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ReleaseTests/ReduceTest.cpp"), reason="the reference tree is not mounted here")
+def test_reference_reducetest_driver_compiles_unmodified_and_passes(driver, tmp_path):
+    # the reference's self-checking ReleaseTests/ReduceTest.cpp: SpParMat::Reduce along rows and columns against vectors read with
+    # FullyDistVec::ReadDistribute, compared with the error-tolerant operator==
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "ReduceTest_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, "/root/reference/ReleaseTests/ReduceTest.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
+                          timeout=600)
+    g = np.load(os.path.join(G, "small.npz"))
+    m, n = int(g["nonsym_m"]), int(g["nonsym_n"])
+    I, J, V = g["nonsym_I"], g["nonsym_J"], g["nonsym_V"]
+    a, cs, rs = str(tmp_path / "a.txt"), str(tmp_path / "colsums.txt"), str(tmp_path / "rowsums.txt")
+    write_triples(a, m, n, I, J, V)
+    write_vector(cs, np.bincount(J, weights=V, minlength=n))
+    write_vector(rs, np.bincount(I, weights=V, minlength=m))
+    assert "Reduction via summation working correctly" in run(exe, a, cs, rs).stderr
+    so, se = run_grid(exe, 4, tmp_path / "rdv", a, cs, rs)
+    assert "Reduction via summation working correctly" in se
+    wrong = np.bincount(I, weights=V, minlength=m)
+    wrong[m // 2] += 1.0
+    write_vector(rs, wrong)
+    assert "ERROR in Reduce via summation" in run(exe, a, cs, rs).stderr
