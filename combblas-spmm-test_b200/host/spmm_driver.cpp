@@ -200,12 +200,12 @@ int main(int argc, char* argv[]) {
             }
             FullyDistVec<int64_t, int64_t> y = SpMV<MinPlusSRing<int64_t, int64_t>>(A, x);
             ok = ok && y.TotalLength() == m;
-            // the same product as an n x 1 panel
-            DenseParMat<int64_t, int64_t> X1 = DenseParMat<int64_t, int64_t>::Global(0, grid, n, 1);
+            // the same product through SpMM: x repeated in one panel column per processor column (every process owns one)
+            DenseParMat<int64_t, int64_t> X1 = DenseParMat<int64_t, int64_t>::Global(0, grid, n, grid->GetGridCols());
             {
                 const std::vector<int64_t> xw = x.Gather();
                 int64_t r0, c0;
-                X1.GetPlaceInGlobalGrid(n, 1, r0, c0);
+                X1.GetPlaceInGlobalGrid(n, (int64_t)grid->GetGridCols(), r0, c0);
                 for (int64_t i = 0; i < X1.getlocalrows(); ++i)
                     for (int64_t j = 0; j < X1.getlocalcols(); ++j) X1(i, j) = xw[(size_t)(r0 + i)];
             }

@@ -65,9 +65,10 @@ DenseParMat<IU, typename promote_trait<NUM, NUV>::T_promote> SpMM(const SpParMat
 // Dense SpMV: y = A (x).(+) x with a FullyDistVec operand and result, the reference's SpMV<SR>(A, x)
 // (include/CombBLAS/ParFriends.h:1924-1996).  The reference moves x to the transposed process (TransposeVector), gathers
 // it along the processor column, runs dcsc_gespmv on an id()-filled local y (SR::axpy, Friends.h:63-78) and reduces y along
-// the processor row.  Here the vector is handed to the SUMMA engine as an n x 1 panel (it lives on the last processor
-// column of the DenseParMat distribution), the multiply runs on the GPUs, and the result is cut back into FullyDistVec
-// pieces.  Starting from id() matters for one semiring: SelectMax<bool,T> yields max(-1, x) here, not x, for x < -1.
+// the processor row.  Same algorithm here: every process runs the local multiply on ITS tile on its GPU (cb_spmm_local with
+// a one-column panel), the partial vectors are folded along the processor row and cut into FullyDistVec pieces; the
+// exchanges of vector pieces are host-side.  Starting from id() matters for one semiring: SelectMax<bool,T> yields
+// max(-1, x) here, not x, for x < -1.
 template <typename IU, typename NUM, typename NUV, typename UDER>
 bool CheckSpMVCompliance(const SpParMat<IU, NUM, UDER>& A, const FullyDistVec<IU, NUV>& x) {         // ParFriends.h:1350-1366
     if (*(A.getcommgrid()) != *(x.getcommgrid())) {
@@ -89,28 +90,45 @@ bool CheckSpMVCompliance(const SpParMat<IU, NUM, UDER>& A, const FullyDistVec<IU
 template <typename SR, typename IU, typename NUM, typename NUV, typename UDER>
 FullyDistVec<IU, typename promote_trait<NUM, NUV>::T_promote> SpMV(const SpParMat<IU, NUM, UDER>& A, const FullyDistVec<IU, NUV>& x) {
     typedef typename promote_trait<NUM, NUV>::T_promote T_promote;
+    typedef typename cb_storage<T_promote>::type ST;
+    static_assert(semiring_traits<SR>::supported, "this semiring / type combination is not implemented by the B200 engine");
     static_assert(std::is_same<T_promote, NUV>::value, "the vector must already have the promoted type");
     CheckSpMVCompliance(A, x);
     std::shared_ptr<CommGrid> grid = A.getcommgrid();
+    cb_ctx* ctx = grid->GetContext();
+    const int pr = grid->GetGridRows(), pc = grid->GetGridCols(), myrow = grid->GetRankInProcCol(), mycol = grid->GetRankInProcRow();
     const IU gm = A.getnrow(), gn = A.getncol();
-    // x as an n x 1 panel: rows block myprocrow, the single column belongs to the last processor column
-    const std::vector<NUV> xw = x.Gather();
-    DenseParMat<IU, NUV> X = DenseParMat<IU, NUV>::Global(NUV(), grid, gn, 1);
-    IU r0, c0;
-    X.GetPlaceInGlobalGrid(gn, (IU)1, r0, c0);
-    if (X.getlocalcols() == 1)
-        for (IU i = 0; i < X.getlocalrows(); ++i) X(i, 0) = xw[(size_t)(r0 + i)];
-    DenseParMat<IU, T_promote> Y = SpMM<SR>(A, X);
-    // row blocks of y sit on the last processor column; everyone assembles the vector and keeps its FullyDistVec piece
+    // the reference's own 2D algorithm (ParFriends.h:1924-1996): every process multiplies ITS tile with the piece of x that
+    // matches its columns, then the partial results are folded along the processor row with SR::add
+    IU c0, cl, r0, rl;
+    DenseParMat<IU, NUV>::Block(gn, pc, mycol, c0, cl);
+    DenseParMat<IU, NUV>::Block(gm, pr, myrow, r0, rl);
+    const std::vector<NUV> xw = x.Gather();                                   // TransposeVector + Allgatherv of the reference
+    cb_dense *dX = nullptr, *dY = nullptr;
+    const int dt = cb_dtype_of<NUV>::value;
+    cb_check(cb_dense_alloc(ctx, cl, 1, dt, &dX), ctx, "cb_dense_alloc");
+    cb_check(cb_dense_alloc(ctx, rl, 1, dt, &dY), ctx, "cb_dense_alloc");
+    if (cl > 0) cb_check(cb_dense_upload(dX, xw.data() + c0, 1), ctx, "cb_dense_upload");
+    std::vector<ST> part((size_t)rl, (ST)SR::id());
+    cb_check(cb_spmm_local(ctx, A.DeviceTile(), dX, dY, semiring_traits<SR>::op, 0), ctx, "cb_spmm_local");       // dcsc_gespmv on the GPU
+    if (rl > 0) cb_check(cb_dense_download(dY, part.data(), 1), ctx, "cb_dense_download");
+    cb_check(cb_ctx_sync(ctx), ctx, "cb_ctx_sync");
+    cb_dense_free(dX);
+    cb_dense_free(dY);
+    // MPI_Reduce with SR::mpi_op along the processor row; y started as id(), so the fold does too
     std::vector<std::vector<char>> all;
-    cb_host_allgatherv(Y.data(), (size_t)Y.getlocalrows() * (size_t)Y.getlocalcols() * sizeof(T_promote), all);
-    std::vector<T_promote> yw;
-    yw.reserve((size_t)gm);
-    for (int i = 0; i < grid->GetGridRows(); ++i) {
-        const std::vector<char>& b = all[(size_t)grid->GetRank(i, grid->GetGridCols() - 1)];
-        const T_promote* v = reinterpret_cast<const T_promote*>(b.data());
-        for (size_t q = 0; q < b.size() / sizeof(T_promote); ++q) yw.push_back(SR::add(SR::id(), v[q]));     // y started as id()
+    cb_host_allgatherv(part.data(), part.size() * sizeof(ST), all);
+    std::vector<T_promote> yw((size_t)gm, SR::id());
+    for (int i = 0; i < pr; ++i) {
+        IU b0, bl;
+        DenseParMat<IU, NUV>::Block(gm, pr, i, b0, bl);
+        for (int j = 0; j < pc; ++j) {
+            const std::vector<char>& b = all[(size_t)grid->GetRank(i, j)];
+            const ST* v = reinterpret_cast<const ST*>(b.data());
+            for (size_t q = 0; q < b.size() / sizeof(ST); ++q) yw[(size_t)b0 + q] = SR::add(yw[(size_t)b0 + q], (T_promote)v[q]);
+        }
     }
+    (void)r0; (void)myrow;
     FullyDistVec<IU, T_promote> y(grid);
     y.Scatter(yw);
     return y;
