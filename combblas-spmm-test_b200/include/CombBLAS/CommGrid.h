@@ -34,6 +34,9 @@ public:
         }
         grrows = nrowproc;
         grcols = ncolproc;
+#ifndef CB_HAVE_MPI
+        cb_rt::grid_cols() = grcols;
+#endif
         myproccol = myrank % grcols;
         myprocrow = myrank / grcols;
         unsigned char uid[128] = {0};
@@ -80,8 +83,13 @@ public:
     int GetGridCols() const { return grcols; }
     int GetSize() const { return grrows * grcols; }
     MPI_Comm GetWorld() const { return commWorld; }
-    MPI_Comm GetRowWorld() const { return commWorld; }      // communicator handles are opaque here; the row / column
-    MPI_Comm GetColWorld() const { return commWorld; }      // collectives live inside the device context (GetContext)
+#ifndef CB_HAVE_MPI
+    MPI_Comm GetRowWorld() const { return 1000 + myprocrow; }     // handles of cb_mpi.h: processes with the same myprocrow /
+    MPI_Comm GetColWorld() const { return 2000 + myproccol; }     // myproccol; the device collectives live inside GetContext()
+#else
+    MPI_Comm GetRowWorld() const { return commWorld; }
+    MPI_Comm GetColWorld() const { return commWorld; }
+#endif
 
     cb_ctx* GetContext() const { return ctx.get(); }
 

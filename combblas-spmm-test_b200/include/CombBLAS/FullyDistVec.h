@@ -187,6 +187,17 @@ public:
         Scatter(whole);
         return infile;
     }
+    // the whole vector as text written by `master`, in the format ReadDistribute reads: "length 1 length" and one
+    // "index 1 value" line per element, one-based (reference FullyDistVec.cpp:504-510 through FullyDistSpVec::SaveGathered)
+    void SaveGathered(std::ofstream& outfile, int master) const {
+        const std::vector<NT> whole = Gather();
+        if (commGrid->GetRank() == master && outfile.is_open()) {
+            outfile.precision(17);
+            outfile << glen << "\t" << 1 << "\t" << glen << "\n";
+            for (size_t i = 0; i < whole.size(); ++i) outfile << i + 1 << "\t" << 1 << "\t" << +whole[i] << "\n";
+            outfile.flush();
+        }
+    }
     // the whole vector on every process (the concatenation of the pieces in owner order)
     std::vector<NT> Gather() const {
         std::vector<std::vector<char>> all;

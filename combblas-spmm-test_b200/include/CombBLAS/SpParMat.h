@@ -77,6 +77,16 @@ public:
         (void)removeloops;                                        // the device generator never emits self loops
         GenGraph500(rhs.scale, rhs.ef, false, 0, !std::is_same<NT, bool>::value, 1, rhs.init);
     }
+    // value-type conversion (reference SpParMat.h converting constructor / operator SpParMat<IT,NNT,NDER>()): same structure,
+    // every value cast to NT (a nonzero becomes true for bool)
+    template <class NNT, class NDER>
+    SpParMat(const SpParMat<IT, NNT, NDER>& rhs) : commGrid(rhs.getcommgrid()), spSeq(nullptr), gm(rhs.getnrow()), gn(rhs.getncol()) {
+        auto src = TilesToTuples(rhs.seq());
+        SpTuples<LocalIT, NT> t(0, (LocalIT)rhs.seq().getnrow(), (LocalIT)rhs.seq().getncol());
+        t.tuples.reserve((size_t)src.getnnz());
+        for (int64_t p = 0; p < src.getnnz(); ++p) t.tuples.emplace_back((LocalIT)src.rowindex(p), (LocalIT)src.colindex(p), (NT)src.numvalue(p));
+        spSeq = new DER(t, false);
+    }
     SpParMat(const SpParMat& rhs) : commGrid(rhs.commGrid), spSeq(new DER(rhs.seq())), gm(rhs.gm), gn(rhs.gn) {}
     SpParMat& operator=(const SpParMat& rhs) {
         if (this != &rhs) { DER* copy = new DER(rhs.seq()); Release(); commGrid = rhs.commGrid; spSeq = copy; gm = rhs.gm; gn = rhs.gn; }
@@ -270,6 +280,23 @@ public:
             spSeq = fresh; gm = keep_m; gn = keep_n;
         }
         return (IT)commGrid->SumWorld(removed);
+    }
+
+    // columns ci (LOCAL indices, the same list on every process) of every tile: a matrix with |ci| columns per processor column
+    // (reference SpParMat.cpp:2012-2017)
+    SpParMat SubsRefCol(const std::vector<IT>& ci) const {
+        std::vector<LocalIT> ri, lci(ci.begin(), ci.end());
+        return SpParMat(new DER(seq()(ri, lci)), commGrid);
+    }
+    // apply a unary function to every stored value (reference SpParMat.h Apply)
+    template <typename _UnaryOperation>
+    void Apply(_UnaryOperation f) {
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq());
+        for (auto& e : tup.tuples) std::get<2>(e) = (NT)f(std::get<2>(e));
+        DER* fresh = new DER(tup, false);
+        const IT keep_m = gm, keep_n = gn;
+        Release();
+        spSeq = fresh; gm = keep_m; gn = keep_n;
     }
 
     // Fold the matrix along a dimension into a distributed vector (reference SpParMat.cpp:929-1100): dim == Row folds every
@@ -489,6 +516,33 @@ private:
     int64_t dnnz = 0;
     bool devvals = false;
 };
+
+// Element-wise product of two sparse matrices with the same distribution (reference ParFriends.h:2174-2200, sequential
+// EWiseMult of Friends.h): exclude == false keeps the entries present in both, value A(i,j) * B(i,j) in the promoted type;
+// exclude == true keeps the entries of A that are NOT in B, with A's values.
+template <typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, typename promote_trait<NU1, NU2>::T_promote, SpDCCols<typename UDERA::LocalIT, typename promote_trait<NU1, NU2>::T_promote>>
+EWiseMult(const SpParMat<IU, NU1, UDERA>& A, const SpParMat<IU, NU2, UDERB>& B, bool exclude) {
+    typedef typename promote_trait<NU1, NU2>::T_promote N_promote;
+    typedef typename UDERA::LocalIT LIT;
+    typedef SpDCCols<LIT, N_promote> DER_promote;
+    if (*A.getcommgrid() != *B.getcommgrid()) {
+        SpParHelper::Print("Grids are not comparable elementwise multiplication\n");
+        MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+    }
+    auto ta = TilesToTuples(A.seq());
+    auto tb = TilesToTuples(B.seq());                             // both column-major sorted
+    SpTuples<LIT, N_promote> out(0, (LIT)A.seq().getnrow(), (LIT)A.seq().getncol());
+    int64_t q = 0;
+    for (int64_t p = 0; p < ta.getnnz(); ++p) {
+        const auto ka = std::make_pair(ta.colindex(p), ta.rowindex(p));
+        while (q < tb.getnnz() && std::make_pair((decltype(ka.first))tb.colindex(q), (decltype(ka.second))tb.rowindex(q)) < ka) ++q;
+        const bool both = q < tb.getnnz() && (decltype(ka.first))tb.colindex(q) == ka.first && (decltype(ka.second))tb.rowindex(q) == ka.second;
+        if (exclude && !both) out.tuples.emplace_back(ta.rowindex(p), ta.colindex(p), (N_promote)ta.numvalue(p));
+        if (!exclude && both) out.tuples.emplace_back(ta.rowindex(p), ta.colindex(p), (N_promote)((N_promote)ta.numvalue(p) * (N_promote)tb.numvalue(q)));
+    }
+    return SpParMat<IU, N_promote, DER_promote>(new DER_promote(out, false), A.getcommgrid(), A.getnrow(), A.getncol());
+}
 
 template <class IT, class NT>
 template <typename DER>

@@ -123,6 +123,35 @@ public:
         ir.assign((size_t)ess[0], 0); numx.assign((size_t)ess[0], ST());
         jc.assign((size_t)ess[3], 0); cp.assign((size_t)ess[3] + 1, 0);
     }
+    // build from a tuple array (reference SpDCCols.cpp Create(size, nRow, nCol, mytuples)); the array is consumed like there
+    void Create(IT size, IT nRow, IT nCol, std::tuple<IT, IT, NT>* mytuples) {
+        m = nRow; n = nCol;
+        std::vector<std::tuple<IT, IT, NT>> t;
+        if (mytuples && size > 0) t.assign(mytuples, mytuples + size);
+        delete[] mytuples;
+        build(t);
+    }
+    // A(ri, ci): the rows ri and columns ci of the tile, in that order; an empty index vector means "all"
+    // (reference SpDCCols.cpp operator()(ri, ci), used as A.seq()(empty, single) and by SubsRefCol)
+    SpDCCols operator()(const std::vector<IT>& ri, const std::vector<IT>& ci) const {
+        std::vector<std::vector<IT>> newrow, newcol;             // old index -> new positions (an index may be listed twice)
+        if (!ri.empty()) { newrow.resize((size_t)m); for (size_t q = 0; q < ri.size(); ++q) newrow[(size_t)ri[q]].push_back((IT)q); }
+        if (!ci.empty()) { newcol.resize((size_t)n); for (size_t q = 0; q < ci.size(); ++q) newcol[(size_t)ci[q]].push_back((IT)q); }
+        std::vector<std::tuple<IT, IT, NT>> t;
+        for (size_t c = 0; c < jc.size(); ++c)
+            for (IT p = cp[c]; p < cp[c + 1]; ++p) {
+                const IT r = ir[(size_t)p], col = jc[c];
+                const std::vector<IT> one_r{r}, one_c{col};
+                const std::vector<IT>& rs = ri.empty() ? one_r : newrow[(size_t)r];
+                const std::vector<IT>& cs = ci.empty() ? one_c : newcol[(size_t)col];
+                for (IT nr : rs) for (IT nc : cs) t.emplace_back(nr, nc, (NT)numx[(size_t)p]);
+            }
+        SpDCCols out;
+        out.m = ri.empty() ? m : (IT)ri.size();
+        out.n = ci.empty() ? n : (IT)ci.size();
+        out.build(t);
+        return out;
+    }
     Arr<IT, NT> GetArrays() const {                              // SpDCCols.cpp:826-846: {cp, jc, ir | numx}
         Arr<IT, NT> a(3, 1);
         SpDCCols* self = const_cast<SpDCCols*>(this);

@@ -46,17 +46,27 @@ inline std::string rendezvous_dir() {
     const char* run = std::getenv("TORCHELASTIC_RUN_ID");
     return std::string("/tmp/cb_rdv_") + (port ? port : "0") + "_" + (run ? run : "none") + "_" + std::to_string((long)getppid());
 }
-inline long& seq() { static long s = 0; return s; }
+// Row / column worlds as distinct handles: 1 = world, 1000 + r = processor row r, 2000 + c = processor column c of the most
+// recently built CommGrid (its shape is kept here).  Enough for user code that reduces over GetRowWorld() / GetColWorld().
+inline int& grid_cols() { static int pc = 1; return pc; }
+inline bool in_comm(int comm, int rank) {
+    if (comm >= 2000) return rank % grid_cols() == comm - 2000;
+    if (comm >= 1000) return rank / grid_cols() == comm - 1000;
+    return true;
+}
+inline long& seq(int comm) { static long s[3] = {0, 0, 0}; return s[comm >= 2000 ? 2 : comm >= 1000 ? 1 : 0]; }
 
-// every rank contributes `bytes` bytes; afterwards everyone holds all contributions in rank order
-inline void allgather_bytes(const void* mine, size_t bytes, std::vector<char>& all) {
+// every member of `comm` contributes `bytes` bytes; afterwards every member holds all contributions, indexed by WORLD rank
+// (the slots of non-members stay zero).  Each communicator counts its own operations, so the processor rows / columns may
+// run different numbers of collectives, as they may with a real MPI.
+inline void allgather_bytes(const void* mine, size_t bytes, std::vector<char>& all, int comm = 1) {
     const int p = size(), r = rank();
     all.assign(bytes * (size_t)p, 0);
     if (p == 1) { std::memcpy(all.data(), mine, bytes); return; }
     const std::string dir = rendezvous_dir();
     mkdir(dir.c_str(), 0700);
-    const long s = seq()++;
-    const std::string base = dir + "/op" + std::to_string(s) + ".r";
+    const long s = seq(comm)++;
+    const std::string base = dir + "/c" + std::to_string(comm) + "_op" + std::to_string(s) + ".r";
     {
         const std::string tmp = base + std::to_string(r) + ".tmp", fin = base + std::to_string(r);
         FILE* f = std::fopen(tmp.c_str(), "wb");
@@ -66,6 +76,7 @@ inline void allgather_bytes(const void* mine, size_t bytes, std::vector<char>& a
         std::rename(tmp.c_str(), fin.c_str());
     }
     for (int q = 0; q < p; ++q) {
+        if (!in_comm(comm, q)) continue;
         const std::string fin = base + std::to_string(q);
         for (int tries = 0;; ++tries) {
             FILE* f = std::fopen(fin.c_str(), "rb");
@@ -88,10 +99,52 @@ inline void bcast_bytes(void* buf, size_t bytes, int root) {
 
 }  // namespace cb_rt
 
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+#define MPI_INT 104
+#define MPI_LONG_LONG 108
+#define MPI_DOUBLE 208
+#define MPI_FLOAT 204
+#define MPI_SUM 1
+#define MPI_MAX 2
+#define MPI_MIN 3
+namespace cb_rt {
+template <class T>
+inline void reduce_typed(const std::vector<char>& all, size_t bytes, int count, int op, MPI_Comm comm, T* out) {
+    bool first = true;
+    for (int q = 0; q < size(); ++q) {
+        if (!in_comm(comm, q)) continue;
+        const T* v = reinterpret_cast<const T*>(all.data() + bytes * (size_t)q);
+        for (int i = 0; i < count; ++i) out[i] = first ? v[i] : op == MPI_SUM ? (T)(out[i] + v[i]) : op == MPI_MAX ? (out[i] < v[i] ? v[i] : out[i]) : (v[i] < out[i] ? v[i] : out[i]);
+        first = false;
+    }
+}
+}  // namespace cb_rt
+inline int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm comm) {
+    const size_t bytes = (size_t)count * (size_t)(dt % 100);
+    std::vector<char> all;
+    cb_rt::allgather_bytes(sendbuf, bytes, all, comm);
+    switch (dt) {
+        case MPI_INT: cb_rt::reduce_typed<int>(all, bytes, count, op, comm, (int*)recvbuf); break;
+        case MPI_LONG_LONG: cb_rt::reduce_typed<long long>(all, bytes, count, op, comm, (long long*)recvbuf); break;
+        case MPI_DOUBLE: cb_rt::reduce_typed<double>(all, bytes, count, op, comm, (double*)recvbuf); break;
+        case MPI_FLOAT: cb_rt::reduce_typed<float>(all, bytes, count, op, comm, (float*)recvbuf); break;
+        default: std::fprintf(stderr, "cb_mpi: MPI_Allreduce datatype %d\n", dt); std::_Exit(1);
+    }
+    return MPI_SUCCESS;
+}
 inline int MPI_Init(int*, char***) { return MPI_SUCCESS; }
 inline int MPI_Finalize() { if (cb_rt::size() > 1) cb_rt::barrier(); return MPI_SUCCESS; }
-inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = cb_rt::rank(); return MPI_SUCCESS; }
-inline int MPI_Comm_size(MPI_Comm, int* s) { *s = cb_rt::size(); return MPI_SUCCESS; }
+inline int MPI_Comm_rank(MPI_Comm c, int* r) {
+    const int w = cb_rt::rank(), pc = cb_rt::grid_cols();
+    *r = c >= 2000 ? w / pc : c >= 1000 ? w % pc : w;            // rank in a column world = processor row, in a row world = column
+    return MPI_SUCCESS;
+}
+inline int MPI_Comm_size(MPI_Comm c, int* s) {
+    const int p = cb_rt::size(), pc = cb_rt::grid_cols();
+    *s = c >= 2000 ? p / pc : c >= 1000 ? pc : p;
+    return MPI_SUCCESS;
+}
 inline int MPI_Barrier(MPI_Comm) { cb_rt::barrier(); return MPI_SUCCESS; }
 inline int MPI_Abort(MPI_Comm, int code) { std::fprintf(stderr, "MPI_Abort(%d)\n", code); std::fflush(stderr); std::_Exit(code & 0xff ? code & 0xff : 1); }
 inline int MPI_Pcontrol(int, ...) { return MPI_SUCCESS; }        // profiling hook of ReleaseTests/MultTiming.cpp:67

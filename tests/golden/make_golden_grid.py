@@ -10,6 +10,8 @@ Contents (results of the reference's own multi-proce
                                  (R-MAT scale 9, edge factor 8, seed 3, ragged m = n-5, n = n-3, k = 13)
   <case>_p4_spmv                 the same product through k x SpMV<SR>(A, FullyDistVec) on 2x2 processes
   layout_<glen>_p<p>_{until,len,owner,lind}   the FullyDistVec distribution computed by the reference's FullyDist.h
+  betwcent_p1, betwcent_p4      betweenness-centrality scores written by the reference's own Applications/BetwCent.cpp (unmodified)
+                                 on 1 process and on 2x2 processes for the graph of betwcent_input()
   hepth_p4, hepth_p4_report      BASELINE config C1 on 2x2 processes: Applications/hep-th.mtx read by the reference's own
                                  ParallelReadMM on four ranks, x X(k=16, fp64, seed 42) through Mult_AnXBn_Synch
 Only numeric outputs are stored; inputs are regenerated from the counter-based generators at test time.
@@ -38,6 +40,21 @@ CASES = {  # the cases of tests/summa_worker.py
 # FullyDistVec layouts stored from the reference: (global length, processes); short lengths hit the "everything on the last
 # processor row / column" branches of FullyDist::Owner (FullyDist.h:117-146)
 LAYOUTS = [(11, 4), (8361, 4), (100, 9), (5, 9), (2, 9), (1000, 16)]
+
+
+# Applications/BetwCent.cpp: <dir>/input.mtx, K4APPROX (2^K4 starting vertices), BATCHSIZE
+BC_K4APPROX, BC_BATCH = 6, 32
+
+
+def betwcent_input(directory):
+    """input.mtx for the betweenness-centrality application: R-MAT scale 8 (symmetric pattern), Matrix Market general"""
+    n, I, J = O.rmat_matrix(8, 8, seed=5)
+    with open(os.path.join(directory, "input.mtx"), "w") as f:
+        f.write("%%MatrixMarket matrix coordinate pattern general\n")
+        f.write(f"{n} {n} {len(I)}\n")
+        for i, j in zip(I, J):
+            f.write(f"{i + 1} {j + 1}\n")
+    return n
 
 
 def operands(case, scale=SCALE, k=K):
@@ -69,6 +86,16 @@ def main():
     for glen, p in LAYOUTS:
         for key, val in O.ref_grid_layout(glen, p).items():
             out[f"layout_{glen}_p{p}_{key}"] = val
+    # the reference's own application Applications/BetwCent.cpp on the graph of betwcent_input(): 1 process and 2x2 processes
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory(prefix="cb_betwcent_") as d:
+        betwcent_input(d)
+        for p, exe, env in ((1, "betwcent_ref", {}), (4, "betwcent_grid", {"CBMPI_NP": "4"})):
+            res = os.path.join(d, f"bc_{p}.txt")
+            subprocess.run([os.path.join(ROOT, "oracle", "_ref", exe), d, str(BC_K4APPROX), str(BC_BATCH), res], check=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS="1", **env), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[f"betwcent_p{p}"] = np.loadtxt(res, skiprows=1)[:, 2]
     hep = np.load(os.path.join(OUT, "hepth.npz"))
     Y, report = O.ref_grid_mm("/root/reference/Applications/hep-th.mtx", 4, O.dense_operand(int(hep["n"]), 16, 42, np.float64))
     out["hepth_p4"], out["hepth_p4_report"] = Y, np.array(report)

@@ -152,6 +152,25 @@ def test_reference_transposetest_driver_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_betwcent_application_unmodified_on_the_gpu(tmp_path):
+    # oracle/_ref/BetwCent_b200 = the reference's Applications/BetwCent.cpp compiled UNMODIFIED against this host layer and
+    # libcombblas_b200.so: batched BFS + back-propagation, every step a tall-skinny PSpGEMM on the GPU.  Scores against the ones
+    # the reference itself wrote for the same graph (tests/golden/grid_ref.npz, betwcent_p1).
+    exe = os.path.join(ROOT, "oracle", "_ref", "BetwCent_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/BetwCent_b200 was not built (needs the reference tree)")
+    from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
+    betwcent_input(str(tmp_path))
+    out = str(tmp_path / "bc.txt")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Computation finished" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    gold = np.load(os.path.join(G, "grid_ref.npz"))["betwcent_p1"]
+    got = np.loadtxt(out, skiprows=1)[:, 2]
+    assert np.abs(got - gold).max() <= 1e-9 * np.abs(gold).max()
+
+
+@pytest.mark.gpu
 def test_reference_reducetest_driver_unmodified_on_the_gpu(tmp_path):
     # the reference's self-checking ReleaseTests/ReduceTest.cpp, compiled unmodified against this layer (oracle/_ref/ReduceTest_b200)
     exe = os.path.join(ROOT, "oracle", "_ref", "ReduceTest_b200")

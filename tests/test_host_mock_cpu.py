@@ -244,3 +244,29 @@ def test_reference_reducetest_driver_compiles_unmodified_and_passes(driver, tmp_
     wrong[m // 2] += 1.0
     write_vector(rs, wrong)
     assert "ERROR in Reduce via summation" in run(exe, a, cs, rs).stderr
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Applications/BetwCent.cpp"), reason="the reference tree is not mounted here")
+def test_reference_betwcent_application_unmodified_matches_the_reference(driver, tmp_path):
+    # Applications/BetwCent.cpp - the application that calls the tall-skinny PSpGEMM with DenseParMat
+    # updates around it - compiled as it is against the host layer.  Its scores are compared with the scores the reference itself
+    # wrote for the same graph on 1 process and on 2x2 processes (tests/golden/grid_ref.npz; the two differ by up to 670 because
+    # every processor column picks its own roots, so the 2x2 comparison checks the distributed semantics too).
+    from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "BetwCent_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, "/root/reference/Applications/BetwCent.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
+                          timeout=600)
+    gold = np.load(os.path.join(G, "grid_ref.npz"))
+    betwcent_input(str(tmp_path))
+    one = str(tmp_path / "bc1.txt")
+    r = run(exe, tmp_path, BC_K4APPROX, BC_BATCH, one)
+    assert "Computation finished" in r.stdout
+    got = np.loadtxt(one, skiprows=1)[:, 2]
+    assert np.abs(got - gold["betwcent_p1"]).max() <= 1e-9 * np.abs(gold["betwcent_p1"]).max()
+    four = str(tmp_path / "bc4.txt")
+    run_grid(exe, 4, tmp_path / "rdv", tmp_path, BC_K4APPROX, BC_BATCH, four)
+    got4 = np.loadtxt(four, skiprows=1)[:, 2]
+    assert np.abs(got4 - gold["betwcent_p4"]).max() <= 1e-9 * np.abs(gold["betwcent_p4"]).max()
+    assert np.abs(gold["betwcent_p1"] - gold["betwcent_p4"]).max() > 1.0          # the two references really differ
