@@ -265,6 +265,14 @@ def test_reference_betwcent_application_unmodified_matches_the_reference(driver,
     assert "Computation finished" in r.stdout
     got = np.loadtxt(one, skiprows=1)[:, 2]
     assert np.abs(got - gold["betwcent_p1"]).max() <= 1e-9 * np.abs(gold["betwcent_p1"]).max()
+    # the same run with the column filter for sparse right-hand sides (CB_SPGEMM_FILTER=1): BFS frontiers are sparse, the filter engages
+    os.environ["CB_SPGEMM_FILTER"] = "1"
+    try:
+        filt = str(tmp_path / "bc1f.txt")
+        run(exe, tmp_path, BC_K4APPROX, BC_BATCH, filt)
+    finally:
+        del os.environ["CB_SPGEMM_FILTER"]
+    assert np.abs(np.loadtxt(filt, skiprows=1)[:, 2] - gold["betwcent_p1"]).max() <= 1e-9 * np.abs(gold["betwcent_p1"]).max()
     four = str(tmp_path / "bc4.txt")
     run_grid(exe, 4, tmp_path / "rdv", tmp_path, BC_K4APPROX, BC_BATCH, four)
     got4 = np.loadtxt(four, skiprows=1)[:, 2]
