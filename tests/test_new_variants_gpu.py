@@ -216,3 +216,21 @@ def test_driver_sparse_rhs_with_column_filter():
     build()
     r = subprocess.run([DRIVER, "spgemm", "11", "40", "1"], capture_output=True, text=True, timeout=300, env=dict(os.environ, CB_SPGEMM_FILTER="1"))
     assert r.returncode == 0 and "SpGEMM (sparse x sparse) working correctly" in r.stderr, r.stdout + r.stderr
+
+
+def test_betwcent_application_with_column_filter(tmp_path):
+    # the reference's unmodified BetwCent on this layer with CB_SPGEMM_FILTER=1: same scores as the reference wrote
+    import numpy as np
+    exe = os.path.join(ROOT, "oracle", "_ref", "BetwCent_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/BetwCent_b200 was not built (needs the reference tree)")
+    from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
+    betwcent_input(str(tmp_path))
+    out = str(tmp_path / "bc.txt")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out], capture_output=True, text=True, timeout=600,
+                       env=dict(env, CB_SPGEMM_FILTER="1"))
+    assert r.returncode == 0 and "Computation finished" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "grid_ref.npz"))["betwcent_p1"]
+    got = np.loadtxt(out, skiprows=1)[:, 2]
+    assert np.abs(got - gold).max() <= 1e-9 * np.abs(gold).max()
