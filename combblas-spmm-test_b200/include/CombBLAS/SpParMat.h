@@ -282,6 +282,30 @@ public:
         return (IT)commGrid->SumWorld(removed);
     }
 
+    // value(i,j) <- op(value(i,j), x[j]) for dim == Column, x[i] for dim == Row (reference SpParMat.cpp:801-880)
+    template <typename _BinaryOperation>
+    void DimApply(Dim dim, const FullyDistVec<IT, NT>& x, _BinaryOperation op) {
+        if (*x.getcommgrid() != *commGrid) {
+            SpParHelper::Print("Grids are not comparable, SpParMat::DimApply() fails!\n");
+            MPI_Abort(MPI_COMM_WORLD, GRIDMISMATCH);
+        }
+        if (x.TotalLength() != (dim == Column ? getncol() : getnrow())) {
+            SpParHelper::Print("Vector length does not match the matrix dimension in DimApply\n");
+            MPI_Abort(MPI_COMM_WORLD, DIMMISMATCH);
+        }
+        const std::vector<NT> xw = x.Gather();
+        IT roff = 0, coff = 0;
+        GetPlaceInGlobalGrid(roff, coff);
+        SpTuples<LocalIT, NT> tup = TilesToTuples(seq());
+        for (auto& e : tup.tuples) {
+            const IT g = dim == Column ? (IT)std::get<1>(e) + coff : (IT)std::get<0>(e) + roff;
+            std::get<2>(e) = (NT)op(std::get<2>(e), xw[(size_t)g]);
+        }
+        DER* fresh = new DER(tup, false);
+        const IT keep_m = gm, keep_n = gn;
+        Release();
+        spSeq = fresh; gm = keep_m; gn = keep_n;
+    }
     // columns ci (LOCAL indices, the same list on every process) of every tile: a matrix with |ci| columns per processor column
     // (reference SpParMat.cpp:2012-2017)
     SpParMat SubsRefCol(const std::vector<IT>& ci) const {

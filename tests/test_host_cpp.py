@@ -171,6 +171,19 @@ def test_reference_betwcent_application_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_galerkinnew_driver_unmodified_on_the_gpu(tmp_path):
+    # the reference's self-checking SpGEMM test ReleaseTests/GalerkinNew.cpp, compiled unmodified against this layer
+    exe = os.path.join(ROOT, "oracle", "_ref", "GalerkinNew_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/GalerkinNew_b200 was not built (needs the reference tree)")
+    from tests.test_host_mock_cpu import galerkin_inputs
+    files = galerkin_inputs(str(tmp_path))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, *files], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Splitting approach is correct" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_reference_reducetest_driver_unmodified_on_the_gpu(tmp_path):
     # the reference's self-checking ReleaseTests/ReduceTest.cpp, compiled unmodified against this layer (oracle/_ref/ReduceTest_b200)
     exe = os.path.join(ROOT, "oracle", "_ref", "ReduceTest_b200")

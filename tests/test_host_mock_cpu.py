@@ -278,3 +278,38 @@ def test_reference_betwcent_application_unmodified_matches_the_reference(driver,
     got4 = np.loadtxt(four, skiprows=1)[:, 2]
     assert np.abs(got4 - gold["betwcent_p4"]).max() <= 1e-9 * np.abs(gold["betwcent_p4"]).max()
     assert np.abs(gold["betwcent_p1"] - gold["betwcent_p4"]).max() > 1.0          # the two references really differ
+
+
+def galerkin_inputs(d, n=40, m=12, seed=11):
+    """A = L + diag(D) (triples files A, L; vector file D) and a restriction matrix T (n x m) for ReleaseTests/GalerkinNew.cpp"""
+    rng = np.random.default_rng(seed)
+    LI, LJ = rng.integers(0, n, 160), rng.integers(0, n, 160)
+    keep = (LI != LJ)
+    key = np.unique(LI[keep] * n + LJ[keep])
+    LI, LJ = key // n, key % n
+    LV = rng.integers(1, 9, len(LI)).astype(float)
+    D = rng.integers(1, 9, n).astype(float)
+    TI, TJ = rng.integers(0, n, 60), rng.integers(0, m, 60)
+    key = np.unique(TI * m + TJ)
+    TI, TJ = key // m, key % m
+    TV = rng.integers(1, 5, len(TI)).astype(float)
+    write_triples(os.path.join(d, "A.txt"), n, n, np.concatenate([LI, np.arange(n)]), np.concatenate([LJ, np.arange(n)]), np.concatenate([LV, D]))
+    write_triples(os.path.join(d, "L.txt"), n, n, LI, LJ, LV)
+    write_vector(os.path.join(d, "D.txt"), D)
+    write_triples(os.path.join(d, "T.txt"), n, m, TI, TJ, TV)
+    return [os.path.join(d, f) for f in ("A.txt", "L.txt", "D.txt", "T.txt")]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ReleaseTests/GalerkinNew.cpp"), reason="the reference tree is not mounted here")
+def test_reference_galerkinnew_driver_compiles_unmodified_and_passes(driver, tmp_path):
+    # the reference's self-checking SpGEMM test ReleaseTests/GalerkinNew.cpp: S(AT) against SLT + (S scaled by D)T - five
+    # PSpGEMMs, Transpose, DimApply, +=, error-tolerant == ("Splitting approach is correct")
+    d = os.path.dirname(driver)
+    exe = os.path.join(d, "GalerkinNew_mock")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-w", f"-I{PKG}/include/mpi_shim", f"-I{PKG}/include", f"-I{ROOT}/include",
+                           "-o", exe, "/root/reference/ReleaseTests/GalerkinNew.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
+                          timeout=600)
+    files = galerkin_inputs(str(tmp_path))
+    assert "Splitting approach is correct" in run(exe, *files).stderr
+    so, se = run_grid(exe, 4, tmp_path / "rdv", *files)
+    assert "Splitting approach is correct" in se
