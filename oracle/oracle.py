@@ -58,7 +58,7 @@ def build(ref: bool | None = None) -> None:
     if ref is None:
         ref = os.path.isdir("/root/reference/include/CombBLAS")
     if ref:
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-j4", "-C", HERE, "ref"])
 
 
 def lib():
