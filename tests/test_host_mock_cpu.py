@@ -313,3 +313,24 @@ def test_reference_galerkinnew_driver_compiles_unmodified_and_passes(driver, tmp
     assert "Splitting approach is correct" in run(exe, *files).stderr
     so, se = run_grid(exe, 4, tmp_path / "rdv", *files)
     assert "Splitting approach is correct" in se
+
+
+def test_prebuilt_reference_binaries_for_the_gpu_box_are_current(driver, tmp_path):
+    # oracle/_ref/*_b200 are the binaries tests/test_host_cpp.py runs on the GPU box (the reference tree is not there to rebuild
+    # them); run the very same files here with the mock library in front of their RUNPATH so a stale build cannot travel
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "BetwCent_b200")):
+        pytest.skip("oracle/_ref/*_b200 not built (needs the reference tree)")
+    from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
+    subprocess.check_call(["make", "-s", "-C", os.path.join(PKG, "host"), "reference_drivers"])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["LD_LIBRARY_PATH"] = os.path.dirname(driver) + ":" + env.get("LD_LIBRARY_PATH", "")
+    betwcent_input(str(tmp_path))
+    out = str(tmp_path / "bc.txt")
+    r = subprocess.run([os.path.join(ref, "BetwCent_b200"), str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Computation finished" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    gold = np.load(os.path.join(G, "grid_ref.npz"))["betwcent_p1"]
+    assert np.abs(np.loadtxt(out, skiprows=1)[:, 2] - gold).max() <= 1e-9 * np.abs(gold).max()
+    files = galerkin_inputs(str(tmp_path))
+    r = subprocess.run([os.path.join(ref, "GalerkinNew_b200"), *files], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Splitting approach is correct" in r.stderr, r.stdout[-1500:] + r.stderr[-1500:]
