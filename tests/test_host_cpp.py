@@ -171,6 +171,28 @@ def test_reference_betwcent_application_unmodified_on_the_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_betwcent_application_unmodified_on_2x2_gpus(tmp_path):
+    # the same unmodified application on a 2x2 GPU grid against the scores the reference wrote on 2x2 PROCESSES (betwcent_p4)
+    import torch
+    from tests.test_summa_cpu import free_port
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    exe = os.path.join(ROOT, "oracle", "_ref", "BetwCent_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/BetwCent_b200 was not built (needs the reference tree)")
+    from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
+    betwcent_input(str(tmp_path))
+    out = str(tmp_path / "bc.txt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), exe, str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "Computation finished" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    gold = np.load(os.path.join(G, "grid_ref.npz"))["betwcent_p4"]
+    got = np.loadtxt(out, skiprows=1)[:, 2]
+    assert np.abs(got - gold).max() <= 1e-9 * np.abs(gold).max()
+
+
+@pytest.mark.gpu
 def test_reference_galerkinnew_driver_unmodified_on_the_gpu(tmp_path):
     # the reference's self-checking SpGEMM test ReleaseTests/GalerkinNew.cpp, compiled unmodified against this layer
     exe = os.path.join(ROOT, "oracle", "_ref", "GalerkinNew_b200")
