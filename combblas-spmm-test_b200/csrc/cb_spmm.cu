@@ -82,6 +82,8 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
     p.Y = Y; p.ldy_bytes = ldy * (int64_t)es;
     p.total_row_bytes = (int)row_bytes;
     p.accumulate = accumulate;
+    p.slab_bytes = ctx->k2_slab_bytes;
+    p.point = ctx->k2_point;
     cbk::HubPlan hub_plan;                        // opt-in persistent variants K2H / K2R (cb_hub.cu); inactive -> plain K2
     CB_TRY(cb_hub_plan(ctx, t, row_bytes, stream, &hub_plan));
     if (hub_plan.active) p.hub = &hub_plan;
@@ -96,6 +98,16 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
 }
 
 extern "C" {
+
+int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point) {
+    if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_config: null ctx");
+    if (slab_bytes < 0 || (slab_bytes != 0 && slab_bytes != 64 && slab_bytes != 128 && slab_bytes != 256 && slab_bytes != 512))
+        return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_config: slab of %d bytes (0 = automatic, 64, 128, 256 or 512)", slab_bytes);
+    if (point < -1 || point > 1) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_config: operating point %d (-1 automatic, 0 deep, 1 wide)", point);
+    ctx->k2_slab_bytes = slab_bytes;
+    ctx->k2_point = point;
+    return CB_OK;
+}
 
 int cb_spmm_local(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y, int semiring, int accumulate) {
     if (!ctx || !t || !X || !Y) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_local: null argument");

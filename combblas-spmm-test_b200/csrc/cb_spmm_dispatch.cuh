@@ -36,6 +36,8 @@ struct LaunchParams {
     int total_row_bytes;      // padded to 16
     int accumulate;
     const HubPlan* hub = nullptr;   // non-null: run the hub variant (K2H) with this shape
+    int slab_bytes = 0;             // > 0: column slabs of this width for plain K2 (0 = one slab as wide as the layout allows)
+    int point = -1;                 // operating point of plain K2: 0 deep, 1 wide, -1 choose by footprint
 };
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
@@ -161,12 +163,18 @@ template <class Op>
 static int launch_op(const LaunchParams& p) {
     const cb_tile* t = p.t;
     if (t->nnz > 0) {
-        const int nvec = p.total_row_bytes / 16;
+        // CB_K2_SLAB=<bytes>: run panels wider than this as sequential column slabs of that width (gridDim.y, scheduled slab
+        // after slab), so the X rows one pass touches are narrower and more of them stay in L2 (experiments / cb_k2_plan)
+        static const int slab_env = getenv("CB_K2_SLAB") ? atoi(getenv("CB_K2_SLAB")) : 0;
+        const int slab_force = p.slab_bytes > 0 ? p.slab_bytes : slab_env;
+        int nvec = p.total_row_bytes / 16;
+        if (slab_force >= 16 && nvec > slab_force / 16) nvec = slab_force / 16;
         int s = CB_HUB_FALLBACK;
         if (p.hub) s = launch_hub<Op>(p);
         if (s == CB_HUB_FALLBACK) {
             // X rows this tile touches: mostly L2-resident (R-MAT scale <= 22 class) or streaming from DRAM?
-            static const int force = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;      // 0 deep, 1 wide (experiments)
+            static const int force_env = getenv("CB_K2_POINT") ? atoi(getenv("CB_K2_POINT")) : -1;  // 0 deep, 1 wide (experiments)
+            const int force = p.point >= 0 ? p.point : force_env;
             const bool wide = force >= 0 ? force == 1 : (nvec <= 16 && (double)t->nzc * (double)p.total_row_bytes < 1.0e9);
             // 64-bit element types need more registers per gathered vector's arithmetic: one CTA per SM fewer
             constexpr int WB = sizeof(typename Op::T) == 8 ? CB_WIDE_B64 : CB_WIDE_B;

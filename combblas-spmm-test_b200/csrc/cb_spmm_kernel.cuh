@@ -46,11 +46,21 @@ template <> struct Arith<float> {
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }   // no FMA contraction:
     static __device__ __forceinline__ float maxv() { return 3.402823466e+38f; }                 // multiply, then add
+#ifdef CB_FMA      // experiment only (-DCB_FMA): one rounding instead of two; inside the 1e-5 tolerance, not bit-identical
+    static __device__ __forceinline__ float madd(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+    static __device__ __forceinline__ float madd(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+#endif
 };
 template <> struct Arith<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double maxv() { return 1.7976931348623157e+308; }
+#ifdef CB_FMA
+    static __device__ __forceinline__ double madd(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+    static __device__ __forceinline__ double madd(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+#endif
 };
 template <> struct Arith<int32_t> {   // wrap-around like the host's two's complement arithmetic
     static __device__ __forceinline__ int32_t add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -77,6 +87,12 @@ struct PlusTimes {
         if (AK == A_BOOL) return Arith<T>::mul((T)(a != 0), x);          // static_cast<T>(a) * x
         return Arith<T>::mul((T)a, x);
     }
+#ifdef CB_FMA
+    static __device__ __forceinline__ T madd(TA a, T x, T acc) {
+        if constexpr (AK == A_SAME && (std::is_same<T, float>::value || std::is_same<T, double>::value)) return Arith<T>::madd((T)a, x, acc);
+        else return add(mul(a, x), acc);
+    }
+#endif
 };
 // MinPlusSRing<T,T>  (Semirings.h:235-255, inf_plus :40-47)
 template <typename T_>
@@ -91,6 +107,9 @@ struct MinPlus {
         const T inf = Arith<T>::maxv();
         return (a == inf || x == inf) ? inf : Arith<T>::add(a, x);
     }
+#ifdef CB_FMA
+    static __device__ __forceinline__ T madd(TA a, T x, T acc) { return add(mul(a, x), acc); }
+#endif
 };
 // SelectMaxSRing<bool,T>  (Semirings.h:191-210): multiply returns its second argument
 template <typename T_>
@@ -102,6 +121,9 @@ struct SelectMax {
     static __device__ __forceinline__ T id() { return T(-1); }
     static __device__ __forceinline__ T add(T a, T b) { return a < b ? b : a; }     // std::max(a, b)
     static __device__ __forceinline__ T mul(TA, T x) { return x; }
+#ifdef CB_FMA
+    static __device__ __forceinline__ T madd(TA a, T x, T acc) { return add(mul(a, x), acc); }
+#endif
 };
 // PlusTimesSRing<bool,bool> (promote.h:78): + is OR, * is AND.  T = 4 packed 0/1 bytes.
 template <int AK>
@@ -113,6 +135,9 @@ struct OrAnd {
     static __device__ __forceinline__ T id() { return 0u; }
     static __device__ __forceinline__ T add(T a, T b) { return a | b; }
     static __device__ __forceinline__ T mul(TA a, T x) { return AK == A_PATTERN ? x : (x & (0u - (uint32_t)(a != 0))); }
+#ifdef CB_FMA
+    static __device__ __forceinline__ T madd(TA a, T x, T acc) { return add(mul(a, x), acc); }
+#endif
 };
 
 // ------------------------------------------------------------------------------ 16-byte vectors
@@ -248,11 +273,15 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < EPL; ++q) {
+#ifdef CB_FMA
+                acc.v[r].v[q] = (Op::first_touch && first) ? Op::mul(av, x.v[r].v[q]) : Op::madd(av, x.v[r].v[q], acc.v[r].v[q]);
+#else
                 const T prod = Op::mul(av, x.v[r].v[q]);
                 // the reference stores the first product of an output entry and folds later ones with
                 // add(product, acc) (mtSpGEMM.h:403-414).  add(product, id) == product for every semiring here
                 // except SelectMax with values below its identity, which keeps the explicit first-touch select.
                 acc.v[r].v[q] = (Op::first_touch && first) ? prod : Op::add(prod, acc.v[r].v[q]);
+#endif
             }
         first = false;
     };

@@ -196,6 +196,11 @@ int cb_spmm_hub_info(const cb_tile* tile, int64_t info[4]);
  * so an SM keeps threads x depth x 16 bytes of gathers in flight instead of what its register file allows.  Results are
  * bit-identical to the default kernel.  depth: 8 on (the depth this build instantiates), 0 off, -1 follow CB_SPMM_RING. */
 int cb_spmm_ring_config(cb_ctx* ctx, int depth);
+/* Shape of the default local multiply (K2), for tuning: slab_bytes > 0 runs panels wider than that as column slabs of that
+ * width, one after the other, so the X rows one pass gathers are narrower and more of them stay in L2 (0 = one slab as wide
+ * as the layout allows; 64, 128, 256, 512); point = 0 deep / 1 wide / -1 chosen from the footprint of the X rows.  Results
+ * do not depend on either (columns are independent). */
+int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point);
 /* The hub selection rule as pure host arithmetic (no device needed): the max_hubs most frequent columns with at least
  * two nonzeros, most frequent first, ties by ascending column; cum[r] = nonzeros in the columns of rank <= r.
  * Returns the number of hubs written, or -1 on bad arguments. */
