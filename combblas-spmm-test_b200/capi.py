@@ -23,7 +23,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
-           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config"]
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host"]
 
 
 class CBError(RuntimeError):
@@ -105,6 +105,10 @@ def lib():
         L.cb_spmm_hub_info.argtypes = [c_void_p, POINTER(c_int64)]
         L.cb_spmm_ring_config.argtypes = [c_void_p, c_int]
         L.cb_spmm_k2_config.argtypes = [c_void_p, c_int, c_int]
+        L.cb_tile_row_lengths.argtypes = [c_void_p, c_void_p]
+        L.cb_tile_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+        L.cb_dense_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+        L.cb_spmm_summa_host.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int]
         L.cb_tile_filter_columns.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]
         L.cb_hub_select_host.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
         _lib = L
@@ -278,6 +282,13 @@ class Context:
     def spmm_summa(self, tile, X, Y, semiring, gm, gn, gk):
         _check(lib().cb_spmm_summa(self.h, tile.h, X.h, Y.h, semiring, gm, gn, gk), self.h)
 
+    def spmm_summa_host(self, tile, X: np.ndarray, Y: np.ndarray, semiring, gm, gn, gk):
+        """This rank's X tile in host memory in, its Y tile in host memory out; collective over the grid."""
+        assert X.flags.c_contiguous and Y.flags.c_contiguous and X.dtype == Y.dtype
+        _check(lib().cb_spmm_summa_host(self.h, tile.h, _ptr(X), X.shape[1] if X.ndim == 2 else 0, _ptr(Y), Y.shape[1] if Y.ndim == 2 else 0,
+                                        semiring, gm, gn, gk, CODE_OF[np.dtype(np.uint8) if X.dtype == np.bool_ else X.dtype]), self.h)
+        return Y
+
     def hub_config(self, enable, cluster=0, slab_bytes=0):
         """Opt into the hub variant of the local multiply (K2H); enable=-1 follows CB_SPMM_HUB."""
         _check(lib().cb_spmm_hub_config(self.h, int(enable), int(cluster), int(slab_bytes)), self.h)
@@ -350,6 +361,21 @@ class Tile:
         _check(lib().cb_tile_pattern_view(self.h, byref(v)), self.ctx.h)
         return Tile(self.ctx, v)
 
+    def row_lengths(self):
+        """number of nonzeros of every row"""
+        out = np.empty(self.m, np.int64)
+        _check(lib().cb_tile_row_lengths(self.h, _ptr(out)), self.ctx.h)
+        return out
+
+    def rows(self, rows, lengths, val_dtype=None):
+        """-> (offsets [len(rows)+1], columns, values or None) of the selected rows; lengths = row_lengths()"""
+        rows = np.ascontiguousarray(rows, np.int64)
+        off = np.concatenate([[0], np.cumsum(lengths[rows])]).astype(np.int64)
+        cols = np.empty(max(int(off[-1]), 1), np.int64)
+        vals = None if val_dtype is None else np.empty(max(int(off[-1]), 1), val_dtype)
+        _check(lib().cb_tile_download_rows(self.h, len(rows), _ptr(rows), _ptr(cols), _ptr(vals)), self.ctx.h)
+        return off, cols[:off[-1]], (None if vals is None else vals[:off[-1]])
+
     def to_csr(self, val_dtype=None):
         rowptr = np.empty(self.m + 1, np.int64)
         col = np.empty(self.nnz, np.int64)
@@ -380,6 +406,13 @@ class Dense:
         if out is None:
             out = np.empty((self.rows, self.cols), NP_OF[self.code])
         _check(lib().cb_dense_download(self.h, _ptr(out), out.shape[1] if out.ndim == 2 else self.cols), self.ctx.h)
+        return out
+
+    def download_rows(self, rows):
+        """selected rows of the panel, packed"""
+        rows = np.ascontiguousarray(rows, np.int64)
+        out = np.empty((len(rows), self.cols), NP_OF[self.code])
+        _check(lib().cb_dense_download_rows(self.h, len(rows), _ptr(rows), _ptr(out)), self.ctx.h)
         return out
 
     def fill(self, value):

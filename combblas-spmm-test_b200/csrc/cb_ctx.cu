@@ -243,6 +243,45 @@ int cb_dense_download(cb_dense* d, void* host, int64_t ld_host) {
     return CB_OK;
 }
 
+
+}  // extern "C"
+__global__ void __launch_bounds__(256)
+cb_gather_rows_kernel(const char* __restrict__ src, int64_t ld_bytes, const int64_t* __restrict__ rows, int64_t nrows, int row_bytes, char* __restrict__ dst) {
+    const int64_t total = nrows * row_bytes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / row_bytes;
+        dst[i] = src[rows[r] * ld_bytes + (i - r * row_bytes)];
+    }
+}
+
+extern "C" {
+// selected rows of a panel, packed: host[i, 0:cols] = d[rows[i], 0:cols].  For parity checks at sizes where copying the whole
+// panel back is too much (bench.py's sampled-row check, tests at BASELINE.json's full sizes).
+int cb_dense_download_rows(cb_dense* d, int64_t nrows, const int64_t* rows, void* host) {
+    if (!d || (nrows > 0 && (!rows || !host))) return cb_fail(d ? d->ctx : nullptr, CB_ERR_INVALIDPARAMS, "cb_dense_download_rows: null argument");
+    cb_ctx* c = d->ctx;
+    const size_t es = cb_dtype_size(d->dtype);
+    if (nrows <= 0 || d->cols == 0) return CB_OK;
+    for (int64_t i = 0; i < nrows; ++i)
+        if (rows[i] < 0 || rows[i] >= d->rows) return cb_fail(c, CB_ERR_INVALIDPARAMS, "cb_dense_download_rows: row %lld of %lld", (long long)rows[i], (long long)d->rows);
+    CB_CUDA(c, cudaSetDevice(c->device));
+    cb_scratch sc;
+    int64_t* d_rows = nullptr;
+    char* d_out = nullptr;
+    const size_t rb = (size_t)d->cols * es;
+    CB_CUDA(c, sc.alloc(&d_rows, (size_t)nrows));
+    CB_CUDA(c, sc.alloc(&d_out, (size_t)nrows * rb));
+    CB_CUDA(c, cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)nrows, cudaMemcpyHostToDevice, c->compute));
+    int64_t blocks = ((int64_t)nrows * (int64_t)rb + 255) / 256;
+    if (blocks > (int64_t)c->sm_count * 16) blocks = (int64_t)c->sm_count * 16;
+    cb_gather_rows_kernel<<<(unsigned)blocks, 256, 0, c->compute>>>((const char*)d->ptr, (int64_t)d->ld * (int64_t)es, d_rows, nrows, (int)rb, d_out);
+    CB_LAUNCHED(c);
+    CB_CUDA(c, cudaGetLastError());
+    CB_CUDA(c, cudaMemcpyAsync(host, d_out, (size_t)nrows * rb, cudaMemcpyDeviceToHost, c->compute));
+    CB_CUDA(c, cudaStreamSynchronize(c->compute));
+    return CB_OK;
+}
+
 int cb_dense_info(const cb_dense* d, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype, void** ptr) {
     if (rows) *rows = d->rows;
     if (cols) *cols = d->cols;

@@ -61,68 +61,108 @@ struct Handles {
 static P2P* get(cb_ctx* ctx) { return (P2P*)ctx->p2p_state; }
 
 // Collective over the processor column.  Makes sure every rank's xfull holds `need` bytes and that all peers are mapped.
+// Anything that can fail on one rank only (driver entry points, allocation, IPC) is recorded and carried through the
+// collective steps, and the column agrees on the outcome at the end: if any rank could not set the transport up, every
+// rank of the column switches to the NCCL broadcast path (ctx->summa_p2p = false) instead of failing the multiply.
 int cb_p2p_prepare(cb_ctx* ctx, size_t need) {
     if (ctx->pr <= 1) return CB_OK;
     P2P* P = get(ctx);
+    bool ok = true;
+    const bool first = P == nullptr;      // every rank of the grid sets the transport up in its first stage loop: a grid-wide decision
+    std::string why;
+    auto soft = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && ok) { ok = false; why = std::string(what) + ": " + cudaGetErrorString(e); } cudaGetLastError(); return e == cudaSuccess; };
     if (!P) {
         P = new P2P();
-        ctx->p2p_state = P;
         P->np = ctx->pr;
         P->me = ctx->myprocrow;
-        if (P->np > MAXP) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "peer transport supports up to %d ranks per processor column", (int)MAXP);
-        cudaDriverEntryPointQueryResult q;
-        void *w = nullptr, *wr = nullptr;
-        CB_CUDA(ctx, cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q));
-        CB_CUDA(ctx, cudaGetDriverEntryPoint("cuStreamWriteValue32", &wr, cudaEnableDefault, &q));
-        if (!w || !wr) return cb_fail(ctx, CB_ERR_CUDA, "stream memory operations are not available in this driver");
-        P->wait32 = (WaitValue32Fn)w;
-        P->write32 = (WriteValue32Fn)wr;
-        CB_CUDA(ctx, cudaMalloc((void**)&P->mailbox, sizeof(Mailbox)));
-        CB_CUDA(ctx, cudaMemset(P->mailbox, 0, sizeof(Mailbox)));
+        // size everything before the first step that can fail, so release() can always walk the vectors
         P->peer_xfull.assign(P->np, nullptr);
         P->peer_mailbox.assign(P->np, nullptr);
         P->push.assign(P->np, nullptr);
         P->push_done.assign(P->np, nullptr);
         P->push_start.assign(P->np, nullptr);
         P->used.assign(P->np, 0);
-        for (int q2 = 0; q2 < P->np; ++q2) {
+        ctx->p2p_state = P;
+        if (P->np > MAXP) { ok = false; why = "more ranks per processor column than the peer transport supports"; }
+        cudaDriverEntryPointQueryResult q;
+        void *w = nullptr, *wr = nullptr;
+        soft(cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q), "cuStreamWaitValue32");
+        soft(cudaGetDriverEntryPoint("cuStreamWriteValue32", &wr, cudaEnableDefault, &q), "cuStreamWriteValue32");
+        if ((!w || !wr) && ok) { ok = false; why = "stream memory operations are not available in this driver"; }
+        P->wait32 = (WaitValue32Fn)w;
+        P->write32 = (WriteValue32Fn)wr;
+        if (soft(cudaMalloc((void**)&P->mailbox, sizeof(Mailbox)), "cudaMalloc(mailbox)")) soft(cudaMemset(P->mailbox, 0, sizeof(Mailbox)), "cudaMemset(mailbox)");
+        for (int q2 = 0; q2 < P->np && ok; ++q2) {
             if (q2 == P->me) continue;
-            CB_CUDA(ctx, cudaStreamCreateWithFlags(&P->push[q2], cudaStreamNonBlocking));
-            CB_CUDA(ctx, cudaEventCreate(&P->push_done[q2]));
-            CB_CUDA(ctx, cudaEventCreate(&P->push_start[q2]));
+            soft(cudaStreamCreateWithFlags(&P->push[q2], cudaStreamNonBlocking), "cudaStreamCreate");
+            soft(cudaEventCreate(&P->push_done[q2]), "cudaEventCreate");
+            soft(cudaEventCreate(&P->push_start[q2]), "cudaEventCreate");
         }
     }
     if (need <= P->xfull_bytes && P->mailbox_mapped) return CB_OK;
     // (re)allocate: nobody may still be writing into the old buffer.  Every rank drains its own pushes, then the
     // allgather below is the barrier after which all pushes of all ranks are known to be complete.
-    for (int q = 0; q < P->np; ++q) if (P->push[q]) CB_CUDA(ctx, cudaStreamSynchronize(P->push[q]));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    {
-        char token = 0;
-        std::vector<char> all((size_t)P->np);
-        CB_TRY(cb_nccl_allgather_col(ctx, &token, all.data(), 1));
-    }
+    for (int q = 0; q < P->np; ++q) if (P->push[q]) soft(cudaStreamSynchronize(P->push[q]), "cudaStreamSynchronize");
+    soft(cudaStreamSynchronize(ctx->compute), "cudaStreamSynchronize");
+    auto column_barrier = [&]() -> int { char token = 0; std::vector<char> all((size_t)P->np); return cb_nccl_allgather_col(ctx, &token, all.data(), 1); };
+    CB_TRY(column_barrier());
     for (int q = 0; q < P->np; ++q)
-        if (P->peer_xfull[q]) { CB_CUDA(ctx, cudaIpcCloseMemHandle(P->peer_xfull[q])); P->peer_xfull[q] = nullptr; }
+        if (P->peer_xfull[q]) { soft(cudaIpcCloseMemHandle(P->peer_xfull[q]), "cudaIpcCloseMemHandle"); P->peer_xfull[q] = nullptr; }
+    // an exporter may free its buffer only after every importer has closed its mapping (cudaFree before the importer's
+    // cudaIpcCloseMemHandle is undefined behaviour): meet the column once more between closing and freeing
+    CB_TRY(column_barrier());
     if (need > P->xfull_bytes) {
-        if (P->xfull) CB_CUDA(ctx, cudaFree(P->xfull));
+        if (P->xfull) soft(cudaFree(P->xfull), "cudaFree");
         P->xfull = nullptr;
+        P->xfull_bytes = 0;
         // two buffers (even / odd epochs) in one allocation, with head room so a slightly larger panel does not remap
         const size_t bytes = (need + need / 4 + 4096 + 255) & ~(size_t)255;
-        cudaError_t e = cudaMalloc((void**)&P->xfull, 2 * bytes);
-        if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for the peer panel buffers: %s", 2 * bytes, cudaGetErrorString(e));
-        P->xfull_bytes = bytes;
+        if (ok && soft(cudaMalloc((void**)&P->xfull, 2 * bytes), "cudaMalloc(peer panel buffers)")) P->xfull_bytes = bytes;
     }
     Handles mine;
-    CB_CUDA(ctx, cudaIpcGetMemHandle(&mine.xfull, P->xfull));
-    CB_CUDA(ctx, cudaIpcGetMemHandle(&mine.mailbox, P->mailbox));
+    memset(&mine, 0, sizeof mine);
+    if (ok && P->xfull) soft(cudaIpcGetMemHandle(&mine.xfull, P->xfull), "cudaIpcGetMemHandle");
+    if (ok && P->mailbox) soft(cudaIpcGetMemHandle(&mine.mailbox, P->mailbox), "cudaIpcGetMemHandle");
     std::vector<Handles> all((size_t)P->np);
     CB_TRY(cb_nccl_allgather_col(ctx, &mine, all.data(), sizeof(Handles)));
-    for (int q = 0; q < P->np; ++q) {
+    // did every rank get this far in one piece?  Only then may anyone open a peer's handles.
+    std::vector<char> oks((size_t)P->np);
+    {
+        char mine_ok = ok ? 1 : 0;
+        CB_TRY(cb_nccl_allgather_col(ctx, &mine_ok, oks.data(), 1));
+    }
+    bool all_ok = true;
+    for (char c : oks) all_ok = all_ok && c;
+    for (int q = 0; q < P->np && all_ok; ++q) {
         if (q == P->me) continue;
-        CB_CUDA(ctx, cudaIpcOpenMemHandle((void**)&P->peer_xfull[q], all[(size_t)q].xfull, cudaIpcMemLazyEnablePeerAccess));
+        soft(cudaIpcOpenMemHandle((void**)&P->peer_xfull[q], all[(size_t)q].xfull, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
         if (!P->peer_mailbox[q])
-            CB_CUDA(ctx, cudaIpcOpenMemHandle((void**)&P->peer_mailbox[q], all[(size_t)q].mailbox, cudaIpcMemLazyEnablePeerAccess));
+            soft(cudaIpcOpenMemHandle((void**)&P->peer_mailbox[q], all[(size_t)q].mailbox, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    }
+    {
+        char mine_ok = ok ? 1 : 0;
+        CB_TRY(cb_nccl_allgather_col(ctx, &mine_ok, oks.data(), 1));
+    }
+    for (char c : oks) all_ok = all_ok && c;
+    if (first) {
+        // the stage order depends on the transport and must be the same along a processor row (the broadcasts of A have to
+        // match), so the first set-up is agreed on by the whole grid
+        int64_t v = all_ok ? 1 : 0;
+        CB_TRY(cb_comm_allreduce_i64(ctx, 0, 2, &v, 1));
+        all_ok = v != 0;
+    } else if (!all_ok) {
+        return cb_fail(ctx, CB_ERR_CUDA, "growing the peer panel buffers failed on a rank of this processor column (%s)", ok ? "a peer" : why.c_str());
+    }
+    if (!all_ok) {
+        // the column falls back to NCCL broadcasts together; what was mapped is closed again (a barrier apart from any free)
+        for (int q = 0; q < P->np; ++q)
+            if (P->peer_xfull[q]) { cudaIpcCloseMemHandle(P->peer_xfull[q]); P->peer_xfull[q] = nullptr; }
+        cudaGetLastError();
+        CB_TRY(column_barrier());
+        P->mailbox_mapped = false;
+        ctx->summa_p2p = false;
+        if (!ok) fprintf(stderr, "combblas_b200: rank %d: peer panel transport unavailable (%s); this processor column uses NCCL broadcasts\n", ctx->rank, why.c_str());
+        return CB_OK;
     }
     P->mailbox_mapped = true;
     return CB_OK;
@@ -200,10 +240,17 @@ void cb_p2p_release(cb_ctx* ctx) {
     P2P* P = get(ctx);
     if (!P) return;
     // a peer may still be writing its last ack into my mailbox: drain my streams, then meet the column before freeing
-    for (int q = 0; q < P->np; ++q) if (P->push[q]) cudaStreamSynchronize(P->push[q]);
+    const int nq = (int)P->push.size();
+    for (int q = 0; q < nq; ++q) if (P->push[q]) cudaStreamSynchronize(P->push[q]);
     cudaStreamSynchronize(ctx->compute);
     if (P->mailbox_mapped && ctx->nccl_col) { char token = 0; std::vector<char> all((size_t)P->np); cb_nccl_allgather_col(ctx, &token, all.data(), 1); }
-    for (int q = 0; q < P->np; ++q) {
+    for (int q = 0; q < nq; ++q) {
+        if (P->peer_xfull[q]) { cudaIpcCloseMemHandle(P->peer_xfull[q]); P->peer_xfull[q] = nullptr; }
+        if (P->peer_mailbox[q]) { cudaIpcCloseMemHandle(P->peer_mailbox[q]); P->peer_mailbox[q] = nullptr; }
+    }
+    // importers have closed; only then may the exporters free (second meeting of the column)
+    if (P->mailbox_mapped && ctx->nccl_col) { char token = 0; std::vector<char> all((size_t)P->np); cb_nccl_allgather_col(ctx, &token, all.data(), 1); }
+    for (int q = 0; q < nq; ++q) {
         if (P->push[q]) { cudaStreamSynchronize(P->push[q]); cudaStreamDestroy(P->push[q]); }
         if (P->push_done[q]) cudaEventDestroy(P->push_done[q]);
         if (P->push_start[q]) cudaEventDestroy(P->push_start[q]);

@@ -134,8 +134,10 @@ int cb_spmm_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx,
     // Host panels in, host panel out.  The panel is cut into column slabs that flow through three streams - slab s+1 goes up
     // (H2D) while slab s is multiplied and slab s-1 comes down (D2H) - so both PCIe directions and the kernel overlap;
     // the device panels are kept in the ctx between calls.
+    if (!ctx || !t) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_host: null argument");
     const size_t es = cb_dtype_size(dtype);
     if (!es || k <= 0 || ldx < k || ldy < k) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_host: bad dtype / k / leading dimension");
+    if ((t->n > 0 && !X_host) || (t->m > 0 && !Y_host)) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_host: null panel");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t per16 = 16 / (int64_t)es;
     const int64_t ld = (k + per16 - 1) / per16 * per16;

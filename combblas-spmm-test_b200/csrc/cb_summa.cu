@@ -375,7 +375,8 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     block_range(gm, pr, ctx->myprocrow, &r0, &rl);
     block_range(gn, pc, ctx->myproccol, &c0, &cl);
     block_range(gn, pr, ctx->myprocrow, &x0, &xl);
-    block_range(gk, pc, ctx->myproccol, &k0, &kl);
+    block_range(gk >= 0 ? gk : 0, pc, ctx->myproccol, &k0, &kl);
+    if (gk < 0) kl = X->cols;        // internal (cb_spmm_summa_host): a column slab; the ranks of a processor column agree on its width
     // CheckSpGEMMCompliance (ParFriends.h:160-181) on the local blocks
     if (tile->m != rl || tile->n != cl || X->rows != xl || X->cols != kl || Y->rows != rl || Y->cols != kl)
         return cb_fail(ctx, CB_ERR_DIMMISMATCH,
@@ -385,6 +386,11 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     if (X->dtype != Y->dtype) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm_summa: X and Y dtypes differ");
     if (X->ptr == Y->ptr) return cb_fail(ctx, CB_ERR_MATRIXALIAS, "cb_spmm_summa: X and Y alias");
     if (ctx->nranks == 1) return cb_spmm_local(ctx, tile, X, Y, semiring, 0);
+    if (gn == 0) {                         // empty inner dimension: no stage runs, the product is SR::id() everywhere (as on one rank)
+        unsigned char idv[8] = {0};
+        if (cb_semiring_id(semiring, X->dtype, idv) != CB_OK) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm_summa: semiring %d with dtype %d", semiring, X->dtype);
+        return cb_dense_fill(Y, idv);
+    }
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t es = cb_dtype_size(X->dtype);
 
@@ -477,8 +483,8 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         }
     }
     // ---- panel transport: copy-engine pushes into peer memory (cb_p2p.cu) unless CB_SUMMA_TRANSPORT=nccl
+    if (pr > 1 && ctx->summa_p2p) CB_TRY(cb_p2p_prepare(ctx, (size_t)gn * (size_t)X->ld * es));    // may switch the column to NCCL
     const bool p2p = pr > 1 && ctx->summa_p2p;
-    if (p2p) CB_TRY(cb_p2p_prepare(ctx, (size_t)gn * (size_t)X->ld * es));
 
     // ---- steady state with a resident block-row: once every part of my block-row of A is on this GPU (second multiply with
     // the same tile onwards) the parts that meet the same X row block are fused into one tile, so a multiply is pr kernel
@@ -623,6 +629,93 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
     }
     if (p2p) CB_TRY(cb_p2p_finish(ctx, ctx->compute));
     CB_CUDA(ctx, cudaEventRecord(S->end, ctx->compute));
+    return CB_OK;
+}
+
+
+// cb_spmm_summa with HOST panels: this rank's X tile comes from host memory and its Y tile goes back to host memory.
+// The k-block is cut into column slabs that flow through three streams - slab s+1 goes up (H2D) while slab s runs the
+// stage loop and slab s-1 comes down (D2H) - so both PCIe directions and the multiply overlap.  Every slab is its own
+// compact device panel (leading dimension = slab width), because the panels that travel between column peers are whole
+// contiguous blocks.  Collective: every rank of the grid calls it with its tiles of the same global product.
+int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int semiring,
+                       int64_t gm, int64_t gn, int64_t gk, int dtype) {
+    if (!ctx || !tile) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_summa_host: null argument");
+    const size_t es = cb_dtype_size(dtype);
+    if (!es) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmm_summa_host: dtype %d", dtype);
+    const int pr = ctx->pr, pc = ctx->pc;
+    int64_t r0, rl, x0, xl, k0, kl;
+    block_range(gm, pr, ctx->myprocrow, &r0, &rl);
+    block_range(gn, pr, ctx->myprocrow, &x0, &xl);
+    block_range(gk, pc, ctx->myproccol, &k0, &kl);
+    if ((kl > 0 && ((xl > 0 && !X_host) || (rl > 0 && !Y_host))) || ldx < kl || ldy < kl)
+        return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_summa_host: null panel or leading dimension below the local width %lld", (long long)kl);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h2d) {
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < CB_MAX_SLABS; ++i) {
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slab_up[i], cudaEventDisableTiming));
+            CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slab_done[i], cudaEventDisableTiming));
+        }
+        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->host_begin, cudaEventDisableTiming));
+    }
+    // Slab widths must be the same on every rank of a processor column (they exchange the panels) and a multiple of 16
+    // bytes; every rank of the grid must run the same NUMBER of slabs (the stage loop is collective over processor rows
+    // too).  Both follow from the floor rule: all ranks but the last processor column have per = gk / pc columns.
+    const int64_t per16 = 16 / (int64_t)es;
+    const int64_t per = pc > 1 ? gk / pc : gk;                       // width of every k-block but the last
+    static const int want = getenv("CB_HOST_SLABS") ? atoi(getenv("CB_HOST_SLABS")) : 4;
+    const int64_t min_cols = std::max<int64_t>(per16, 128 / (int64_t)es);
+    int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, CB_MAX_SLABS), per / min_cols));
+    const int64_t slab_cols = per > 0 ? ((per + nslab - 1) / nslab + per16 - 1) / per16 * per16 : 0;
+    if (slab_cols > 0) nslab = (int)((per + slab_cols - 1) / slab_cols);
+    if (per == 0) nslab = 1;
+    // slab i covers local columns [i*slab_cols, ...); the last slab takes whatever is left of THIS rank's block (the last
+    // processor column holds the remainder of gk)
+    const size_t xbytes = (size_t)std::max<int64_t>(xl, 1) * (size_t)((std::max<int64_t>(kl, 1) + per16 - 1) / per16 * per16 + (int64_t)nslab * per16) * es;
+    const size_t ybytes = (size_t)std::max<int64_t>(rl, 1) * (size_t)((std::max<int64_t>(kl, 1) + per16 - 1) / per16 * per16 + (int64_t)nslab * per16) * es;
+    auto reserve = [&](void** p, size_t* have, size_t need) -> int {
+        if (*have >= need) return CB_OK;
+        if (*p) { CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute)); CB_CUDA(ctx, cudaFree(*p)); *p = nullptr; *have = 0; }
+        cudaError_t e = cudaMalloc(p, need);
+        if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a host-path panel: %s", need, cudaGetErrorString(e));
+        *have = need;
+        return CB_OK;
+    };
+    CB_TRY(reserve(&ctx->ws_x, &ctx->ws_x_bytes, xbytes));
+    CB_TRY(reserve(&ctx->ws_y, &ctx->ws_y_bytes, ybytes));
+    CB_CUDA(ctx, cudaEventRecord(ctx->host_begin, ctx->compute));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->host_begin, 0));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->host_begin, 0));
+    size_t xoff = 0, yoff = 0;
+    for (int i = 0; i < nslab; ++i) {
+        const int64_t c0 = (int64_t)i * slab_cols;
+        const int64_t cw = i == nslab - 1 ? std::max<int64_t>(kl - c0, 0) : std::min<int64_t>(slab_cols, std::max<int64_t>(kl - c0, 0));
+        const int64_t ld = (cw + per16 - 1) / per16 * per16;
+        char* dx = (char*)ctx->ws_x + xoff;
+        char* dy = (char*)ctx->ws_y + yoff;
+        xoff += ((size_t)xl * (size_t)ld * es + 255) & ~(size_t)255;
+        yoff += ((size_t)rl * (size_t)ld * es + 255) & ~(size_t)255;
+        if (cw > 0 && xl > 0) {
+            if (ld != cw) CB_CUDA(ctx, cudaMemsetAsync(dx, 0, (size_t)xl * (size_t)ld * es, ctx->h2d));
+            CB_CUDA(ctx, cudaMemcpy2DAsync(dx, (size_t)ld * es, (const char*)X_host + (size_t)c0 * es, (size_t)ldx * es, (size_t)cw * es,
+                                           (size_t)xl, cudaMemcpyHostToDevice, ctx->h2d));
+        }
+        CB_CUDA(ctx, cudaEventRecord(ctx->slab_up[i], ctx->h2d));
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->slab_up[i], 0));
+        cb_dense X, Y;
+        X.ctx = ctx; X.rows = xl; X.cols = cw; X.ld = ld; X.dtype = dtype; X.ptr = dx; X.owned = false;
+        Y.ctx = ctx; Y.rows = rl; Y.cols = cw; Y.ld = ld; Y.dtype = dtype; Y.ptr = dy; Y.owned = false;
+        CB_TRY(cb_spmm_summa(ctx, tile, &X, &Y, semiring, gm, gn, -1));
+        CB_CUDA(ctx, cudaEventRecord(ctx->slab_done[i], ctx->compute));
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->slab_done[i], 0));
+        if (cw > 0 && rl > 0)
+            CB_CUDA(ctx, cudaMemcpy2DAsync((char*)Y_host + (size_t)c0 * es, (size_t)ldy * es, dy, (size_t)ld * es, (size_t)cw * es,
+                                           (size_t)rl, cudaMemcpyDeviceToHost, ctx->d2h));
+    }
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return CB_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
+#include <algorithm>
 #include "cb_common.cuh"
 #include "cb_hub.cuh"
 
@@ -33,7 +34,18 @@ __global__ void expand_csc_kernel(const IT* __restrict__ cp, const IT* __restric
 template <typename IT>
 __global__ void coo_keys_kernel(const IT* __restrict__ rows, const IT* __restrict__ cols, int64_t nz, uint64_t* __restrict__ keys) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x)
-        keys[p] = ((uint64_t)rows[p] << 32) | (uint64_t)cols[p];
+        keys[p] = ((uint64_t)rows[p] >> 32 || (uint64_t)cols[p] >> 32) ? ~0ull          // negative or >= 2^32: caught by validate_keys_kernel
+                                                                        : (((uint64_t)rows[p] << 32) | (uint64_t)cols[p]);
+}
+
+// ingestion check: a nonzero outside the m x n tile would write outside the column / row arrays further down
+__global__ void validate_keys_kernel(const uint64_t* __restrict__ keys, int64_t nz, uint32_t m, uint32_t n, unsigned int* __restrict__ bad) {
+    unsigned int mine = 0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[p];
+        if ((uint32_t)(k >> 32) >= m || (uint32_t)k >= n) mine = 1;
+    }
+    if (__any_sync(0xffffffffu, mine) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
 }
 
 __global__ void iota_kernel(uint32_t* p, int64_t n) {
@@ -158,6 +170,18 @@ int cb_tile_build_from_keys(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, uint6
         T_CUDA(cudaStreamSynchronize(st));
         *out = t;
         return CB_OK;
+    }
+    // 0. every index inside the tile?  (malformed COO / CSC input must not turn into an out-of-bounds device write)
+    {
+        unsigned int* d_bad = nullptr;
+        T_CUDA(sc.alloc(&d_bad, 1));
+        T_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), st));
+        validate_keys_kernel<<<grid_for(nz, sm), 256, 0, st>>>(d_keys, nz, (uint32_t)m, (uint32_t)n, d_bad);
+        CB_LAUNCHED(ctx);
+        unsigned int bad = 0;
+        T_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+        T_CUDA(cudaStreamSynchronize(st));
+        if (bad) { cb_fail(ctx, CB_ERR_INVALIDPARAMS, "tile input holds a row index >= %lld or a column index >= %lld (or a negative one)", (long long)m, (long long)n); return fail(CB_ERR_INVALIDPARAMS); }
     }
     // 1. stable radix sort by (row, col)
     uint64_t* keys_sorted = d_keys; uint32_t *perm = nullptr, *perm_sorted = nullptr;
@@ -409,6 +433,54 @@ int cb_tile_download_csr(cb_tile* t, int64_t* rowptr, int64_t* colidx, void* val
     if (vals && t->vals && t->nnz) {
         CB_CUDA(ctx, cudaMemcpyAsync(vals, t->vals, cb_dtype_size(t->val_dtype) * (size_t)t->nnz, cudaMemcpyDeviceToHost, st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return CB_OK;
+}
+
+
+// lengths of all m rows (0 for rows without nonzeros): the row pointer differences of the reference's CSR view
+int cb_tile_row_lengths(cb_tile* t, int64_t* len) {
+    if (!t || !len) return cb_fail(t ? t->ctx : nullptr, CB_ERR_INVALIDPARAMS, "cb_tile_row_lengths: null argument");
+    cb_ctx* ctx = t->ctx;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> rp((size_t)t->nzr + 1, 0), rows((size_t)t->nzr);
+    if (t->nzr) {
+        CB_CUDA(ctx, cudaMemcpyAsync(rp.data(), t->rowptr, sizeof(int32_t) * (size_t)(t->nzr + 1), cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaMemcpyAsync(rows.data(), t->nzrows, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    }
+    for (int64_t r = 0; r < t->m; ++r) len[r] = 0;
+    for (int64_t i = 0; i < t->nzr; ++i) len[rows[(size_t)i]] = rp[(size_t)i + 1] - rp[(size_t)i];
+    return CB_OK;
+}
+
+// the nonzeros of selected rows, concatenated in the order of `rows` (columns ascending inside a row); the caller sizes
+// cols / vals from cb_tile_row_lengths.  For parity checks at sizes where copying the whole tile back is too much.
+int cb_tile_download_rows(cb_tile* t, int64_t nrows, const int64_t* rows, int64_t* cols, void* vals) {
+    if (!t || (nrows > 0 && (!rows || !cols))) return cb_fail(t ? t->ctx : nullptr, CB_ERR_INVALIDPARAMS, "cb_tile_download_rows: null argument");
+    cb_ctx* ctx = t->ctx;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int32_t> rp((size_t)t->nzr + 1, 0), nzrows((size_t)t->nzr);
+    if (t->nzr) {
+        CB_CUDA(ctx, cudaMemcpyAsync(rp.data(), t->rowptr, sizeof(int32_t) * (size_t)(t->nzr + 1), cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaMemcpyAsync(nzrows.data(), t->nzrows, sizeof(int32_t) * (size_t)t->nzr, cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    }
+    const size_t vs = (t->vals && vals) ? cb_dtype_size(t->val_dtype) : 0;
+    std::vector<int32_t> tmp;
+    int64_t out = 0;
+    for (int64_t i = 0; i < nrows; ++i) {
+        if (rows[i] < 0 || rows[i] >= t->m) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_download_rows: row %lld of %lld", (long long)rows[i], (long long)t->m);
+        auto it = std::lower_bound(nzrows.begin(), nzrows.end(), (int32_t)rows[i]);
+        if (it == nzrows.end() || *it != (int32_t)rows[i]) continue;                       // empty row
+        const size_t ri = (size_t)(it - nzrows.begin());
+        const int64_t s = rp[ri], n = rp[ri + 1] - rp[ri];
+        tmp.resize((size_t)n);
+        CB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), t->colflag + s, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
+        if (vs) CB_CUDA(ctx, cudaMemcpyAsync((char*)vals + (size_t)out * vs, (const char*)t->vals + (size_t)s * vs, vs * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+        for (int64_t j = 0; j < n; ++j) cols[out + j] = (int64_t)(tmp[(size_t)j] & 0x7fffffff);
+        out += n;
     }
     return CB_OK;
 }

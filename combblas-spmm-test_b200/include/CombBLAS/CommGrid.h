@@ -54,6 +54,13 @@ public:
         int ndev = 1;
         cb_device_count(&ndev);
         const int device = myrank % (ndev > 0 ? ndev : 1);
+        // processor-row and processor-column communicators exactly as the reference builds them (src/CommGrid.cpp:66-67):
+        // user code reduces / broadcasts over GetRowWorld() / GetColWorld()
+        MPI_Comm row = MPI_COMM_NULL, col = MPI_COMM_NULL;
+        MPI_Comm_split(world, myprocrow, myrank, &row);
+        MPI_Comm_split(world, myproccol, myrank, &col);
+        rowWorld.reset(new MPI_Comm(row), [](MPI_Comm* c) { int fin = 0; MPI_Finalized(&fin); if (!fin && *c != MPI_COMM_NULL) MPI_Comm_free(c); delete c; });
+        colWorld.reset(new MPI_Comm(col), [](MPI_Comm* c) { int fin = 0; MPI_Finalized(&fin); if (!fin && *c != MPI_COMM_NULL) MPI_Comm_free(c); delete c; });
 #endif
         cb_ctx* c = nullptr;
         cb_check(cb_ctx_create_grid(device, myrank, nproc, grrows, grcols, nproc > 1 ? uid : nullptr, &c), nullptr, "cb_ctx_create_grid");
@@ -87,8 +94,8 @@ public:
     MPI_Comm GetRowWorld() const { return 1000 + myprocrow; }     // handles of cb_mpi.h: processes with the same myprocrow /
     MPI_Comm GetColWorld() const { return 2000 + myproccol; }     // myproccol; the device collectives live inside GetContext()
 #else
-    MPI_Comm GetRowWorld() const { return commWorld; }
-    MPI_Comm GetColWorld() const { return commWorld; }
+    MPI_Comm GetRowWorld() const { return *rowWorld; }            // MPI_Comm_split(world, myprocrow, rank), src/CommGrid.cpp:66
+    MPI_Comm GetColWorld() const { return *colWorld; }            // MPI_Comm_split(world, myproccol, rank), src/CommGrid.cpp:67
 #endif
 
     cb_ctx* GetContext() const { return ctx.get(); }
@@ -102,6 +109,9 @@ public:
 
 private:
     MPI_Comm commWorld;
+#ifdef CB_HAVE_MPI
+    std::shared_ptr<MPI_Comm> rowWorld, colWorld;                 // shared by the copies of a grid, freed with the last one
+#endif
     int grrows = 1, grcols = 1, myprocrow = 0, myproccol = 0, myrank = 0;
     std::shared_ptr<cb_ctx> ctx;
 };

@@ -48,16 +48,9 @@ DenseParMat<IU, typename promote_trait<NUM, NUV>::T_promote> SpMM(const SpParMat
     const IU lm = A.getlocalrows(), kl = X.getlocalcols();
     DenseParMat<IU, T_promote> Y(SR::id(), grid, lm, kl);
     cb_tile* tile = A.DeviceTile();
-    cb_dense *dX = nullptr, *dY = nullptr;
-    const int dt = cb_dtype_of<NUV>::value;
-    cb_check(cb_dense_alloc(ctx, X.getlocalrows(), kl, dt, &dX), ctx, "cb_dense_alloc");
-    cb_check(cb_dense_alloc(ctx, lm, kl, dt, &dY), ctx, "cb_dense_alloc");
-    if (kl > 0) cb_check(cb_dense_upload(dX, X.data(), kl), ctx, "cb_dense_upload");
-    cb_check(cb_spmm_summa(ctx, tile, dX, dY, semiring_traits<SR>::op, gm, gn, gk), ctx, "cb_spmm_summa");
-    if (kl > 0) cb_check(cb_dense_download(dY, Y.data(), kl), ctx, "cb_dense_download");
-    cb_check(cb_ctx_sync(ctx), ctx, "cb_ctx_sync");
-    cb_dense_free(dX);
-    cb_dense_free(dY);
+    // host panels in, host panel out: column slabs pipelined over H2D / stage loop / D2H on the device side
+    cb_check(cb_spmm_summa_host(ctx, tile, X.data(), kl, Y.data(), kl, semiring_traits<SR>::op, gm, gn, gk, cb_dtype_of<NUV>::value), ctx,
+             "cb_spmm_summa_host");
     return Y;
 }
 
@@ -171,6 +164,19 @@ SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA>& A, SpParMat<
     // dense images of my tile of B: values (promoted type) and structure
     const UDERB& bt = B.seq();
     const IU xl = bt.getnrow(), kl = bt.getncol(), lm = A.getlocalrows();
+    {
+        // the lowering holds two dense lm x kl and two xl x kl panels per process: say so instead of dying in an allocation
+        static const double limit = std::getenv("CB_SPGEMM_DENSE_LIMIT_GB") ? std::atof(std::getenv("CB_SPGEMM_DENSE_LIMIT_GB")) * 1e9 : 32e9;
+        const double need = ((double)lm + (double)xl) * (double)kl * (double)(sizeof(T_promote) + 1);
+        if (need > limit) {
+            std::ostringstream outs;
+            outs << "Mult_AnXBn_Synch / PSpGEMM of this build multiplies through dense panels and is meant for a tall-skinny right-hand side: "
+                 << "local panels of " << lm << " x " << kl << " and " << xl << " x " << kl << " would take " << need / 1e9
+                 << " GB (limit " << limit / 1e9 << " GB, CB_SPGEMM_DENSE_LIMIT_GB)" << std::endl;
+            SpParHelper::Print(outs.str());
+            MPI_Abort(MPI_COMM_WORLD, INVALIDPARAMS);
+        }
+    }
     // absent entries of B hold SR::id(): it annihilates under every supported multiply (0*a, inf_plus(a, max), a AND false,
     // select2nd -> id), so they cannot change a folded value; which entries of C exist is decided by the structure product
     DenseParMat<IU, T_promote> Xv(SR::id(), grid, xl, kl);

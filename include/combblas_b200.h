@@ -118,6 +118,13 @@ int cb_tile_filter_columns(cb_ctx* ctx, const cb_tile* tile, const uint8_t* keep
 /* copy the device tile back as CSR (rowptr[m+1], colidx[nnz], vals) for inspection/tests; any pointer may be NULL */
 int cb_tile_download_csr(cb_tile* tile, int64_t* rowptr, int64_t* colidx, void* vals);
 
+/* row-level inspection for parity checks at sizes where copying a whole operand back is too much (bench.py's sampled-row
+ * check, tests at BASELINE.json's full sizes) - the role of SpParMat::operator() / SpRef on a handful of rows
+ * (include/CombBLAS/SpParMat.cpp:1743-): lengths of all m rows; then the (column, value) pairs of selected rows, concatenated
+ * in the order asked for, columns ascending inside a row (vals may be NULL). */
+int cb_tile_row_lengths(cb_tile* tile, int64_t* len);
+int cb_tile_download_rows(cb_tile* tile, int64_t nrows, const int64_t* rows, int64_t* cols, void* vals);
+
 /* ------------------------------------------------------------------ dense panel
  * Replaces DenseParMat<IT,NT>'s local block (include/CombBLAS/DenseParMat.h:49-128; the reference
  * allocates NT** with one new[] per row, SpHelper.h:241-247) by one contiguous row-major device
@@ -127,6 +134,7 @@ int cb_dense_wrap(cb_ctx* ctx, void* device_ptr, int64_t rows, int64_t cols, int
 int cb_dense_free(cb_dense* d);
 int cb_dense_upload(cb_dense* d, const void* host, int64_t ld_host);     /* async on the compute stream if host is pinned */
 int cb_dense_download(cb_dense* d, void* host, int64_t ld_host);         /* returns after the copy completed */
+int cb_dense_download_rows(cb_dense* d, int64_t nrows, const int64_t* rows, void* host);   /* host[i, 0:cols] = d[rows[i], 0:cols], packed */
 int cb_dense_fill(cb_dense* d, const void* scalar);                      /* std::fill_n(localy, ysize, SR::id()), ParFriends.h:1960-1963 */
 int cb_dense_info(const cb_dense* d, int64_t* rows, int64_t* cols, int64_t* ld, int* dtype, void** device_ptr);
 int cb_semiring_id(int semiring, int dtype, void* scalar_out);           /* SR::id() as a value of dtype */
@@ -178,6 +186,13 @@ int cb_summa_plan(int pr, int pc, int64_t gn, int64_t* seg, int* a_owner_col, in
  * This is what SpMM<SR>(A, X) of the C++ layer calls when the panels live in host memory. */
 int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy,
                  int64_t k, int dtype, int semiring);
+
+/* cb_spmm_summa with HOST panels: this rank's X tile is read from host memory and its Y tile written to host memory (row-major,
+ * leading dimensions in elements); dtype is the panels' element type.  The k-block is cut into column slabs that flow up,
+ * through the stage loop and down on three streams, so both PCIe directions overlap the multiply.  Collective over the grid.
+ * This is what SpMM<SR>(A, X) of the C++ layer calls: the distributed counterpart of cb_spmm_host. */
+int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int semiring,
+                       int64_t gm, int64_t gn, int64_t gk, int dtype);
 
 /* Hub variant of the local multiply (K2H, csrc/cb_spmm_hub_kernel.cuh) - OPT-IN, off by default.
  * For tiles whose columns are very unevenly used (R-MAT / power-law inputs) the panel rows of the most frequent columns

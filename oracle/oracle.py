@@ -65,7 +65,7 @@ def lib():
     global _lib
     if _lib is None:
         path = os.path.join(HERE, "liboracle.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "spmm_oracle.c")):
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("spmm_oracle.c", "gen_oracle.c")):
             subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
         L = ctypes.CDLL(path)
         L.oracle_spmm_colcompressed.restype = c_int
@@ -80,6 +80,15 @@ def lib():
         L.oracle_block_range.argtypes = [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]
         L.oracle_spmv_pt_f64.restype = None
         L.oracle_spmv_pt_f64.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.oracle_gen_matrix.restype = c_int
+        L.oracle_gen_matrix.argtypes = [c_int, c_int, ctypes.c_uint64, c_void_p, c_int, c_int, c_int, POINTER(c_int64),
+                                        POINTER(c_void_p), POINTER(c_void_p)]
+        L.oracle_free.restype = None
+        L.oracle_free.argtypes = [c_void_p]
+        L.oracle_matrix_values.restype = None
+        L.oracle_matrix_values.argtypes = [c_void_p, c_void_p, c_int64, c_int64, ctypes.c_uint64, c_int, c_void_p]
+        L.oracle_dense_columns.restype = None
+        L.oracle_dense_columns.argtypes = [c_int64, c_int64, c_int64, c_int64, ctypes.c_uint64, c_int, c_int, c_void_p]
         _lib = L
     return _lib
 
@@ -318,6 +327,50 @@ def ref_grid_mm(path, ranks, X):
     return Y, [l for l in out.splitlines() if l.startswith("A:")][0]
 
 
+class RefMatrix:
+    """A matrix resident in the unmodified reference (SpParMat over SpDCCols, built once) for repeated Mult_AnXBn_Synch
+    calls with fresh panels - bench.py's CPU legs at BASELINE.json's full sizes."""
+
+    def __init__(self, semiring, m, n, I, J, V, x_dtype, colmajor_sorted=False, threads=None):
+        R = ref()
+        R.cbref_matrix_create.restype = c_void_p
+        R.cbref_matrix_create.argtypes = [c_char_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int]
+        R.cbref_matrix_mult.restype = c_int
+        R.cbref_matrix_mult.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_double), POINTER(c_int64)]
+        R.cbref_matrix_free.restype = None
+        R.cbref_matrix_free.argtypes = [c_void_p]
+        if threads:
+            R.cbref_set_num_threads(int(threads))
+        I = np.ascontiguousarray(I, np.int64)
+        J = np.ascontiguousarray(J, np.int64)
+        if V is None:
+            ad, Vb = PATTERN, None
+        else:
+            Vb = np.ascontiguousarray(V)
+            Vb = Vb.view(np.uint8) if Vb.dtype == np.bool_ else Vb
+            ad = CODE_OF[Vb.dtype]
+        self.m, self.n, self.nnz, self.xdt = m, n, len(I), np.dtype(x_dtype)
+        self.h = R.cbref_matrix_create(ref_key(semiring, ad, CODE_OF[self.xdt]).encode(), m, n, len(I), _p(I), _p(J), _p(Vb),
+                                       int(colmajor_sorted))
+        if not self.h:
+            raise ValueError("reference: no such semiring / type combination")
+
+    def mult(self, X, want_y=True):
+        """-> (Y or None, seconds of the Mult_AnXBn_Synch call, nnz of the reference's sparse C)"""
+        X = np.ascontiguousarray(X, self.xdt)
+        Y = np.empty((self.m, X.shape[1]), self.xdt) if want_y else None
+        sec, nnzc = c_double(0), c_int64(0)
+        rc = ref().cbref_matrix_mult(self.h, X.shape[1], _p(X), _p(Y), ctypes.byref(sec), ctypes.byref(nnzc))
+        if rc:
+            raise ValueError(f"reference: rc={rc}")
+        return Y, sec.value, nnzc.value
+
+    def free(self):
+        if self.h:
+            ref().cbref_matrix_free(self.h)
+            self.h = None
+
+
 def ref_best_time(semiring, m, n, I, J, V, X, cores, reps=1):
     """Seconds of the fastest configuration of the unmodified reference on `cores` host cores: 1 process x cores OpenMP
     threads (libcbref.so) or a 2x2 process grid x cores/4 threads (cbref_grid) - its MPI+OpenMP design is faster with
@@ -481,6 +534,46 @@ def rmat_matrix(scale, edgefactor=16, seed=0, initiator=(0.57, 0.19, 0.19, 0.05)
         I, J = np.concatenate([I, J]), np.concatenate([J, I])
     I, J, _ = dedup(I, J, None, n)
     return n, I, J
+
+
+def _thresholds(initiator):
+    a, b, c, _ = initiator
+    return np.array([int(round(a * 65536)), int(round((a + b) * 65536)), int(round((a + b + c) * 65536))], np.uint32)
+
+
+def rmat_matrix_fast(scale, edgefactor=16, seed=0, initiator=(0.57, 0.19, 0.19, 0.05), symmetric=True, remove_loops=True,
+                     col_major=False):
+    """rmat_matrix() through the C restatement (gen_oracle.c, OpenMP): the same (n, I, J), in seconds at scale 24.
+    col_major=True returns the entries sorted by column then row (what SpDCCols' tuple constructor wants)."""
+    thr = _thresholds(initiator)
+    nnz, pi, pj = c_int64(), c_void_p(), c_void_p()
+    rc = lib().oracle_gen_matrix(scale, edgefactor, seed, _p(thr), int(symmetric), int(remove_loops), int(col_major),
+                                 ctypes.byref(nnz), ctypes.byref(pi), ctypes.byref(pj))
+    if rc:
+        raise MemoryError("oracle_gen_matrix: out of memory")
+    try:
+        I = np.ctypeslib.as_array(ctypes.cast(pi, POINTER(c_int64)), (max(nnz.value, 1),))[:nnz.value].copy()
+        J = np.ctypeslib.as_array(ctypes.cast(pj, POINTER(c_int64)), (max(nnz.value, 1),))[:nnz.value].copy()
+    finally:
+        lib().oracle_free(pi)
+        lib().oracle_free(pj)
+    return 1 << scale, I, J
+
+
+def matrix_values_fast(I, J, n, seed, dtype):
+    """matrix_values() through the C restatement"""
+    I = np.ascontiguousarray(I, np.int64)
+    J = np.ascontiguousarray(J, np.int64)
+    out = np.empty(len(I), dtype)
+    lib().oracle_matrix_values(_p(I), _p(J), len(I), n, seed, CODE_OF[np.dtype(dtype)], _p(out))
+    return out
+
+
+def dense_columns_fast(n, k, c0, kc, seed, dtype, kind="value"):
+    """columns [c0, c0+kc) of dense_operand(n, k, ...) through the C restatement, packed n x kc"""
+    out = np.empty((n, kc), dtype)
+    lib().oracle_dense_columns(n, k, c0, kc, seed, CODE_OF[np.dtype(dtype)], 1 if kind == "x_minplus" else 0, _p(out))
+    return out
 
 
 def er_matrix(scale, edgefactor=16, seed=0):

@@ -38,13 +38,14 @@ std::shared_ptr<CommGrid> grid1() {
 }
 
 template <class NT>
-SpDCCols<int64_t, NT>* tile_from_coo(int64_t m, int64_t n, int64_t nnz, const int64_t* I, const int64_t* J, const void* Vv) {
+SpDCCols<int64_t, NT>* tile_from_coo(int64_t m, int64_t n, int64_t nnz, const int64_t* I, const int64_t* J, const void* Vv, bool colmajor_sorted = false) {
     typedef std::tuple<int64_t, int64_t, NT> Tup;
     const NT* V = static_cast<const NT*>(Vv);
     Tup* t = new Tup[nnz > 0 ? nnz : 1];
 #pragma omp parallel for
     for (int64_t p = 0; p < nnz; ++p) t[p] = Tup(I[p], J[p], V ? V[p] : NT(1));
     // column-major order, as the SpDCCols tuple-array ctor requires (SpDCCols.cpp:186-195)
+    if (!colmajor_sorted)
     std::sort(t, t + nnz, [](const Tup& a, const Tup& b) {
         return std::get<1>(a) != std::get<1>(b) ? std::get<1>(a) < std::get<1>(b) : std::get<0>(a) < std::get<0>(b);
     });
@@ -137,9 +138,64 @@ int run(int via, int64_t m, int64_t n, int64_t nnz, const int64_t* I, const int6
     return run_synch<SR, NA, NX>(m, n, nnz, I, J, V, k, X, Y, panel, seconds);
 }
 
+// A resident reference matrix for repeated multiplies (bench.py's CPU legs at BASELINE.json's full sizes: the SpParMat is
+// built once, every timed step is one Mult_AnXBn_Synch with a fresh panel).
+struct RefMatBase {
+    virtual ~RefMatBase() {}
+    virtual int mult(int64_t k, const void* X, void* Y, double* seconds, int64_t* nnzC) = 0;
+};
+template <class SR, class NA, class NX>
+struct RefMat : RefMatBase {
+    typedef typename SR::T_promote NO;
+    typedef SpDCCols<int64_t, NA> DA;
+    typedef SpDCCols<int64_t, NX> DX;
+    typedef SpDCCols<int64_t, NO> DO;
+    int64_t m, n;
+    SpParMat<int64_t, NA, DA> A;
+    RefMat(int64_t m_, int64_t n_, int64_t nnz, const int64_t* I, const int64_t* J, const void* V, bool sorted)
+        : m(m_), n(n_), A(tile_from_coo<NA>(m_, n_, nnz, I, J, V, sorted), grid1()) {}
+    int mult(int64_t k, const void* Xv, void* Yv, double* seconds, int64_t* nnzC) override {
+        SpParMat<int64_t, NX, DX> Xs(dense_as_tile<NX>(n, k, static_cast<const NX*>(Xv)), grid1());
+        double t0 = MPI_Wtime();
+        SpParMat<int64_t, NO, DO> C = Mult_AnXBn_Synch<SR, NO, DO>(A, Xs);
+        if (seconds) *seconds = MPI_Wtime() - t0;
+        if (nnzC) *nnzC = C.getnnz();
+        if (Yv) {
+            NO* Y = static_cast<NO*>(Yv);
+            const NO id = SR::id();
+            for (int64_t q = 0; q < m * k; ++q) Y[q] = id;
+            Dcsc<int64_t, NO>* d = C.seq().GetDCSC();
+            if (d)
+                for (int64_t c = 0; c < d->nzc; ++c)
+                    for (int64_t p = d->cp[c]; p < d->cp[c + 1]; ++p) Y[d->ir[p] * k + d->jc[c]] = d->numx[p];
+        }
+        return 0;
+    }
+};
+
 }  // namespace
 
 extern "C" {
+
+// key as in cbref_spmm; colmajor_sorted != 0 promises (I, J) sorted by column then row (skips the driver's own sort)
+void* cbref_matrix_create(const char* key, int64_t m, int64_t n, int64_t nnz, const int64_t* I, const int64_t* J, const void* V, int colmajor_sorted) {
+    std::string s(key);
+#define CASE(name, SR, NA, NX) if (s == name) return new RefMat<SR<NA, NX>, NA, NX>(m, n, nnz, I, J, V, colmajor_sorted != 0);
+    CASE("plus_times:f64:f64", PlusTimesSRing, double, double)
+    CASE("plus_times:f32:f32", PlusTimesSRing, float, float)
+    CASE("plus_times:bool:i32", PlusTimesSRing, bool, int32_t)
+    CASE("plus_times:bool:bool", PlusTimesSRing, bool, bool)
+    CASE("min_plus:i32:i32", MinPlusSRing, int32_t, int32_t)
+    CASE("select_max:bool:i32", SelectMaxSRing, bool, int32_t)
+#undef CASE
+    fprintf(stderr, "cbref_matrix_create: unknown key %s\n", key);
+    return nullptr;
+}
+// one Mult_AnXBn_Synch of the resident matrix with the n x k row-major panel X; Y (m x k, may be NULL) receives the product
+int cbref_matrix_mult(void* h, int64_t k, const void* X, void* Y, double* seconds, int64_t* nnzC) {
+    return h ? static_cast<RefMatBase*>(h)->mult(k, X, Y, seconds, nnzC) : 1;
+}
+void cbref_matrix_free(void* h) { delete static_cast<RefMatBase*>(h); }
 
 int cbref_num_threads() { return omp_get_max_threads(); }
 void cbref_set_num_threads(int t) { omp_set_num_threads(t); }

@@ -361,5 +361,19 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y,
     build_csr(&arow, trip);
     return cb_spmm_local(ctx, &arow, &xcol, Y, sr, 0);
 }
+int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int sr,
+                       int64_t gm, int64_t gn, int64_t gk, int dtype) {
+    const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;
+    int64_t r0, rl, x0, xl, k0, kl;
+    block_range(gm, pr, myrow, &r0, &rl); block_range(gn, pr, myrow, &x0, &xl); block_range(gk, pc, mycol, &k0, &kl);
+    cb_dense *X = nullptr, *Y = nullptr;
+    cb_dense_alloc(ctx, ctx->nranks == 1 ? gn : xl, kl, dtype, &X);
+    cb_dense_alloc(ctx, rl, kl, dtype, &Y);
+    if (kl > 0 && X->rows > 0) cb_dense_upload(X, X_host, ldx);
+    const int st = cb_spmm_summa(ctx, t, X, Y, sr, gm, gn, gk);
+    if (st == CB_OK && kl > 0 && rl > 0) cb_dense_download(Y, Y_host, ldy);
+    cb_dense_free(X); cb_dense_free(Y);
+    return st;
+}
 
 }  // extern "C"

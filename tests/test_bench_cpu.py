@@ -35,9 +35,46 @@ def test_workloads_cover_the_baseline_configs():
 
 
 def test_reference_arm_runs_without_a_gpu():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--ref-scale", "10", "--ref-cols", "4"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    """--impl reference on a small workload: the same matrix and panel as our arm (leading rows x leading columns), steps and
+    warm-up as asked, no GPU, none of the product's libraries."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "2", "--warmup", "1",
+                        "--ref-budget", "20"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["steps"] == 2 and line["warmup"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "GFLOP/s"
+    assert line["config"]["workload"].startswith("tiny: ") and "of the same panel" in line["config"]["sample"]
+    # a small matrix fits the budget whole: the sample is the full row range
+    assert "rows [0, 16384) of the 16384 x 16384 matrix" in line["config"]["sample"]
+
+
+def test_host_evaluation_of_sampled_rows_matches_the_oracle():
+    """bench.py's in-run parity check evaluates sampled rows with numpy; that evaluation itself is checked here against the
+    oracle (whole product) for every semiring the workloads use."""
+    import numpy as np
+    from oracle import oracle as O
+    n, I, J = O.rmat_matrix(9, 8, seed=3)
+    order = np.lexsort((J, I))
+    I, J = I[order], J[order]
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(I, minlength=n), out=rowptr[1:])
+    rows = np.array([0, 5, 17, int(np.argmax(np.diff(rowptr))), n - 1])
+    off = np.concatenate([[0], np.cumsum(np.diff(rowptr)[rows])])
+    sel = np.concatenate([np.arange(rowptr[r], rowptr[r + 1]) for r in rows])
+    for name, sr, adt, xdt, kind in (("c2", O.PLUS_TIMES, np.float32, np.float32, "value"), ("c4", O.PLUS_TIMES, np.float64, np.float64, "value"),
+                                     ("c5", O.MIN_PLUS, np.int32, np.int32, "x_minplus"), ("c5b", O.OR_AND, None, np.uint8, "value")):
+        w = bench.WORKLOADS[name]
+        V = None if adt is None else O.matrix_values(I, J, n, 1, adt)
+        X = O.dense_operand(n, 8, 42, xdt, kind)
+        ref = O.spmm(sr, n, n, I, J, V, X)
+        cols = J[sel]
+        ucols = np.unique(cols)
+        got = bench.host_rows(w, off, cols, None if V is None else V[sel], X[ucols], ucols)
+        for i, r in enumerate(rows):
+            if got[i] is None:
+                assert rowptr[r] == rowptr[r + 1] and (ref[r] == bench.semiring_identity(w)).all()
+            elif name in ("c2", "c4"):
+                assert np.allclose(got[i], ref[r].astype(np.float64), rtol=bench.TOL[w["xdt"]], atol=0)
+            else:
+                assert np.array_equal(got[i], ref[r])

@@ -54,6 +54,27 @@ def test_spmv_fullydistvec_and_dense_epilogues_on_process_grids(driver, tmp_path
     assert "SpMV and dense epilogues working correctly" in se and "rows reached" in so
 
 
+def test_rendezvous_survives_stale_files_and_cleans_up(driver, tmp_path):
+    """The file rendezvous behind the host collectives (CombBLAS/cb_mpi.h): a directory that still holds the files of a run
+    that died - same names, plausible sizes, another session - must not be read as this run's data (every file carries the
+    session nonce agreed on at start-up), and a run that ends normally leaves none of its files behind."""
+    rdv = tmp_path / "rdv"
+    rdv.mkdir()
+    stale = np.random.default_rng(0).integers(0, 255, 136, dtype=np.uint8).tobytes()       # nonce + 128-byte NCCL id of "op 0"
+    for q in range(4):
+        (rdv / f"c1_op0.r{q}").write_bytes(stale)
+        (rdv / f"c1_op1.r{q}").write_bytes(stale[:9])
+        (rdv / f"hello.{q}").write_bytes(stale[:8])
+        (rdv / f"ack.{q}").write_bytes(stale[:24])
+    (rdv / "session").write_bytes(np.full(3 + 256, 7, np.uint64).tobytes())                 # a finished session of that dead run
+    for _ in range(2):                                                                      # and twice in a row in the same directory
+        so, se = run_grid(driver, 4, rdv, "torus")
+        assert so.count("112 nonzeros") == 3 and "SpGEMM (sparse x sparse) working correctly" in se
+        left = sorted(f.name for f in rdv.iterdir() if not f.name.startswith("mock"))
+        # what may remain are the dead run's files nobody owns any more (ranks only remove their own session files)
+        assert all(n.startswith("c1_op") for n in left) and len(left) <= 8, left
+
+
 def test_spmmerror_program_on_2x2_processes(driver, tmp_path):
     so, se = run_grid(driver, 4, tmp_path, "torus")
     assert so.count("112 nonzeros") == 3 and "SpGEMM (sparse x sparse) working correctly" in se
@@ -334,3 +355,23 @@ def test_prebuilt_reference_binaries_for_the_gpu_box_are_current(driver, tmp_pat
     files = galerkin_inputs(str(tmp_path))
     r = subprocess.run([os.path.join(ref, "GalerkinNew_b200"), *files], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "Splitting approach is correct" in r.stderr, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("nproc,grid", [(4, ()), (6, (2, 3))])
+def test_host_layer_with_a_real_mpi_has_row_and_column_communicators(tmp_path, nproc, grid):
+    """-DCB_HAVE_MPI: CommGrid must split the world into processor-row / processor-column communicators the way the
+    reference does (src/CommGrid.cpp:66-67); user code reduces and broadcasts over GetRowWorld() / GetColWorld().
+    The MPI is the process-per-rank stand-in of oracle/mpi_multi, the C ABI the test-only mock."""
+    d = tmp_path
+    inc = [f"-I{PKG}/include", f"-I{ROOT}/include"]
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", *inc, "-o", str(d / "libcombblas_b200.so"),
+                           f"{ROOT}/tests/mock_abi/mock_combblas_b200.cpp"], timeout=300)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-w", "-DCB_HAVE_MPI", "-Dmain=cb_rank_main", f"-I{ROOT}/oracle/mpi_multi", *inc,
+                           "-c", f"{ROOT}/tests/hostmpi/commgrid_mpi_test.cpp", "-o", str(d / "t.o")], timeout=300)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-w", f"-I{ROOT}/oracle/mpi_multi", "-c", f"{ROOT}/oracle/mpi_multi/cbmpi.cpp",
+                           "-o", str(d / "cbmpi.o")], timeout=300)
+    subprocess.check_call(["/usr/bin/g++", "-o", str(d / "t"), str(d / "t.o"), str(d / "cbmpi.o"), f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}",
+                           "-lpthread"], timeout=300)
+    env = dict({k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}, CBMPI_NP=str(nproc))
+    r = subprocess.run([str(d / "t"), *[str(g) for g in grid]], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "CB_HAVE_MPI grid working correctly" in r.stdout, r.stdout + r.stderr
