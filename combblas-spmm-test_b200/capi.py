@@ -23,7 +23,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
-           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host"]
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe"]
 
 
 class CBError(RuntimeError):
@@ -105,6 +105,7 @@ def lib():
         L.cb_spmm_hub_info.argtypes = [c_void_p, POINTER(c_int64)]
         L.cb_spmm_ring_config.argtypes = [c_void_p, c_int]
         L.cb_spmm_k2_config.argtypes = [c_void_p, c_int, c_int]
+        L.cb_spmm_k2_pipe.argtypes = [c_void_p, c_int]
         L.cb_tile_row_lengths.argtypes = [c_void_p, c_void_p]
         L.cb_tile_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
         L.cb_dense_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
@@ -300,6 +301,10 @@ class Context:
     def k2_config(self, slab_bytes=0, point=-1):
         """Shape of the default local multiply: column-slab width in bytes (0 automatic) and operating point (-1 automatic)."""
         _check(lib().cb_spmm_k2_config(self.h, int(slab_bytes), int(point)), self.h)
+
+    def k2_pipe(self, depth=-1):
+        """Ring depth of the pipelined local multiply (K2P): 4, 8, 0 = round-1 walk, -1 = default."""
+        _check(lib().cb_spmm_k2_pipe(self.h, int(depth)), self.h)
 
     def summa_cache_a(self, on=True):
         _check(lib().cb_summa_cache_a(self.h, int(on)), self.h)

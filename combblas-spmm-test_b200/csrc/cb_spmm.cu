@@ -84,6 +84,7 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
     p.accumulate = accumulate;
     p.slab_bytes = ctx->k2_slab_bytes;
     p.point = ctx->k2_point;
+    p.pipe = ctx->k2_pipe;
     cbk::HubPlan hub_plan;                        // opt-in persistent variants K2H / K2R (cb_hub.cu); inactive -> plain K2
     CB_TRY(cb_hub_plan(ctx, t, row_bytes, stream, &hub_plan));
     if (hub_plan.active) p.hub = &hub_plan;
@@ -98,6 +99,13 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
 }
 
 extern "C" {
+
+int cb_spmm_k2_pipe(cb_ctx* ctx, int depth) {
+    if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: null ctx");
+    if (depth != -1 && depth != 0 && depth != 4 && depth != 8) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: depth %d (-1 default, 0 off, 4, 8)", depth);
+    ctx->k2_pipe = depth;
+    return CB_OK;
+}
 
 int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point) {
     if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_config: null ctx");

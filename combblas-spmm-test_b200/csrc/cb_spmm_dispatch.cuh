@@ -19,6 +19,9 @@
 #endif
 // hub variant: one persistent CTA of CB_HUB_BT threads per SM, CB_HUB_U row gathers in flight per lane.  1024 threads cap
 // the kernel at 64 registers, which U=4 fits without spills for every element type (U=8 spills 16-200 bytes on 4-byte types)
+#ifndef CB_PIPE_DEFAULT
+#define CB_PIPE_DEFAULT 0            // ring depth of K2P used when nothing else is asked for (0 = the round-1 walk)
+#endif
 #ifndef CB_HUB_U
 #define CB_HUB_U 4
 #endif
@@ -38,11 +41,12 @@ struct LaunchParams {
     const HubPlan* hub = nullptr;   // non-null: run the hub variant (K2H) with this shape
     int slab_bytes = 0;             // > 0: column slabs of this width for plain K2 (0 = one slab as wide as the layout allows)
     int point = -1;                 // operating point of plain K2: 0 deep, 1 wide, -1 choose by footprint
+    int pipe = -1;                  // register-ring depth of the pipelined walk K2P: 4 or 8; 0 = the round-1 walk; -1 = default
 };
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
-template <class Op, int VW, int R, int U, int MINB, bool FULL>
+template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PIPE = false>
 static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -67,7 +71,8 @@ static int launch_layout_f(const LaunchParams& p) {
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
-        cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
+        if constexpr (PIPE) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
+        else cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
     CB_CUDA(p.ctx, cudaGetLastError());
@@ -79,6 +84,12 @@ template <class Op, int VW, int R, int U, int MINB>
 static int launch_layout(const LaunchParams& p) {
     if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true>(p);
     return launch_layout_f<Op, VW, R, U, MINB, false>(p);
+}
+// K2P: D row gathers in flight per lane in a register ring
+template <class Op, int VW, int R, int D, int MINB>
+static int launch_pipe(const LaunchParams& p) {
+    if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, D, MINB, true, true>(p);
+    return launch_layout_f<Op, VW, R, D, MINB, false, true>(p);
 }
 
 // K2H / K2R: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
@@ -183,6 +194,20 @@ static int launch_op(const LaunchParams& p) {
             // lanes of a virtual warp carry no columns.  CB_K2_NARROW=1 runs them on 1- and 2-lane virtual warps (32 / 16 row
             // walkers per warp) - the same walker, other template arguments; opt-in until it has been timed on hardware
             static const bool narrow = getenv("CB_K2_NARROW") && atoi(getenv("CB_K2_NARROW")) != 0;
+            static const int pipe_env = getenv("CB_K2_PIPE") ? atoi(getenv("CB_K2_PIPE")) : -1;
+            const int pipe = p.pipe >= 0 ? p.pipe : (pipe_env >= 0 ? pipe_env : CB_PIPE_DEFAULT);
+            constexpr bool W64 = sizeof(typename Op::T) == 8;
+            if (pipe == 4 && nvec > 4) {
+                if (nvec <= 8) s = launch_pipe<Op, 8, 1, 4, (W64 ? 3 : 4)>(p);
+                else if (nvec <= 16) s = launch_pipe<Op, 16, 1, 4, (W64 ? 3 : 4)>(p);
+                else if (nvec <= 32) s = launch_pipe<Op, 32, 1, 4, (W64 ? 3 : 4)>(p);
+                else s = launch_pipe<Op, 32, 2, 4, (W64 ? 2 : 3)>(p);
+            } else if (pipe == 8 && nvec > 4) {
+                if (nvec <= 8) s = launch_pipe<Op, 8, 1, 8, (W64 ? 2 : 3)>(p);
+                else if (nvec <= 16) s = launch_pipe<Op, 16, 1, 8, (W64 ? 2 : 3)>(p);
+                else if (nvec <= 32) s = launch_pipe<Op, 32, 1, 8, (W64 ? 2 : 3)>(p);
+                else s = launch_pipe<Op, 32, 2, 4, (W64 ? 2 : 3)>(p);
+            } else
             if (narrow && nvec == 1) s = launch_layout<Op, 1, 1, 1, 4>(p);
             else if (narrow && nvec <= 2) s = launch_layout<Op, 2, 1, 2, 4>(p);
             else if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);

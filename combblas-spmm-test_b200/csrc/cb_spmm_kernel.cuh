@@ -393,6 +393,186 @@ cb_spmm_kernel(const SpmmArgs a) {
     cb_spmm_walk<Op, VW, R, U, FULL, false>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K2P: the same walk with the row gathers PIPELINED THROUGH A REGISTER RING (the default kernel since round 2).
+//
+// What the profile of K2 said (profiles/r02_*): on L2-resident panels a warp spends only ~45 % of its time with gathers in
+// flight - per step of VW nonzeros it waits once for the (column, value) entries and once per group of U gathers, and folds
+// in between - so the SM sustains about half of what a pure gather loop reaches on the same hardware (tools/gather_probe.cu:
+// 20 TB/s from L2, 7.3-7.8 TB/s from DRAM).  Here
+//   * the entries of step s+1 are loaded while step s is processed (one step of prefetch, two registers);
+//   * every lane keeps D row gathers in flight ALL the time: slot j mod D of a register ring holds the row of nonzero j;
+//     right after nonzero j has been folded out of its slot, the gather of nonzero j+D is issued into the same slot - also
+//     across step boundaries, since the next step's columns are already there.  The loop over the VW entries of a step is
+//     fully unrolled, so the slots are static registers;
+//   * three copies of the unrolled body, chosen per step by warp-uniform tests: no row end anywhere in the step and all
+//     entries in range (straight-line fold / gather code), row ends but in range, and the general predicated one for the
+//     last steps of a chunk.
+// Fold order, row ends, split-row pieces and the accumulate mode are K2's, so every result bit is K2's.
+template <class Op, int VW, int R, int D, bool FULL>
+__device__ __forceinline__ void cb_spmm_walk_pipe(const SpmmArgs& a, const int64_t chunk) {
+    static_assert(D >= 1 && D <= VW && (VW % D) == 0, "ring depth must divide the virtual warp width");
+    typedef typename Op::T T;
+    typedef typename Op::TA TA;
+    constexpr int EPL = 16 / sizeof(T);
+    constexpr bool HASVAL = Op::akind != A_PATTERN;
+    const int lane = threadIdx.x & 31;
+    const int vl = lane & (VW - 1);
+    const int vshift = lane & ~(VW - 1);
+    const bool live = chunk < a.nchunks;
+
+    const int slab_off = blockIdx.y * a.slab_bytes;
+    const int slab_row_bytes = min(a.row_bytes, a.total_row_bytes - slab_off);
+    bool lane_on[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) lane_on[r] = FULL || (vl + r * VW) * 16 < slab_row_bytes;
+    const char* const xbase = a.X + slab_off + vl * 16;
+    const uint32_t ldx = (uint32_t)a.ldx_bytes;
+
+    int s = 0, e = 0, ridx = 0;
+    bool head_open = false;
+    if (live) {
+        s = a.chunk_start[chunk];
+        e = a.chunk_start[chunk + 1];
+        const int cr = a.chunk_row[chunk];
+        ridx = cr & 0x7fffffff;
+        head_open = cr < 0;
+    }
+    const int len = e - s;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);       // every lane of the warp runs the same number of steps
+
+    const int32_t* const cfp = a.colflag + s + vl;
+    const TA* const avp = reinterpret_cast<const TA*>(a.vals) + s + vl;
+    RowFrag<Op, R> acc;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::id();
+    bool first = true;
+    int row = live ? a.nzrows[ridx] : 0;
+    char* const carry_head = a.carry + (2 * chunk) * a.carry_stride + slab_off;
+
+    auto fold = [&](const TA av, const RowFrag<Op, R>& x) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) {
+#ifdef CB_FMA
+                acc.v[r].v[q] = (Op::first_touch && first) ? Op::mul(av, x.v[r].v[q]) : Op::madd(av, x.v[r].v[q], acc.v[r].v[q]);
+#else
+                const T prod = Op::mul(av, x.v[r].v[q]);
+                acc.v[r].v[q] = (Op::first_touch && first) ? prod : Op::add(prod, acc.v[r].v[q]);     // see cb_spmm_walk
+#endif
+            }
+        first = false;
+    };
+    auto flush = [&](bool more) {
+        char* dst;
+        bool rmw = false;
+        if (head_open) { dst = carry_head; head_open = false; }            // piece of a split row
+        else { dst = a.Y + (int64_t)row * a.ldy_bytes + slab_off; rmw = a.accumulate != 0; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (lane_on[r]) {
+                char* d = dst + (vl + r * VW) * 16;
+                if (rmw) {
+                    const Vec16<T> y = ld16<T>(d);
+#pragma unroll
+                    for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::add(y.v[q], acc.v[r].v[q]);
+                }
+                st16_stream<T>(d, acc.v[r]);
+#pragma unroll
+                for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::id();
+            }
+        }
+        first = true;
+        ++ridx;
+        if (more) row = a.nzrows[ridx];
+    };
+    auto gather = [&](RowFrag<Op, R>& dst, const uint32_t c) {
+        const char* xr = xbase + (uint64_t)c * ldx;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lane_on[r]) dst.v[r] = ldg16<T>(xr + r * VW * 16);
+    };
+
+    // entries of this step and of the next one: lane vl holds nonzero base + vl of the chunk
+    int cf_cur = 0, cf_nxt = 0;
+    TA av_cur = TA(), av_nxt = TA();
+    if (vl < len) { cf_cur = ld_stream(cfp); if (HASVAL) av_cur = ld_stream_val<TA>(avp); }
+    if (VW + vl < len) { cf_nxt = ld_stream(cfp + VW); if (HASVAL) av_nxt = ld_stream_val<TA>(avp + VW); }
+
+    RowFrag<Op, R> x[D];
+#pragma unroll
+    for (int u = 0; u < D; ++u) {   // fill the ring: rows of the first D nonzeros
+        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cf_cur, u, VW) & 0x7fffffffu;
+        if (u < len) gather(x[u], c);
+    }
+
+    for (int base = 0; base < maxlen; base += VW) {
+        const int rem = len - base;                         // nonzeros this virtual warp still owns (may be <= 0)
+        const uint32_t fm = (__ballot_sync(0xffffffffu, cf_cur < 0) >> vshift) & (VW == 32 ? 0xffffffffu : ((1u << VW) - 1u));
+        cf_cur &= 0x7fffffff;                               // the row-end flags now live in fm; what is left is the column
+        // column of nonzero jn >= j + D of this step, or of the next step's entries (their flag is still in place)
+        auto col_of = [&](const int jn) -> uint32_t {
+            return jn < VW ? (uint32_t)__shfl_sync(0xffffffffu, cf_cur, jn, VW) : ((uint32_t)__shfl_sync(0xffffffffu, cf_nxt, jn - VW, VW) & 0x7fffffffu);
+        };
+        // warp-uniform: every virtual warp of the warp has this step and the whole next one in range / no row ends in this step
+        const bool deep = __all_sync(0xffffffffu, rem >= 2 * VW);
+        const bool ends = __any_sync(0xffffffffu, fm != 0u);
+        if (deep && !ends) {
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const TA av = HASVAL ? (TA)__shfl_sync(0xffffffffu, av_cur, j, VW) : TA();
+                fold(av, x[j % D]);
+                gather(x[j % D], col_of(j + D));
+            }
+        } else if (deep) {
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const TA av = HASVAL ? (TA)__shfl_sync(0xffffffffu, av_cur, j, VW) : TA();
+                fold(av, x[j % D]);
+                if ((fm >> j) & 1u) flush(true);
+                gather(x[j % D], col_of(j + D));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const TA av = HASVAL ? (TA)__shfl_sync(0xffffffffu, av_cur, j, VW) : TA();
+                if (j < rem) {
+                    fold(av, x[j % D]);
+                    if ((fm >> j) & 1u) flush(j + 1 < rem);
+                }
+                const uint32_t c = col_of(j + D);
+                if (j + D < rem) gather(x[j % D], c);
+            }
+        }
+        cf_cur = cf_nxt;
+        av_cur = av_nxt;
+        cf_nxt = 0;
+        av_nxt = TA();
+        if (base + 2 * VW + vl < len) {
+            cf_nxt = ld_stream(cfp + base + 2 * VW);
+            if (HASVAL) av_nxt = ld_stream_val<TA>(avp + base + 2 * VW);
+        }
+    }
+    // a row still open at the end of the chunk continues in the next chunk: park the piece
+    if (live && !first) {
+        char* dst = carry_head + (head_open ? 0 : a.carry_stride);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lane_on[r]) st16<T>(dst + (vl + r * VW) * 16, acc.v[r]);
+    }
+}
+
+template <class Op, int VW, int R, int D, int MINB, bool FULL>
+__global__ void __launch_bounds__(256, MINB)
+cb_spmm_pipe_kernel(const SpmmArgs a) {
+    constexpr int NV = 32 / VW;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    cb_spmm_walk_pipe<Op, VW, R, D, FULL>(a, warp * NV + ((threadIdx.x & 31) / VW));
+}
+
 // Combine the pieces of split rows in chunk order: Y[row] = tail[c0] (+) head[c0+1] (+) ... (+) head[c1].
 // One virtual warp of 32 lanes per split row, looping over the row's vectors.
 struct FixupArgs {

@@ -216,6 +216,9 @@ int cb_spmm_ring_config(cb_ctx* ctx, int depth);
  * as the layout allows; 64, 128, 256, 512); point = 0 deep / 1 wide / -1 chosen from the footprint of the X rows.  Results
  * do not depend on either (columns are independent). */
 int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point);
+/* Ring depth of the pipelined local multiply (K2P, csrc/cb_spmm_kernel.cuh): every lane keeps `depth` row gathers in flight
+ * in a register ring; 4 or 8, 0 = the round-1 walk (gathers in groups), -1 = the build's default.  Results are identical. */
+int cb_spmm_k2_pipe(cb_ctx* ctx, int depth);
 /* The hub selection rule as pure host arithmetic (no device needed): the max_hubs most frequent columns with at least
  * two nonzeros, most frequent first, ties by ascending column; cum[r] = nonzeros in the columns of rank <= r.
  * Returns the number of hubs written, or -1 on bad arguments. */

@@ -54,7 +54,7 @@ template <> double rnd_val<double>(std::mt19937& g) { return (double)(1 + g() % 
 // requires its result to be bit-identical to plain K2's.
 template <class Op, int VW, int R, int U, bool FULL>
 static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elements of Op::T per panel row */, int32_t L, int hub, unsigned seed,
-                     bool accumulate, int hub_cs = 0, int nhub = 0, int ring = 0) {
+                     bool accumulate, int hub_cs = 0, int nhub = 0, int ring = 0, int pipe = 0) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     std::mt19937 g(seed);
@@ -107,7 +107,16 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
     dim3 grid((unsigned)((t.nchunks + 8 * NV - 1) / (8 * NV)), (unsigned)((row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     long long syncs = 0;
     std::vector<T> Yplain;
-    if (hub_cs > 0) {
+    if (pipe) {
+        // K2P (register-ring walk, U = ring depth) after plain K2 on a copy: must reproduce it bit for bit
+        std::vector<T> Ysave = Y;
+        emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL>(a); });
+        Yplain = Y;
+        Y = Ysave;
+        a.Y = (char*)Y.data();
+        std::fill(carry.begin(), carry.end(), (char)0x77);
+        if constexpr (U <= VW) syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_pipe_kernel<Op, VW, R, U, 3, FULL>(a); });
+    } else if (hub_cs > 0) {
         // plain K2 on a copy first: K2H must reproduce it bit for bit (same walk, same fold order)
         std::vector<T> Ysave = Y;
         emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, U, 3, FULL>(a); });
@@ -153,7 +162,7 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         emul::launch(dim3((unsigned)((t.nsplit + 7) / 8)), dim3(256), [&] { cb_fixup_kernel<Op>(f); });
     }
     long bad = 0;
-    if (hub_cs > 0) {
+    if (hub_cs > 0 || pipe) {
         if (t.nsplit) {      // fix-up of the plain run, so the two results are comparable row for row
             FixupArgs f{};
             f.split_row = t.split_row.data(); f.nsplit = t.nsplit; f.nzrows = t.nzrows.data(); f.rowptr = t.rowptr.data();
@@ -201,6 +210,22 @@ int main(int argc, char** argv) {
     bad += run_case<PlusTimes<double, A_BOOL>, 1, 1, 1, true>("narrow pt_f64 boolA VW1 k=2", 45, 50, 2, 32, 45, 44 + sd, true);
     bad += run_case<OrAnd<A_PATTERN>, 2, 1, 2, true>("narrow or_and VW2 k=32 bytes", 50, 40, 8, 32, 38, 45 + sd, false);
     bad += run_case<SelectMax<int32_t>, 1, 1, 1, false>("narrow selectmax_i32 VW1 k=3", 45, 50, 3, 32, 45, 46 + sd, false);
+    // K2P, the pipelined walk (register ring of depth D = the U argument): every layout, row ends in every position,
+    // chunks shorter than a step, shorter than the ring, one step and two steps long, ragged widths, accumulate mode
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pipe pt_f32 VW16 D4", 61, 97, 64, 32, 150, 51 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("pipe pt_f32 VW16 D8 acc", 61, 97, 64, 32, 150, 52 + sd, true, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, false>("pipe pt_f32 VW32 k=100 D8", 40, 200, 100, 32, 90, 53 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_PATTERN>, 32, 1, 4, false>("pipe pt_f32 pat 3 slabs D4", 33, 60, 300, 32, 55, 54 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, true>("pipe pt_f64 VW32 R2 D4", 30, 80, 128, 32, 70, 55 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<double, A_BOOL>, 32, 2, 4, false>("pipe pt_f64 boolA R2 ragged acc", 30, 80, 100, 32, 70, 56 + sd, true, 0, 0, 0, 1);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 4, true>("pipe minplus_i32 VW8 D4", 70, 64, 32, 32, 60, 57 + sd, false, 0, 0, 0, 1);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("pipe minplus_i32 VW8 D8 acc", 70, 64, 32, 32, 60, 58 + sd, true, 0, 0, 0, 1);
+    bad += run_case<SelectMax<int64_t>, 8, 1, 8, false>("pipe selectmax_i64 VW8 k=13", 45, 50, 13, 32, 45, 59 + sd, false, 0, 0, 0, 1);
+    bad += run_case<OrAnd<A_PATTERN>, 8, 1, 4, false>("pipe or_and VW8 k=96 bytes", 50, 40, 24, 32, 38, 60 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("pipe pt_f32 VW16 larger D4", 400, 900, 64, 64, 700, 61 + sd, false, 0, 0, 0, 1);
+    bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("pipe minplus_i64 larger acc D8", 300, 500, 32, 64, 400, 62 + sd, true, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 63 + sd, false, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_BOOL>, 8, 1, 8, true>("pipe pt_f32 boolA VW8 L=40 D8", 200, 300, 32, 40, 170, 64 + sd, true, 0, 0, 0, 1);
     // K2H, the hub variant: persistent CTAs, dynamic chunks, hub rows in the shared memory of a 1/2/4-CTA cluster
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs1", 61, 97, 64, 32, 150, 21 + sd, false, 1, 20);
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs2 acc", 61, 97, 64, 32, 150, 22 + sd, true, 2, 33);
