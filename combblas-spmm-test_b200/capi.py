@@ -23,7 +23,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
-           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe"]
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe", "cb_spmm_k2_l2", "cb_spgemm_local", "cb_spgemm_summa", "cb_coo_info", "cb_coo_download", "cb_coo_free"]
 
 
 class CBError(RuntimeError):
@@ -106,6 +106,12 @@ def lib():
         L.cb_spmm_ring_config.argtypes = [c_void_p, c_int]
         L.cb_spmm_k2_config.argtypes = [c_void_p, c_int, c_int]
         L.cb_spmm_k2_pipe.argtypes = [c_void_p, c_int]
+        L.cb_spmm_k2_l2.argtypes = [c_void_p, c_int]
+        L.cb_spgemm_local.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]
+        L.cb_spgemm_summa.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int64, POINTER(c_void_p)]
+        L.cb_coo_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]
+        L.cb_coo_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+        L.cb_coo_free.argtypes = [c_void_p]
         L.cb_tile_row_lengths.argtypes = [c_void_p, c_void_p]
         L.cb_tile_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
         L.cb_dense_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
@@ -283,6 +289,27 @@ class Context:
     def spmm_summa(self, tile, X, Y, semiring, gm, gn, gk):
         _check(lib().cb_spmm_summa(self.h, tile.h, X.h, Y.h, semiring, gm, gn, gk), self.h)
 
+    def _coo_out(self, c):
+        nnz, m, k, dt = c_int64(), c_int64(), c_int64(), c_int()
+        _check(lib().cb_coo_info(c, byref(nnz), byref(m), byref(k), byref(dt)), self.h)
+        rows, cols = np.empty(nnz.value, np.int64), np.empty(nnz.value, np.int64)
+        vals = np.empty(nnz.value, NP_OF[dt.value])
+        _check(lib().cb_coo_download(c, _ptr(rows), _ptr(cols), _ptr(vals)), self.h)
+        lib().cb_coo_free(c)
+        return rows, cols, vals
+
+    def spgemm_local(self, A, B, semiring, dtype):
+        """C = A (x).(+) B for a sparse B on this GPU -> (rows, cols, vals), column-major sorted, merged."""
+        c = c_void_p()
+        _check(lib().cb_spgemm_local(self.h, A.h, B.h, semiring, CODE_OF[np.dtype(dtype)], byref(c)), self.h)
+        return self._coo_out(c)
+
+    def spgemm_summa(self, A, B, semiring, dtype, gm, gn, gk):
+        """the same over the process grid (collective): this rank's block of C with local indices"""
+        c = c_void_p()
+        _check(lib().cb_spgemm_summa(self.h, A.h, B.h, semiring, CODE_OF[np.dtype(dtype)], gm, gn, gk, byref(c)), self.h)
+        return self._coo_out(c)
+
     def spmm_summa_host(self, tile, X: np.ndarray, Y: np.ndarray, semiring, gm, gn, gk):
         """This rank's X tile in host memory in, its Y tile in host memory out; collective over the grid."""
         assert X.flags.c_contiguous and Y.flags.c_contiguous and X.dtype == Y.dtype
@@ -301,6 +328,10 @@ class Context:
     def k2_config(self, slab_bytes=0, point=-1):
         """Shape of the default local multiply: column-slab width in bytes (0 automatic) and operating point (-1 automatic)."""
         _check(lib().cb_spmm_k2_config(self.h, int(slab_bytes), int(point)), self.h)
+
+    def k2_l2(self, budget_mb=-1):
+        """L2 residency hints of K2P: MB of most-used X rows gathered with evict_last (0 off, -1 default)."""
+        _check(lib().cb_spmm_k2_l2(self.h, int(budget_mb)), self.h)
 
     def k2_pipe(self, depth=-1):
         """Ring depth of the pipelined local multiply (K2P): 4, 8, 0 = round-1 walk, -1 = default."""

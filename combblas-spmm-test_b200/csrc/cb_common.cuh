@@ -41,6 +41,7 @@ struct cb_ctx {
     // hub variant of K2 (cb_hub.cu): -1 / 0 = follow the CB_SPMM_HUB* environment, otherwise set by cb_spmm_hub_config
     int hub_enable = -1, hub_cluster = 0, hub_slab_bytes = 0;
     int ring_depth = -1;              // K2R ring depth: -1 = follow CB_SPMM_RING, 0 = off (cb_spmm_ring_config)
+    int k2_l2_mb = -1;                // K2P L2 residency hints: budget in MB for the rows kept with evict_last; 0 off, -1 default
     int k2_pipe = -1;                 // K2P ring depth: -1 default, 0 round-1 walk, 4, 8
     int k2_slab_bytes = 0, k2_point = -1;   // plain K2: column-slab width (0 = automatic) and operating point (cb_spmm_k2_config)
     std::string err;

@@ -3,6 +3,7 @@
 // never touches any of this.  Opt-in: cb_spmm_hub_config(ctx, 1, ...) or CB_SPMM_HUB=1.
 #include <algorithm>
 #include <numeric>
+#include <cub/cub.cuh>
 #include "cb_hub.cuh"
 
 struct cb_hub {
@@ -14,6 +15,8 @@ struct cb_hub {
     std::vector<int64_t> cum;         // [nhub_max] nonzeros in the columns of rank <= r
     int last_nhub = 0;
     double last_cover = 0;
+    uint8_t* hubcls = nullptr;        // [nnz] device: floor(log2(rank + 1)) of the nonzero's column by descending use, 255 = used once
+    bool cls_built = false;
 };
 
 void cb_hub_release(cb_tile* t) {
@@ -21,6 +24,7 @@ void cb_hub_release(cb_tile* t) {
     cudaFree(t->hub->hubslot);
     cudaFree(t->hub->hubcols);
     cudaFree(t->hub->counters);
+    cudaFree(t->hub->hubcls);
     delete t->hub;
     t->hub = nullptr;
 }
@@ -35,6 +39,62 @@ __global__ void __launch_bounds__(256)
 cb_hub_slot_kernel(const int32_t* __restrict__ colflag, int64_t nnz, const uint16_t* __restrict__ rank_of_col, uint16_t* __restrict__ hubslot) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
         hubslot[p] = rank_of_col[colflag[p] & 0x7fffffff];
+}
+
+// ---- use classes for the L2 residency hints of K2P
+__global__ void __launch_bounds__(256)
+cb_iota_kernel(int32_t* p, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+__global__ void __launch_bounds__(256)
+cb_class_of_col_kernel(const int* __restrict__ counts_sorted, const int32_t* __restrict__ cols_sorted, int64_t n, uint8_t* __restrict__ class_of_col) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        class_of_col[cols_sorted[r]] = counts_sorted[r] >= 2 ? (uint8_t)(63 - __clzll((long long)(r + 1))) : (uint8_t)255;
+}
+__global__ void __launch_bounds__(256)
+cb_hubcls_kernel(const int32_t* __restrict__ colflag, int64_t nnz, const uint8_t* __restrict__ class_of_col, uint8_t* __restrict__ hubcls) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+        hubcls[p] = class_of_col[colflag[p] & 0x7fffffff];
+}
+
+int cb_hubcls_get(cb_ctx* ctx, const cb_tile* tile, const uint8_t** cls) {
+    *cls = nullptr;
+    if (!tile->owns_slab || tile->nnz == 0 || tile->n >= (1LL << 30)) return CB_OK;
+    cb_tile* t = const_cast<cb_tile*>(tile);
+    if (!t->hub) t->hub = new cb_hub();
+    cb_hub* h = t->hub;
+    if (!h->cls_built) {
+        cb_scratch sc;
+        int *d_counts = nullptr, *d_counts_sorted = nullptr;
+        int32_t *d_cols = nullptr, *d_cols_sorted = nullptr;
+        uint8_t* d_class = nullptr;
+        CB_CUDA(ctx, sc.alloc(&d_counts, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_counts_sorted, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_cols, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_cols_sorted, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_class, (size_t)t->n));
+        CB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)t->n * sizeof(int), ctx->compute));
+        const unsigned blocks = (unsigned)std::min<int64_t>((t->nnz + 255) / 256, (int64_t)ctx->sm_count * 16);
+        const unsigned nblocks = (unsigned)std::min<int64_t>((t->n + 255) / 256, (int64_t)ctx->sm_count * 16);
+        cb_hub_count_kernel<<<blocks, 256, 0, ctx->compute>>>(t->colflag, t->nnz, d_counts);
+        cb_iota_kernel<<<nblocks, 256, 0, ctx->compute>>>(d_cols, t->n);
+        CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+        size_t tmp_bytes = 0;
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_counts, d_counts_sorted, d_cols, d_cols_sorted, (int)t->n, 0, 32, ctx->compute));
+        char* tmp = nullptr;
+        CB_CUDA(ctx, sc.alloc(&tmp, tmp_bytes));
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, d_counts, d_counts_sorted, d_cols, d_cols_sorted, (int)t->n, 0, 32, ctx->compute));
+        cb_class_of_col_kernel<<<nblocks, 256, 0, ctx->compute>>>(d_counts_sorted, d_cols_sorted, t->n, d_class);
+        cudaError_t e = cudaMalloc((void**)&h->hubcls, (size_t)t->nnz);
+        if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%lld) for the column use classes: %s", (long long)t->nnz, cudaGetErrorString(e));
+        cb_hubcls_kernel<<<blocks, 256, 0, ctx->compute>>>(t->colflag, t->nnz, d_class, h->hubcls);
+        CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+        h->cls_built = true;
+    }
+    *cls = h->hubcls;
+    return CB_OK;
 }
 
 extern "C" int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs, int32_t* hubcols, int64_t* cum) {

@@ -27,6 +27,9 @@ struct HubPlan {
 };
 }  // namespace cbk
 
+// per-nonzero use class of its column, for the L2 residency hints of K2P (built lazily, owned tiles only); *cls == nullptr when
+// the tile cannot have one
+int cb_hubcls_get(cb_ctx* ctx, const cb_tile* tile, const uint8_t** cls);
 int cb_hub_plan(cb_ctx* ctx, const cb_tile* tile, int64_t row_bytes, cudaStream_t stream, cbk::HubPlan* plan);
 void cb_hub_release(cb_tile* tile);
 extern "C" int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs, int32_t* hubcols, int64_t* cum);

@@ -2,6 +2,10 @@
 #include <algorithm>
 #include "cb_spmm_dispatch.cuh"
 
+#ifndef CB_L2_HINT_MB_DEFAULT
+#define CB_L2_HINT_MB_DEFAULT 0      // budget of the evict_last rows when nothing else is asked for (0 = no hints)
+#endif
+
 // K3: rows of the tile without nonzeros receive SR::id() - the dense-output convention of the reference's
 // dense SpMV (std::fill_n(localy, ysize, SR::id()), include/CombBLAS/ParFriends.h:1960-1963), restricted to
 // the rows K2 will not write so Y is written exactly once.
@@ -85,6 +89,18 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
     p.slab_bytes = ctx->k2_slab_bytes;
     p.point = ctx->k2_point;
     p.pipe = ctx->k2_pipe;
+    {
+        // L2 residency hints (K2P): worth it only when the X rows this tile touches do not fit in L2 anyway
+        static const int l2_env = getenv("CB_K2_L2_MB") ? atoi(getenv("CB_K2_L2_MB")) : -1;
+        const int l2_mb = ctx->k2_l2_mb >= 0 ? ctx->k2_l2_mb : (l2_env >= 0 ? l2_env : CB_L2_HINT_MB_DEFAULT);
+        if (l2_mb > 0 && stream == ctx->compute && (double)t->nzc * (double)row_bytes > 1.5e6 * (double)l2_mb) {
+            CB_TRY(cb_hubcls_get(ctx, t, &p.hubcls));
+            int c = -1;
+            while ((2LL << (c + 1)) * row_bytes <= (int64_t)l2_mb * 1000000LL) ++c;     // 2^(c+1) rows of the classes 0..c fit the budget
+            p.cls_max = c;
+            if (c < 0) p.hubcls = nullptr;
+        }
+    }
     cbk::HubPlan hub_plan;                        // opt-in persistent variants K2H / K2R (cb_hub.cu); inactive -> plain K2
     CB_TRY(cb_hub_plan(ctx, t, row_bytes, stream, &hub_plan));
     if (hub_plan.active) p.hub = &hub_plan;
@@ -99,6 +115,13 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
 }
 
 extern "C" {
+
+int cb_spmm_k2_l2(cb_ctx* ctx, int budget_mb) {
+    if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_l2: null ctx");
+    if (budget_mb < -1 || budget_mb > 4096) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_l2: budget of %d MB (-1 default, 0 off)", budget_mb);
+    ctx->k2_l2_mb = budget_mb;
+    return CB_OK;
+}
 
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth) {
     if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: null ctx");

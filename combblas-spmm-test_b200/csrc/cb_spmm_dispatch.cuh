@@ -41,12 +41,14 @@ struct LaunchParams {
     const HubPlan* hub = nullptr;   // non-null: run the hub variant (K2H) with this shape
     int slab_bytes = 0;             // > 0: column slabs of this width for plain K2 (0 = one slab as wide as the layout allows)
     int point = -1;                 // operating point of plain K2: 0 deep, 1 wide, -1 choose by footprint
+    const uint8_t* hubcls = nullptr; // non-null: K2P gathers rows of columns of class <= cls_max with evict_last, others evict_first
+    int cls_max = -1;
     int pipe = -1;                  // register-ring depth of the pipelined walk K2P: 4 or 8; 0 = the round-1 walk; -1 = default
 };
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
-template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PIPE = false>
+template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PIPE = false, bool POL = false>
 static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -66,12 +68,14 @@ static int launch_layout_f(const LaunchParams& p) {
     a.carry = (char*)t->carry;
     a.carry_stride = p.total_row_bytes;
     a.accumulate = p.accumulate;
+    a.hubcls = p.hubcls;
+    a.cls_max = p.cls_max;
     constexpr int NV = 32 / VW;
     const int64_t vws_per_block = 8 * NV;
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
-        if constexpr (PIPE) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
+        if constexpr (PIPE) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL, POL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
         else cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
@@ -88,8 +92,12 @@ static int launch_layout(const LaunchParams& p) {
 // K2P: D row gathers in flight per lane in a register ring
 template <class Op, int VW, int R, int D, int MINB>
 static int launch_pipe(const LaunchParams& p) {
-    if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, D, MINB, true, true>(p);
-    return launch_layout_f<Op, VW, R, D, MINB, false, true>(p);
+    const bool full = p.total_row_bytes % (VW * R * 16) == 0;
+    if constexpr (D * R == 8) {        // the L2-hint variant exists for the deep ring (the point used when the gathers go to DRAM)
+        if (p.hubcls && p.t->n < (1LL << 30))
+            return full ? launch_layout_f<Op, VW, R, D, MINB, true, true, true>(p) : launch_layout_f<Op, VW, R, D, MINB, false, true, true>(p);
+    }
+    return full ? launch_layout_f<Op, VW, R, D, MINB, true, true>(p) : launch_layout_f<Op, VW, R, D, MINB, false, true>(p);
 }
 
 // K2H / K2R: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks

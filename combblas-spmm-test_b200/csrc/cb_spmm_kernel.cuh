@@ -178,6 +178,10 @@ struct SpmmArgs {
     char* __restrict__ carry;     // [2*nchunks] slots of carry_stride bytes
     int64_t carry_stride;
     int accumulate;
+    // K2P with L2 residency hints: per nonzero, floor(log2(rank + 1)) of its column among the tile's columns by descending
+    // use (255 = used once); columns of class <= cls_max are gathered with evict_last, all others with evict_first
+    const uint8_t* __restrict__ hubcls;
+    int cls_max;
 };
 
 // One lane's share of a panel row: R vectors at byte offsets (vl + r*VW)*16.
@@ -196,6 +200,23 @@ __device__ __forceinline__ void st16_stream(void* p, const Vec16<T>& v) {
 }
 
 #ifndef CB_CLUSTER_INTRINSICS     // the CPU warp emulator (tests/emul) supplies host versions of these
+// L2 eviction priorities for the row gathers (createpolicy + ld.global.nc.L2::cache_hint): rows of the most used columns are
+// kept (evict_last) while rows that are used once or twice pass through (evict_first) instead of pushing them out
+__device__ __forceinline__ uint64_t cb_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t cb_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 cb_ldg16_hint(const void* ptr, uint64_t policy) {
+    uint4 u;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(ptr), "l"(policy));
+    return u;
+}
 // 16 bytes from shared memory of CTA `cta` of this cluster (distributed shared memory); addr is a shared-window address
 __device__ __forceinline__ uint4 cb_ld_cluster16(uint32_t addr, uint32_t cta) {
     uint32_t remote;
@@ -409,9 +430,14 @@ cb_spmm_kernel(const SpmmArgs a) {
 //     entries in range (straight-line fold / gather code), row ends but in range, and the general predicated one for the
 //     last steps of a chunk.
 // Fold order, row ends, split-row pieces and the accumulate mode are K2's, so every result bit is K2's.
-template <class Op, int VW, int R, int D, bool FULL>
+template <class Op, int VW, int R, int D, bool FULL, bool POL>
 __device__ __forceinline__ void cb_spmm_walk_pipe(const SpmmArgs& a, const int64_t chunk) {
     static_assert(D >= 1 && D <= VW && (VW % D) == 0, "ring depth must divide the virtual warp width");
+    // POL: bit 30 of an entry's column word says "row of a much used column" (set when the entry is loaded, from hubcls);
+    // it travels with the column through the shuffles and picks the L2 eviction priority of the gather (needs n < 2^30)
+    constexpr uint32_t COLMASK = POL ? 0x3fffffffu : 0x7fffffffu;
+    uint64_t pol_last = 0, pol_first = 0;
+    if (POL) { pol_last = cb_policy_evict_last(); pol_first = cb_policy_evict_first(); }
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     constexpr int EPL = 16 / sizeof(T);
@@ -489,18 +515,32 @@ __device__ __forceinline__ void cb_spmm_walk_pipe(const SpmmArgs& a, const int64
         ++ridx;
         if (more) row = a.nzrows[ridx];
     };
-    auto gather = [&](RowFrag<Op, R>& dst, const uint32_t c) {
-        const char* xr = xbase + (uint64_t)c * ldx;
+    auto gather = [&](RowFrag<Op, R>& dst, const uint32_t cw) {
+        const char* xr = xbase + (uint64_t)(cw & COLMASK) * ldx;
+        if (POL) {
+            const uint64_t pol = (cw & 0x40000000u) ? pol_last : pol_first;
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (lane_on[r]) dst.v[r] = ldg16<T>(xr + r * VW * 16);
+            for (int r = 0; r < R; ++r)
+                if (lane_on[r]) *reinterpret_cast<uint4*>(&dst.v[r]) = cb_ldg16_hint(xr + r * VW * 16, pol);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (lane_on[r]) dst.v[r] = ldg16<T>(xr + r * VW * 16);
+        }
+    };
+    // one entry of the nonzero stream: column | row-end flag (bit 31) | with POL: much-used-column mark (bit 30)
+    const uint8_t* const hcp = POL ? a.hubcls + s + vl : nullptr;
+    auto load_entry = [&](const int off) -> int {
+        int cf = ld_stream(cfp + off);
+        if (POL) cf |= ((int)__ldcs(hcp + off) <= a.cls_max) ? 0x40000000 : 0;
+        return cf;
     };
 
     // entries of this step and of the next one: lane vl holds nonzero base + vl of the chunk
     int cf_cur = 0, cf_nxt = 0;
     TA av_cur = TA(), av_nxt = TA();
-    if (vl < len) { cf_cur = ld_stream(cfp); if (HASVAL) av_cur = ld_stream_val<TA>(avp); }
-    if (VW + vl < len) { cf_nxt = ld_stream(cfp + VW); if (HASVAL) av_nxt = ld_stream_val<TA>(avp + VW); }
+    if (vl < len) { cf_cur = load_entry(0); if (HASVAL) av_cur = ld_stream_val<TA>(avp); }
+    if (VW + vl < len) { cf_nxt = load_entry(VW); if (HASVAL) av_nxt = ld_stream_val<TA>(avp + VW); }
 
     RowFrag<Op, R> x[D];
 #pragma unroll
@@ -552,7 +592,7 @@ __device__ __forceinline__ void cb_spmm_walk_pipe(const SpmmArgs& a, const int64
         cf_nxt = 0;
         av_nxt = TA();
         if (base + 2 * VW + vl < len) {
-            cf_nxt = ld_stream(cfp + base + 2 * VW);
+            cf_nxt = load_entry(base + 2 * VW);
             if (HASVAL) av_nxt = ld_stream_val<TA>(avp + base + 2 * VW);
         }
     }
@@ -565,12 +605,12 @@ __device__ __forceinline__ void cb_spmm_walk_pipe(const SpmmArgs& a, const int64
     }
 }
 
-template <class Op, int VW, int R, int D, int MINB, bool FULL>
+template <class Op, int VW, int R, int D, int MINB, bool FULL, bool POL = false>
 __global__ void __launch_bounds__(256, MINB)
 cb_spmm_pipe_kernel(const SpmmArgs a) {
     constexpr int NV = 32 / VW;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    cb_spmm_walk_pipe<Op, VW, R, D, FULL>(a, warp * NV + ((threadIdx.x & 31) / VW));
+    cb_spmm_walk_pipe<Op, VW, R, D, FULL, POL>(a, warp * NV + ((threadIdx.x & 31) / VW));
 }
 
 // Combine the pieces of split rows in chunk order: Y[row] = tail[c0] (+) head[c0+1] (+) ... (+) head[c1].

@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 #include "cb_common.cuh"
 #include "cb_hub.cuh"
+#include "cb_spgemm.cuh"
 
 // ------------------------------------------------------------------------------------------ NCCL, by hand
 namespace {
@@ -717,6 +718,106 @@ int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return CB_OK;
+}
+
+// ---- sparse x sparse on the grid (cb_spgemm.cu has the local kernels)
+}  // extern "C"
+namespace {
+// one tile travels from `root` to every rank of `comm`: its essentials first (GetSetSizes, SpParHelper.cpp:797-809), then the
+// slab as one message (BCastMatrix, :582-601).  The root passes its tile; the others get a view onto a fresh receive buffer.
+int bcast_tile(cb_ctx* ctx, ncclComm_t comm, int root, bool mine, const cb_tile* src, cb_tile* view, char** recvbuf) {
+    cb_scratch sc;
+    cb_tile_meta meta;
+    memset(&meta, 0, sizeof meta);
+    if (mine) meta = cb_tile_get_meta(src);
+    char* d_meta = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_meta, sizeof meta));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_meta, &meta, sizeof meta, cudaMemcpyHostToDevice, ctx->comm));
+    CB_NCCL(ctx, nccl().Broadcast(d_meta, d_meta, sizeof meta, ncclInt8, root, comm, ctx->comm));
+    CB_CUDA(ctx, cudaMemcpyAsync(&meta, d_meta, sizeof meta, cudaMemcpyDeviceToHost, ctx->comm));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+    const size_t bytes = cb_layout(meta).total;
+    char* buf = mine ? src->slab : nullptr;
+    *recvbuf = nullptr;
+    if (!mine) {
+        cudaError_t e = cudaMalloc((void**)recvbuf, bytes);
+        if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for a received tile: %s", bytes, cudaGetErrorString(e));
+        buf = *recvbuf;
+    }
+    CB_NCCL(ctx, nccl().Broadcast(buf, buf, bytes, ncclInt8, root, comm, ctx->comm));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->comm));
+    if (!mine) { view->ctx = ctx; view->owns_slab = false; cb_tile_bind(view, meta, buf); }
+    return CB_OK;
+}
+}  // namespace
+extern "C" {
+
+// C = A (x).(+) B for a SPARSE right-hand side, collective over the grid: the stage loop of Mult_AnXBn_Synch
+// (ParFriends.h:1036-1083) with the tile pair of every stage multiplied on the GPU by expansion, and one sort + merge of all
+// stages' partial products at the end (the role of MultiwayMerge, :1096).  A: rows of block-row myprocrow x columns of
+// block-column myproccol of gn.  B: rows of block-row myprocrow of gn x columns of block myproccol of gk, values already of
+// the product's type `dtype` (or a pattern).  C: this rank's block of the product as merged triples, column-major, local indices.
+int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semiring, int dtype, int64_t gm, int64_t gn, int64_t gk, cb_coo** C) {
+    if (!ctx || !A || !B || !C) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spgemm_summa: null argument");
+    const int pr = ctx->pr, pc = ctx->pc;
+    int64_t r0, rl, c0, cl, x0, xl, k0, kl;
+    block_range(gm, pr, ctx->myprocrow, &r0, &rl);
+    block_range(gn, pc, ctx->myproccol, &c0, &cl);
+    block_range(gn, pr, ctx->myprocrow, &x0, &xl);
+    block_range(gk, pc, ctx->myproccol, &k0, &kl);
+    if (A->m != rl || A->n != cl || B->m != xl || B->n != kl)
+        return cb_fail(ctx, CB_ERR_DIMMISMATCH, "cb_spgemm_summa rank %d: local A %lldx%lld (want %lldx%lld), local B %lldx%lld (want %lldx%lld)", ctx->rank,
+                       (long long)A->m, (long long)A->n, (long long)rl, (long long)cl, (long long)B->m, (long long)B->n, (long long)xl, (long long)kl);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nranks == 1) return cb_spgemm_local(ctx, A, B, semiring, dtype, C);
+    std::vector<int64_t> seg(pr + pc + 1, 0);
+    std::vector<int> a_root(pr + pc, 0), x_root(pr + pc, 0);
+    int ns = 0;
+    cb_summa_plan(pr, pc, gn, seg.data(), a_root.data(), x_root.data(), &ns);
+    // my parts of A, one column slice per stage this rank roots: the cache of the dense stage loop (same key)
+    cb_tile* mt = const_cast<cb_tile*>(A);
+    const int64_t key[3] = {(int64_t)pr * 1000 + pc, gn, ns};
+    if (mt->summa_key[0] != key[0] || mt->summa_key[1] != key[1] || mt->summa_key[2] != key[2]) {
+        for (cb_tile* p : mt->summa_parts) cb_tile_free(p);
+        for (cb_tile* p : mt->summa_remote) cb_tile_free(p);
+        mt->summa_remote.clear();
+        for (cb_tile* p : mt->summa_merged) cb_tile_free(p);
+        mt->summa_merged.clear();
+        mt->summa_parts.assign(ns, nullptr);
+        for (int s = 0; s < ns; ++s) {
+            if (a_root[s] != ctx->myproccol) continue;
+            const int64_t a = seg[s] - c0, b = seg[s + 1] - c0;
+            if (a == 0 && b == cl) continue;
+            CB_TRY(slice_cols(ctx, A, a, b, &mt->summa_parts[s]));
+        }
+        mt->summa_key[0] = key[0]; mt->summa_key[1] = key[1]; mt->summa_key[2] = key[2];
+        if (ctx->summa_state) ((SummaState*)ctx->summa_state)->meta_tile = nullptr;
+    }
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    cb_spgemm_acc acc;
+    int status = CB_OK;
+    for (int r = 0; r < pr && status == CB_OK; ++r) {
+        int64_t b0, bl;
+        block_range(gn, pr, r, &b0, &bl);
+        cb_tile bview;
+        char* brecv = nullptr;
+        const bool b_mine = r == ctx->myprocrow;
+        status = pr > 1 ? bcast_tile(ctx, (ncclComm_t)ctx->nccl_col, r, b_mine, B, &bview, &brecv) : CB_OK;
+        const cb_tile* bt = b_mine ? B : &bview;
+        for (int s = 0; s < ns && status == CB_OK; ++s) {
+            if (x_root[s] != r || seg[s + 1] <= seg[s]) continue;
+            cb_tile aview;
+            char* arecv = nullptr;
+            const bool a_mine = a_root[s] == ctx->myproccol;
+            const cb_tile* mypart = a_mine ? (mt->summa_parts[s] ? mt->summa_parts[s] : A) : nullptr;
+            if (pc > 1) status = bcast_tile(ctx, (ncclComm_t)ctx->nccl_row, a_root[s], a_mine, mypart, &aview, &arecv);
+            if (status == CB_OK) status = cb_spgemm_expand(ctx, a_mine ? mypart : &aview, bt, seg[s] - b0, semiring, dtype, &acc);
+            cudaFree(arecv);
+        }
+        cudaFree(brecv);
+    }
+    if (status != CB_OK) { cb_spgemm_acc_release(&acc); return status; }
+    return cb_spgemm_finish(ctx, &acc, semiring, dtype, rl, kl, C);
 }
 
 // byte allgather over the processor column with host buffers (set-up traffic of the peer transport)

@@ -151,8 +151,66 @@ bool CheckSpGEMMCompliance(const SpParMat<IU, NU1, UDERA>& A, const SpParMat<IU,
     return true;
 }
 
+// The product on the device (cb_spgemm_summa, csrc/cb_spgemm.cu): per stage the tile pair is multiplied by expansion, all
+// stages' partial products are merged by one stable sort + reduce-by-key - the device counterpart of LocalHybridSpGEMM
+// (mtSpGEMM.h:213-460) + MultiwayMerge (MultiwayMerge.h:411-526).  Cost is what the product touches; an entry of C exists
+// exactly where the reference creates one; products are folded in ascending inner index (mtSpGEMM.h:395-423).
+// CB_SPGEMM_DENSE=1 selects the round-1 lowering onto dense panels instead (Mult_AnXBn_DensePanels below).
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_DensePanels(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false);
+
 template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
 SpParMat<IU, NUO, UDERO> Mult_AnXBn_Synch(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA = false, bool clearB = false) {
+    typedef typename promote_trait<NU1, NU2>::T_promote T_promote;
+    static_assert(semiring_traits<SR>::supported, "this semiring / type combination is not implemented by the B200 engine");
+    static_assert(std::is_same<T_promote, NUO>::value, "the output value type must be the promoted type of the operands");
+    static const bool dense_panels = std::getenv("CB_SPGEMM_DENSE") && std::atoi(std::getenv("CB_SPGEMM_DENSE")) != 0;
+    if (dense_panels) return Mult_AnXBn_DensePanels<SR, NUO, UDERO>(A, B, clearA, clearB);
+    typedef typename UDERB::LocalIT LIT;
+    typedef typename UDERO::LocalIT OIT;
+    typedef typename cb_storage<T_promote>::type ST;
+    if (!CheckSpGEMMCompliance(A, B)) return SpParMat<IU, NUO, UDERO>();
+    int stages, dummy;
+    std::shared_ptr<CommGrid> grid = ProductGrid(A.getcommgrid().get(), B.getcommgrid().get(), stages, dummy, dummy);
+    cb_ctx* ctx = grid->GetContext();
+    const IU gm = A.getnrow(), gn = A.getncol(), gk = B.getncol();
+    const int dt = cb_dtype_of<T_promote>::value;
+    // B on the device with values of the product's type: its own resident tile when the types agree, a converted copy otherwise
+    cb_tile* tileB = nullptr;
+    bool own_b = false;
+    if (std::is_same<NU2, T_promote>::value) {
+        tileB = B.DeviceTile();
+    } else {
+        const UDERB& bt = B.seq();
+        SpTuples<LIT, NU2> t = TilesToTuples(bt);
+        const int64_t nz = t.getnnz();
+        std::vector<int64_t> rows((size_t)nz), cols((size_t)nz);
+        std::vector<ST> vals((size_t)nz);
+        for (int64_t p = 0; p < nz; ++p) { rows[(size_t)p] = t.rowindex(p); cols[(size_t)p] = t.colindex(p); vals[(size_t)p] = (ST)(T_promote)t.numvalue(p); }
+        cb_check(cb_tile_upload_coo(ctx, bt.getnrow(), bt.getncol(), nz, rows.data(), cols.data(), vals.data(), CB_I64, dt, &tileB), ctx, "cb_tile_upload_coo");
+        own_b = true;
+    }
+    cb_coo* C = nullptr;
+    cb_check(cb_spgemm_summa(ctx, A.DeviceTile(), tileB, semiring_traits<SR>::op, dt, gm, gn, gk, &C), ctx, "cb_spgemm_summa");
+    int64_t nnzc = 0, lm = 0, kl = 0;
+    cb_check(cb_coo_info(C, &nnzc, &lm, &kl, nullptr), ctx, "cb_coo_info");
+    std::vector<int64_t> ci((size_t)nnzc), cj((size_t)nnzc);
+    std::vector<ST> cv((size_t)nnzc);
+    cb_check(cb_coo_download(C, ci.data(), cj.data(), cv.data()), ctx, "cb_coo_download");
+    cb_coo_free(C);
+    if (own_b) cb_tile_free(tileB);
+    // already sorted by column, then row: the order of every SpTuples the reference's local multiply returns
+    SpTuples<OIT, NUO> ct(0, (OIT)lm, (OIT)kl);
+    ct.tuples.reserve((size_t)nnzc);
+    for (int64_t p = 0; p < nnzc; ++p) ct.tuples.emplace_back((OIT)ci[(size_t)p], (OIT)cj[(size_t)p], (NUO)cv[(size_t)p]);
+    if (clearA) A.FreeDeviceTile();
+    if (clearB) B.FreeDeviceTile();
+    return SpParMat<IU, NUO, UDERO>(new UDERO(ct, false), grid, gm, gk);
+}
+
+// Round-1 formulation, kept for comparison (CB_SPGEMM_DENSE=1): lowered onto the dense engine.
+template <typename SR, typename NUO, typename UDERO, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB>
+SpParMat<IU, NUO, UDERO> Mult_AnXBn_DensePanels(SpParMat<IU, NU1, UDERA>& A, SpParMat<IU, NU2, UDERB>& B, bool clearA, bool clearB) {
     typedef typename promote_trait<NU1, NU2>::T_promote T_promote;
     static_assert(semiring_traits<SR>::supported, "this semiring / type combination is not implemented by the B200 engine");
     static_assert(std::is_same<T_promote, NUO>::value, "the output value type must be the promoted type of the operands");

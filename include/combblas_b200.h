@@ -34,6 +34,7 @@ extern "C" {
 typedef struct cb_ctx cb_ctx;     /* device + streams + (optional) pr x pc process grid */
 typedef struct cb_tile cb_tile;   /* device-resident local sparse tile (doubly compressed rows) */
 typedef struct cb_dense cb_dense; /* device-resident dense panel, row-major */
+typedef struct cb_coo cb_coo;     /* device-resident result of a sparse x sparse product: merged triples, column-major */
 
 /* element types.  CB_U8 carries C++ bool (one byte, 0/1).  CB_PATTERN as a tile value type means
  * "no value array, every stored entry is true/1" (what SpDCCols<IT,bool> holds after a pattern read). */
@@ -194,6 +195,25 @@ int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t l
 int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int semiring,
                        int64_t gm, int64_t gn, int64_t gk, int dtype);
 
+/* ------------------------------------------------------------------ sparse x SPARSE (tall-skinny right-hand side)
+ * The literal Mult_AnXBn_Synch<SR,NUO,UDERO>(A, B) / PSpGEMM<SR>(A, B) of the reference (include/CombBLAS/ParFriends.h:1004-1108,
+ * SpParMat.h:454-467) - the call of Applications/SpMMError.cpp:83 and Applications/BetwCent.cpp:185,204 - on the device.
+ * Replaces LocalHybridSpGEMM's per-column hash / heap accumulator (mtSpGEMM.h:213-460) and MultiwayMerge
+ * (MultiwayMerge.h:411-526) by expand - stable sort - reduce-by-key (csrc/cb_spgemm.cu): cost is what the product touches, the
+ * products of one output entry are folded in ascending inner index like the reference's hash branch (mtSpGEMM.h:395-423), and an
+ * entry exists exactly where the reference creates one.
+ *   B     : a tile (cb_tile_upload_csc / _coo) whose values already have the product's type `dtype` (promote_trait), or a pattern
+ *   dtype : element type of the product; A's values must be of that type, CB_U8 (bool) or a pattern
+ * cb_spgemm_local multiplies two tiles on this GPU; cb_spgemm_summa is the stage loop over the ctx's grid (any pr x pc): per
+ * stage the owner's A part travels along the processor row and the owner's B tile along the processor column as one message
+ * each, the partial products of all stages are merged once at the end.  The result is this rank's block of C as triples with
+ * local indices, sorted by column then row - the order SpDCCols' tuple constructor wants (SpDCCols.cpp:186-195). */
+int cb_spgemm_local(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semiring, int dtype, cb_coo** C);
+int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semiring, int dtype, int64_t gm, int64_t gn, int64_t gk, cb_coo** C);
+int cb_coo_info(const cb_coo* c, int64_t* nnz, int64_t* m, int64_t* k, int* dtype);
+int cb_coo_download(cb_coo* c, int64_t* rows, int64_t* cols, void* vals);        /* any pointer may be NULL */
+int cb_coo_free(cb_coo* c);
+
 /* Hub variant of the local multiply (K2H, csrc/cb_spmm_hub_kernel.cuh) - OPT-IN, off by default.
  * For tiles whose columns are very unevenly used (R-MAT / power-law inputs) the panel rows of the most frequent columns
  * are kept in the shared memory of thread-block clusters for the whole multiply, so that share of the row gathers no
@@ -219,6 +239,10 @@ int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point);
 /* Ring depth of the pipelined local multiply (K2P, csrc/cb_spmm_kernel.cuh): every lane keeps `depth` row gathers in flight
  * in a register ring; 4 or 8, 0 = the round-1 walk (gathers in groups), -1 = the build's default.  Results are identical. */
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth);
+/* L2 residency hints of K2P for tiles whose X rows do not fit in L2: the rows of the tile's most used columns - as many as
+ * fit `budget_mb` megabytes at the current row width - are gathered with the evict_last priority, every other row with
+ * evict_first, so rows that are used once no longer push the shared ones out.  0 = off, -1 = the build's default. */
+int cb_spmm_k2_l2(cb_ctx* ctx, int budget_mb);
 /* The hub selection rule as pure host arithmetic (no device needed): the max_hubs most frequent columns with at least
  * two nonzeros, most frequent first, ties by ascending column; cum[r] = nonzeros in the columns of rank <= r.
  * Returns the number of hubs written, or -1 on bad arguments. */

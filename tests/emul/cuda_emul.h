@@ -77,6 +77,13 @@ using std::min;
 // ---- shared memory, __syncthreads, clusters and distributed shared memory (the hub variant of K2) ----
 // A "shared-window address" is an offset into the owning CTA's dynamic shared memory buffer.
 #define CB_CLUSTER_INTRINSICS
+// L2 eviction-priority hints of K2P: no cache on the host, the policy only has to travel
+inline uint64_t cb_policy_evict_last() { return 0x1111; }
+inline uint64_t cb_policy_evict_first() { return 0x2222; }
+inline uint4 cb_ldg16_hint(const void* p, uint64_t policy) {
+    if (policy != 0x1111 && policy != 0x2222) __builtin_trap();
+    return *reinterpret_cast<const uint4*>(p);
+}
 namespace emul {
 struct Cta {
     pthread_barrier_t bar;                    // __syncthreads

@@ -115,7 +115,20 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         Y = Ysave;
         a.Y = (char*)Y.data();
         std::fill(carry.begin(), carry.end(), (char)0x77);
-        if constexpr (U <= VW) syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_pipe_kernel<Op, VW, R, U, 3, FULL>(a); });
+        std::vector<uint8_t> hubcls;
+        if (pipe == 2) {     // with L2 residency hints: per-nonzero use class of its column (cb_hub.cu), classes <= 2 marked
+            std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
+            for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
+            for (int64_t c = 0; c < n; ++c) order[c] = (int32_t)c;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cnt[x] > cnt[y]; });
+            std::vector<uint8_t> cls_of((size_t)n, 255);
+            for (int64_t r = 0; r < n; ++r) if (cnt[order[r]] >= 2) cls_of[order[r]] = (uint8_t)(63 - __builtin_clzll((unsigned long long)(r + 1)));
+            hubcls.resize((size_t)t.nnz);                                  // exactly nnz bytes: a read past the chunk is an ASan report
+            for (int64_t p = 0; p < t.nnz; ++p) hubcls[p] = cls_of[t.colflag[p] & 0x7fffffff];
+            a.hubcls = hubcls.data();
+            a.cls_max = 2;
+            if constexpr (U <= VW) syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_pipe_kernel<Op, VW, R, U, 3, FULL, true>(a); });
+        } else if constexpr (U <= VW) syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_pipe_kernel<Op, VW, R, U, 3, FULL>(a); });
     } else if (hub_cs > 0) {
         // plain K2 on a copy first: K2H must reproduce it bit for bit (same walk, same fold order)
         std::vector<T> Ysave = Y;
@@ -226,6 +239,10 @@ int main(int argc, char** argv) {
     bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("pipe minplus_i64 larger acc D8", 300, 500, 32, 64, 400, 62 + sd, true, 0, 0, 0, 1);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 63 + sd, false, 0, 0, 0, 1);
     bad += run_case<PlusTimes<float, A_BOOL>, 8, 1, 8, true>("pipe pt_f32 boolA VW8 L=40 D8", 200, 300, 32, 40, 170, 64 + sd, true, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe+l2 pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 65 + sd, false, 0, 0, 0, 2);
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, false>("pipe+l2 pt_f64 R2 ragged acc", 30, 80, 100, 32, 70, 66 + sd, true, 0, 0, 0, 2);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("pipe+l2 minplus_i32 VW8 D8", 70, 64, 32, 32, 60, 67 + sd, false, 0, 0, 0, 2);
+    bad += run_case<OrAnd<A_PATTERN>, 16, 1, 8, false>("pipe+l2 or_and VW16 D8", 90, 70, 50, 64, 60, 68 + sd, false, 0, 0, 0, 2);
     // K2H, the hub variant: persistent CTAs, dynamic chunks, hub rows in the shared memory of a 1/2/4-CTA cluster
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs1", 61, 97, 64, 32, 150, 21 + sd, false, 1, 20);
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 8, true>("hub pt_f32 VW16 cs2 acc", 61, 97, 64, 32, 150, 22 + sd, true, 2, 33);

@@ -76,6 +76,7 @@ struct cb_tile {
     bool view = false;
 };
 struct cb_dense { int64_t rows = 0, cols = 0; int dtype = CB_F32; std::vector<unsigned char> data; };
+struct cb_coo { int64_t m = 0, k = 0; int dtype = CB_F32; std::vector<int64_t> rows, cols; std::vector<unsigned char> vals; };
 
 static std::string g_err;
 static size_t esize(int dt) { return dt == CB_F32 || dt == CB_I32 ? 4 : dt == CB_F64 || dt == CB_I64 ? 8 : dt == CB_U8 ? 1 : 0; }
@@ -207,6 +208,22 @@ int cb_tile_upload_csc(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, int64_t nz
             trip.push_back({{idx(ir, p), jc ? idx(jc, c) : c}, v});
         }
     if ((int64_t)trip.size() != nz) { delete t; return fail(ctx, CB_ERR_INVALIDPARAMS, "mock ABI: nz does not match the column pointers"); }
+    build_csr(t, trip);
+    *tile = t;
+    return CB_OK;
+}
+int cb_tile_upload_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const void* rows, const void* cols, const void* vals, int idt, int vdt, cb_tile** tile) {
+    auto idx = [&](const void* a, int64_t i) { return idt == CB_I32 ? (int64_t)((const int32_t*)a)[i] : ((const int64_t*)a)[i]; };
+    cb_tile* t = new cb_tile();
+    t->m = m; t->n = n; t->val_dtype = vdt;
+    const size_t es = esize(vdt == CB_PATTERN ? CB_U8 : vdt);
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    for (int64_t p = 0; p < nz; ++p) {
+        if (idx(rows, p) < 0 || idx(rows, p) >= m || idx(cols, p) < 0 || idx(cols, p) >= n) { delete t; return fail(ctx, CB_ERR_INVALIDPARAMS, "mock ABI: index outside the tile"); }
+        std::vector<unsigned char> v;
+        if (vdt != CB_PATTERN) v.assign((const unsigned char*)vals + (size_t)p * es, (const unsigned char*)vals + (size_t)(p + 1) * es);
+        trip.push_back({{idx(rows, p), idx(cols, p)}, v});
+    }
     build_csr(t, trip);
     *tile = t;
     return CB_OK;
@@ -361,6 +378,115 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* t, const cb_dense* X, cb_dense* Y,
     build_csr(&arow, trip);
     return cb_spmm_local(ctx, &arow, &xcol, Y, sr, 0);
 }
+}  // extern "C"
+// sparse x sparse: C(i,j) = (+)_kk A(i,kk) (x) B(kk,j), products folded in ascending kk, first product stored; column-major result
+template <class T>
+static void spgemm_typed(const cb_tile* A, const cb_tile* B, int sr, cb_coo* C) {
+    std::map<std::pair<int64_t, int64_t>, T> acc;            // (column, row) -> value: iteration order is column-major
+    const bool same = A->val_dtype == C->dtype && !(A->val_dtype == CB_U8 && C->dtype != CB_U8);
+    for (int64_t i = 0; i < A->m; ++i)
+        for (int64_t p = A->rowptr[(size_t)i]; p < A->rowptr[(size_t)i + 1]; ++p) {
+            const int64_t kk = A->col[(size_t)p];
+            T a = T();
+            bool a_true = true;
+            if (same) std::memcpy(&a, A->vals.data() + (size_t)p * sizeof(T), sizeof(T));
+            else if (A->val_dtype == CB_U8) a_true = A->vals[(size_t)p] != 0;
+            if (sr == CB_OR_AND && same) a_true = a != 0;
+            for (int64_t q = B->rowptr[(size_t)kk]; q < B->rowptr[(size_t)kk + 1]; ++q) {
+                T b = (T)1;
+                if (B->val_dtype != CB_PATTERN) std::memcpy(&b, B->vals.data() + (size_t)q * sizeof(T), sizeof(T));
+                const T prod = sr_mul<T>(sr, same, a, a_true, b);
+                auto it = acc.find({B->col[(size_t)q], i});
+                if (it == acc.end()) acc[{B->col[(size_t)q], i}] = prod;
+                else it->second = sr_add<T>(sr, prod, it->second);
+            }
+        }
+    for (auto& kv : acc) {
+        C->cols.push_back(kv.first.first);
+        C->rows.push_back(kv.first.second);
+        const unsigned char* v = (const unsigned char*)&kv.second;
+        C->vals.insert(C->vals.end(), v, v + sizeof(T));
+    }
+}
+extern "C" {
+int cb_spgemm_local(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int sr, int dtype, cb_coo** out) {
+    if (A->n != B->m) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: spgemm dimension mismatch");
+    if (B->val_dtype != dtype && B->val_dtype != CB_PATTERN) return fail(ctx, CB_ERR_UNSUPPORTED, "mock ABI: B must hold the product's type");
+    if (sr == CB_PLUS_TIMES && dtype == CB_U8) sr = CB_OR_AND;
+    ++ctx->launches;
+    cb_coo* C = new cb_coo();
+    C->m = A->m; C->k = B->n; C->dtype = dtype;
+    switch (dtype) {
+        case CB_F32: spgemm_typed<float>(A, B, sr, C); break;
+        case CB_F64: spgemm_typed<double>(A, B, sr, C); break;
+        case CB_I32: spgemm_typed<int32_t>(A, B, sr, C); break;
+        case CB_I64: spgemm_typed<int64_t>(A, B, sr, C); break;
+        case CB_U8: spgemm_typed<uint8_t>(A, B, sr, C); break;
+        default: delete C; return fail(ctx, CB_ERR_UNSUPPORTED, "mock ABI: dtype");
+    }
+    *out = C;
+    return CB_OK;
+}
+// a tile's triples in global coordinates, appended to a byte string / read back
+static void pack_tile(std::vector<unsigned char>& b, const cb_tile* t, int64_t r0, int64_t c0) {
+    put<int64_t>(b, (int64_t)t->col.size());
+    put<int64_t>(b, (int64_t)t->val_dtype);
+    for (int64_t r = 0; r < t->m; ++r)
+        for (int64_t p = t->rowptr[(size_t)r]; p < t->rowptr[(size_t)r + 1]; ++p) { put<int64_t>(b, r0 + r); put<int64_t>(b, c0 + t->col[(size_t)p]); }
+    b.insert(b.end(), t->vals.begin(), t->vals.end());
+}
+typedef std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> Trips;
+static void unpack_tile(const std::vector<unsigned char>& b, size_t& off, bool keep, int64_t roff, int64_t coff, Trips& trip) {
+    const int64_t nz = take<int64_t>(b, off);
+    const int vdt = (int)take<int64_t>(b, off);
+    const size_t ves = vdt == CB_PATTERN ? 0 : esize(vdt);
+    std::vector<std::pair<int64_t, int64_t>> rc((size_t)nz);
+    for (int64_t p = 0; p < nz; ++p) { rc[(size_t)p].first = take<int64_t>(b, off); rc[(size_t)p].second = take<int64_t>(b, off); }
+    for (int64_t p = 0; p < nz; ++p) {
+        std::vector<unsigned char> v(b.begin() + off, b.begin() + off + ves);
+        off += ves;
+        if (keep) trip.push_back({{rc[(size_t)p].first - roff, rc[(size_t)p].second - coff}, v});
+    }
+}
+int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int sr, int dtype, int64_t gm, int64_t gn, int64_t gk, cb_coo** out) {
+    if (ctx->nranks == 1) return cb_spgemm_local(ctx, A, B, sr, dtype, out);
+    const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;
+    int64_t r0, rl, c0, cl, x0, xl, k0, kl;
+    block_range(gm, pr, myrow, &r0, &rl); block_range(gn, pc, mycol, &c0, &cl);
+    block_range(gn, pr, myrow, &x0, &xl); block_range(gk, pc, mycol, &k0, &kl);
+    if (A->m != rl || A->n != cl || B->m != xl || B->n != kl) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: spgemm summa block mismatch");
+    std::vector<unsigned char> mine;
+    pack_tile(mine, A, r0, c0);
+    pack_tile(mine, B, x0, k0);
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(ctx, mine, all);
+    cb_tile arow, bcol;             // block-row myrow of A (all columns); all rows of B, block-column mycol
+    arow.m = rl; arow.n = gn; arow.val_dtype = A->val_dtype;
+    bcol.m = gn; bcol.n = kl; bcol.val_dtype = B->val_dtype;
+    Trips ta, tb;
+    for (int q = 0; q < ctx->nranks; ++q) {
+        size_t off = 0;
+        unpack_tile(all[(size_t)q], off, q / pc == myrow, r0, 0, ta);
+        unpack_tile(all[(size_t)q], off, q % pc == mycol, 0, k0, tb);
+    }
+    build_csr(&arow, ta);
+    build_csr(&bcol, tb);
+    return cb_spgemm_local(ctx, &arow, &bcol, sr, dtype, out);
+}
+int cb_coo_info(const cb_coo* c, int64_t* nnz, int64_t* m, int64_t* k, int* dtype) {
+    if (nnz) *nnz = (int64_t)c->rows.size();
+    if (m) *m = c->m;
+    if (k) *k = c->k;
+    if (dtype) *dtype = c->dtype;
+    return CB_OK;
+}
+int cb_coo_download(cb_coo* c, int64_t* rows, int64_t* cols, void* vals) {
+    if (rows) std::copy(c->rows.begin(), c->rows.end(), rows);
+    if (cols) std::copy(c->cols.begin(), c->cols.end(), cols);
+    if (vals && !c->vals.empty()) std::memcpy(vals, c->vals.data(), c->vals.size());
+    return CB_OK;
+}
+int cb_coo_free(cb_coo* c) { delete c; return CB_OK; }
 int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int sr,
                        int64_t gm, int64_t gn, int64_t gk, int dtype) {
     const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;

@@ -91,6 +91,17 @@ def main():
             for _ in range(4):                                  # later calls run on the cached, merged block-row (both buffer parities)
                 ctx.spmm_summa(tile, Xd, Yd, sr, m, n, k)
             Yl = Yd.download() if kl else np.zeros((rl, 0), xdt)
+            # the host-panel entry (cb_spmm_summa_host: column slabs through H2D / stage loop / D2H) must give the same bits
+            Yh = np.empty((rl, kl), Xl.dtype)
+            ctx.spmm_summa_host(tile, Xl, Yh, sr, m, n, k)
+            host_same = bool(np.array_equal(Yh, Yl))
+            # sparse right-hand side (cb_spgemm_summa): keep about one entry of X in seven; this rank's block of C as triples
+            keepB = (O.hash_values(np.arange(n * k, dtype=np.uint64), 77, np.int32).reshape(n, k) % 7) == 0
+            Bl_i, Bl_j = np.nonzero(keepB[x0:x0 + xl, k0:k0 + kl])
+            Bl_v = Xl[Bl_i, Bl_j] if kl else np.zeros(0, Xl.dtype)
+            Bt = ctx.tile_from_coo(xl, kl, Bl_i.astype(np.int64), Bl_j.astype(np.int64), Bl_v)
+            sp_i, sp_j, sp_v = ctx.spgemm_summa(tile, Bt, sr, Xl.dtype, m, n, k)
+            Bt.free()
             for h in (tile, Xd, Yd):
                 h.free()
         else:
@@ -117,6 +128,29 @@ def main():
                 Yl = np.zeros((rl, kl), xdt)
         gathered = [None] * world if rank == 0 else None
         dist.gather_object((r0, k0, Yl), gathered, dst=0)
+        if a.mode == "gpu":
+            extra = [None] * world if rank == 0 else None
+            dist.gather_object((host_same, sp_i + r0, sp_j + k0, sp_v), extra, dst=0)
+            if rank == 0:
+                from tests.test_spgemm_gpu import host_spgemm
+                keepB = (O.hash_values(np.arange(n * k, dtype=np.uint64), 77, np.int32).reshape(n, k) % 7) == 0
+                BI, BJ = np.nonzero(keepB)
+                BV = X[BI, BJ]
+                Vh = None if V is None else V
+                ri, rj, rv = host_spgemm(sr, m, I, J, Vh, BI.astype(np.int64), BJ.astype(np.int64), BV, X.dtype.type)
+                gi = np.concatenate([e[1] for e in extra]); gj = np.concatenate([e[2] for e in extra]); gv = np.concatenate([e[3] for e in extra])
+                o = np.lexsort((gi, gj))
+                gi, gj, gv = gi[o], gj[o], gv[o]
+                sp_ok = bool(np.array_equal(gi, ri) and np.array_equal(gj, rj))
+                if sp_ok:
+                    if np.issubdtype(rv.dtype, np.floating):
+                        tolv = 1e-5 if rv.dtype == np.float32 else 1e-12
+                        sp_ok = bool((np.abs(gv - rv) <= tolv * np.abs(rv)).all())
+                    else:
+                        sp_ok = bool(np.array_equal(gv, rv))
+                hp_ok = all(e[0] for e in extra)
+                print(f"[summa {a.mode} {pr}x{pc}] {case} host-panel path: {'same bits' if hp_ok else 'DIFFERENT'}; sparse rhs ({len(ri)} entries): {'matches' if sp_ok else 'WRONG'}", flush=True)
+                failures += 0 if (hp_ok and sp_ok) else 1
         if rank == 0:
             Y = np.zeros((m, k), X.dtype if X.dtype != np.bool_ else np.uint8)
             for (rr, kk, y) in gathered:

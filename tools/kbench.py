@@ -41,12 +41,12 @@ for name in a.workloads:
     ref_sum = None
     for v in a.variants:
         kind, o = parse(v)
-        ctx.k2_config(0, -1); ctx.hub_config(0); ctx.ring_config(0); ctx.k2_pipe(0)
+        ctx.k2_config(0, -1); ctx.hub_config(0); ctx.ring_config(0); ctx.k2_pipe(0); ctx.k2_l2(0)
         try:
             if kind == "k2":
                 ctx.k2_config(o.get("slab", 0), o.get("point", -1))
             elif kind == "pipe":
-                ctx.k2_config(o.get("slab", 0), -1); ctx.k2_pipe(o.get("d", 4))
+                ctx.k2_config(o.get("slab", 0), -1); ctx.k2_pipe(o.get("d", 4)); ctx.k2_l2(o.get("l2", 0))
             elif kind == "hub":
                 ctx.hub_config(1, o.get("c", 4), o.get("slab", 0)); ctx.ring_config(o.get("ring", 0))
             elif kind == "ring":
@@ -76,6 +76,6 @@ for name in a.workloads:
                               fix_ms=round(pm["fixup"] / max(pn["fixup"], 1), 4), tflops=round(2 * t.nnz * k / ms / 1e9, 2),
                               alg_gbs=round(b / k2 / 1e6, 1), frac=round(b / k2 / 1e6 / 6542.1, 4), gather_tbs=round(g / k2 / 1e9, 2),
                               chunks=t.nchunks, split=t.nsplit, hub=t.hub_info(), same_as_first=same)), flush=True)
-    ctx.k2_config(0, -1); ctx.hub_config(0); ctx.ring_config(0); ctx.k2_pipe(-1)
+    ctx.k2_config(0, -1); ctx.hub_config(0); ctx.ring_config(0); ctx.k2_pipe(-1); ctx.k2_l2(-1)
     for h in (t, X, Y): h.free()
 ctx.close()
