@@ -48,7 +48,7 @@ struct LaunchParams {
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
-template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PIPE = false, bool POL = false>
+template <class Op, int VW, int R, int U, int MINB, bool FULL, int PIPE = 0, bool POL = false>      // PIPE: 0 K2, 1 K2P (ring), 2 K2 with prefetch
 static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -75,7 +75,8 @@ static int launch_layout_f(const LaunchParams& p) {
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
     {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
-        if constexpr (PIPE) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL, POL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
+        if constexpr (PIPE == 1) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL, POL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
+        else if constexpr (PIPE == 2) cb_spmm_kernel<Op, VW, R, U, MINB, FULL, true><<<grid, 256, 0, p.stream>>>(a);
         else cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
@@ -93,11 +94,19 @@ static int launch_layout(const LaunchParams& p) {
 template <class Op, int VW, int R, int D, int MINB>
 static int launch_pipe(const LaunchParams& p) {
     const bool full = p.total_row_bytes % (VW * R * 16) == 0;
+#ifdef CB_BUILD_L2HINT                 // measured in round 2 (profiles/r02_sweep_b_k2p_l2hints.jsonl): -9 % DRAM traffic, +24 % instructions, slower
     if constexpr (D * R == 8) {        // the L2-hint variant exists for the deep ring (the point used when the gathers go to DRAM)
         if (p.hubcls && p.t->n < (1LL << 30))
-            return full ? launch_layout_f<Op, VW, R, D, MINB, true, true, true>(p) : launch_layout_f<Op, VW, R, D, MINB, false, true, true>(p);
+            return full ? launch_layout_f<Op, VW, R, D, MINB, true, 1, true>(p) : launch_layout_f<Op, VW, R, D, MINB, false, 1, true>(p);
     }
-    return full ? launch_layout_f<Op, VW, R, D, MINB, true, true>(p) : launch_layout_f<Op, VW, R, D, MINB, false, true>(p);
+#endif
+    return full ? launch_layout_f<Op, VW, R, D, MINB, true, 1>(p) : launch_layout_f<Op, VW, R, D, MINB, false, 1>(p);
+}
+// K2 with the entry prefetch
+template <class Op, int VW, int R, int U, int MINB>
+static int launch_pf(const LaunchParams& p) {
+    if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true, 2>(p);
+    return launch_layout_f<Op, VW, R, U, MINB, false, 2>(p);
 }
 
 // K2H / K2R: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
@@ -205,7 +214,15 @@ static int launch_op(const LaunchParams& p) {
             static const int pipe_env = getenv("CB_K2_PIPE") ? atoi(getenv("CB_K2_PIPE")) : -1;
             const int pipe = p.pipe >= 0 ? p.pipe : (pipe_env >= 0 ? pipe_env : CB_PIPE_DEFAULT);
             constexpr bool W64 = sizeof(typename Op::T) == 8;
-            if (pipe == 4 && nvec > 4) {
+            (void)W64;
+            if (pipe == 1 && nvec > 4) {
+                if (nvec <= 8) s = wide ? launch_pf<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 8, 1, CB_DEEP_U, DB>(p);
+                else if (nvec <= 16) s = wide ? launch_pf<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 16, 1, CB_DEEP_U, DB>(p);
+                else if (nvec <= 32) s = wide ? launch_pf<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 32, 1, CB_DEEP_U, DB>(p);
+                else s = launch_pf<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
+            }
+#ifdef CB_BUILD_K2P                    // the register-ring walk: measured slower than K2 on every workload (profiles/r02_sweep_b_k2p_l2hints.jsonl)
+            else if (pipe == 4 && nvec > 4) {
                 if (nvec <= 8) s = launch_pipe<Op, 8, 1, 4, (W64 ? 3 : 4)>(p);
                 else if (nvec <= 16) s = launch_pipe<Op, 16, 1, 4, (W64 ? 3 : 4)>(p);
                 else if (nvec <= 32) s = launch_pipe<Op, 32, 1, 4, (W64 ? 3 : 4)>(p);
@@ -215,8 +232,9 @@ static int launch_op(const LaunchParams& p) {
                 else if (nvec <= 16) s = launch_pipe<Op, 16, 1, 8, (W64 ? 2 : 3)>(p);
                 else if (nvec <= 32) s = launch_pipe<Op, 32, 1, 8, (W64 ? 2 : 3)>(p);
                 else s = launch_pipe<Op, 32, 2, 4, (W64 ? 2 : 3)>(p);
-            } else
-            if (narrow && nvec == 1) s = launch_layout<Op, 1, 1, 1, 4>(p);
+            }
+#endif
+            else if (narrow && nvec == 1) s = launch_layout<Op, 1, 1, 1, 4>(p);
             else if (narrow && nvec <= 2) s = launch_layout<Op, 2, 1, 2, 4>(p);
             else if (nvec <= 4) s = launch_layout<Op, 4, 1, 4, 4>(p);
             else if (nvec <= 8) s = wide ? launch_layout<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_layout<Op, 8, 1, CB_DEEP_U, DB>(p);

@@ -212,6 +212,8 @@ __device__ __forceinline__ uint64_t cb_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// pull a line of a stream into L2 ahead of its use (a hint: no register, no fault)
+__device__ __forceinline__ void cb_prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ uint4 cb_ldg16_hint(const void* ptr, uint64_t policy) {
     uint4 u;
     asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(ptr), "l"(policy));
@@ -246,7 +248,10 @@ __device__ __forceinline__ Vec16<T> ld_hub16(const HubSrc& hub, uint32_t rank, i
 // One virtual warp walks chunk `chunk` of the tile front to back (all virtual warps of the hardware warp in lock step).
 // FULL: the panel row is exactly VW*R vectors wide (every lane owns real columns) - no lane predicates are generated.
 // HUB : rows of hub columns come from shared memory of the cluster instead of global memory.
-template <class Op, int VW, int R, int U, bool FULL, bool HUB>
+// PF  : the (column, value) entries of step s+1 are loaded while step s is processed, and the lines of both streams that will
+//       be read PF_AHEAD entries later are pulled into L2 now - the profile of the round-1 kernel showed 27 % of the stall
+//       samples on exactly these two loads (profiles/r02_*): they stream from DRAM once and nothing else hides them.
+template <class Op, int VW, int R, int U, bool FULL, bool HUB, bool PF = false>
 __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t chunk, const HubSrc& hub) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
@@ -331,12 +336,33 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
         if (more) row = a.nzrows[ridx];
     };
 
+    constexpr int PF_AHEAD = 512;                        // entries: 2 KB of the column stream
+    int cf_nxt = 0;
+    TA av_nxt = TA();
+    if (PF && vl < e - s) {
+        cf_nxt = ld_stream(a.colflag + s + vl);
+        if (HASVAL) av_nxt = ld_stream_val<TA>(vals + s + vl);
+    }
     for (int base = 0; base < maxlen; base += VW) {
         const int rem = e - (s + base);                 // nonzeros this virtual warp still owns (may be <= 0)
         int cf = 0;
         TA av = TA();
         int hs = 0xffff;
-        if (vl < rem) {
+        if (PF) {
+            cf = cf_nxt;
+            av = av_nxt;
+            cf_nxt = 0;
+            av_nxt = TA();
+            if (VW + vl < rem) {
+                cf_nxt = ld_stream(a.colflag + s + base + VW + vl);
+                if (HASVAL) av_nxt = ld_stream_val<TA>(vals + s + base + VW + vl);
+            }
+            // one lane per virtual warp touches the line PF_AHEAD entries on (a 128-byte line holds 32 columns)
+            if (vl == 0 && PF_AHEAD < rem && (VW >= 32 || ((base / VW) & (32 / VW - 1)) == 0)) {
+                cb_prefetch_l2(a.colflag + s + base + PF_AHEAD);
+                if (HASVAL) cb_prefetch_l2(vals + s + base + PF_AHEAD);
+            }
+        } else if (vl < rem) {
             cf = ld_stream(a.colflag + s + base + vl);
             if (HASVAL) av = ld_stream_val<TA>(vals + s + base + vl);
             if (HUB) hs = (int)__ldcs(hub.hubslot + s + base + vl);
@@ -406,12 +432,12 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
 }
 
 // K2: one chunk per virtual warp, grid sized to the chunk count
-template <class Op, int VW, int R, int U, int MINB, bool FULL>
+template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PF = false>
 __global__ void __launch_bounds__(256, MINB)
 cb_spmm_kernel(const SpmmArgs a) {
     constexpr int NV = 32 / VW;                       // virtual warps per warp
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    cb_spmm_walk<Op, VW, R, U, FULL, false>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
+    cb_spmm_walk<Op, VW, R, U, FULL, false, PF>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
 }
 
 // ------------------------------------------------------------------------------------------------------------------

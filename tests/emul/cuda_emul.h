@@ -80,6 +80,7 @@ using std::min;
 // L2 eviction-priority hints of K2P: no cache on the host, the policy only has to travel
 inline uint64_t cb_policy_evict_last() { return 0x1111; }
 inline uint64_t cb_policy_evict_first() { return 0x2222; }
+inline void cb_prefetch_l2(const void* p) { if (!p) __builtin_trap(); }          // a hint; must at least be a pointer
 inline uint4 cb_ldg16_hint(const void* p, uint64_t policy) {
     if (policy != 0x1111 && policy != 0x2222) __builtin_trap();
     return *reinterpret_cast<const uint4*>(p);

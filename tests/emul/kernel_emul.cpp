@@ -116,7 +116,9 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         a.Y = (char*)Y.data();
         std::fill(carry.begin(), carry.end(), (char)0x77);
         std::vector<uint8_t> hubcls;
-        if (pipe == 2) {     // with L2 residency hints: per-nonzero use class of its column (cb_hub.cu), classes <= 2 marked
+        if (pipe == 3) {     // the round-1 walk with the entry prefetch
+            syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL, true>(a); });
+        } else if (pipe == 2) {     // with L2 residency hints: per-nonzero use class of its column (cb_hub.cu), classes <= 2 marked
             std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
             for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
             for (int64_t c = 0; c < n; ++c) order[c] = (int32_t)c;
@@ -239,6 +241,13 @@ int main(int argc, char** argv) {
     bad += run_case<MinPlus<int64_t>, 16, 1, 8, true>("pipe minplus_i64 larger acc D8", 300, 500, 32, 64, 400, 62 + sd, true, 0, 0, 0, 1);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 63 + sd, false, 0, 0, 0, 1);
     bad += run_case<PlusTimes<float, A_BOOL>, 8, 1, 8, true>("pipe pt_f32 boolA VW8 L=40 D8", 200, 300, 32, 40, 170, 64 + sd, true, 0, 0, 0, 1);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("prefetch pt_f32 VW16 U4", 61, 97, 64, 32, 150, 71 + sd, false, 0, 0, 0, 3);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, false>("prefetch pt_f32 VW32 k=100 acc", 40, 200, 100, 32, 90, 72 + sd, true, 0, 0, 0, 3);
+    bad += run_case<PlusTimes<double, A_BOOL>, 32, 2, 4, false>("prefetch pt_f64 boolA R2 ragged", 30, 80, 100, 32, 70, 73 + sd, false, 0, 0, 0, 3);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 4, true>("prefetch minplus_i32 VW8", 70, 64, 32, 32, 60, 74 + sd, false, 0, 0, 0, 3);
+    bad += run_case<SelectMax<int64_t>, 8, 1, 4, false>("prefetch selectmax_i64 k=13", 45, 50, 13, 32, 45, 75 + sd, false, 0, 0, 0, 3);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, true>("prefetch pt_f32 VW32 L=1200", 300, 3000, 128, 1200, 2900, 76 + sd, false, 0, 0, 0, 3);
+    bad += run_case<OrAnd<A_PATTERN>, 8, 1, 4, false>("prefetch or_and VW8 L=700", 200, 2000, 24, 700, 1800, 77 + sd, false, 0, 0, 0, 3);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe+l2 pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 65 + sd, false, 0, 0, 0, 2);
     bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, false>("pipe+l2 pt_f64 R2 ragged acc", 30, 80, 100, 32, 70, 66 + sd, true, 0, 0, 0, 2);
     bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("pipe+l2 minplus_i32 VW8 D8", 70, 64, 32, 32, 60, 67 + sd, false, 0, 0, 0, 2);

@@ -1,13 +1,10 @@
 """The persistent variants of the local multiply (csrc/cb_spmm_hub_kernel.cuh) on the GPU, through the C ABI: K2H (hub rows
 resident in cluster shared memory) and K2R (gathers pipelined through a shared-memory ring with cp.async).
 
-STATUS: both have been validated on the CPU warp/cluster emulator only (tests/test_kernel_emul_cpu.py); no GPU time was
-left in the round that wrote it.  It is opt-in in the product (cb_spmm_hub_config / CB_SPMM_HUB=1) and these tests are
-opt-in too: they run with CB_TEST_NEW=1 and are skipped otherwise, so an untested kernel cannot turn the validated suite
-red.  Also here: the narrow-panel layouts (CB_K2_NARROW=1) and the column filter for sparse right-hand sides
-(cb_tile_filter_columns / CB_SPGEMM_FILTER=1).  First thing to run on hardware next round:
-
-    CB_TEST_NEW=1 python -m pytest tests/test_new_variants_gpu.py -x -q
+STATUS: validated on hardware in round 2 (44 / 44 cases, bit-identical to K2) and part of the regular GPU suite since.  Both
+variants stay opt-in in the product (cb_spmm_hub_config / cb_spmm_ring_config): on every workload measured they are slower than
+K2 (profiles/r02_sweep_a_k2_k2h_k2r.jsonl).  Also here: the narrow-panel layouts (CB_K2_NARROW=1) and the column filter for
+sparse right-hand sides (cb_tile_filter_columns / CB_SPGEMM_FILTER=1).
 
 Each case runs in its own process (own CUDA context, hard timeout): a fault or a hang of the new kernel stays contained.
 The bar is stronger than parity: K2H walks chunks exactly like K2, so its result must equal K2's BIT FOR BIT for every
@@ -19,9 +16,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CB_TEST_NEW") != "1" and os.environ.get("CB_TEST_HUB") != "1",
-                                 reason="device code written without a GPU, not yet validated on hardware: set CB_TEST_NEW=1")]
+pytestmark = pytest.mark.gpu
 
 WORKER = r'''
 import sys, numpy as np

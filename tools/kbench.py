@@ -45,6 +45,8 @@ for name in a.workloads:
         try:
             if kind == "k2":
                 ctx.k2_config(o.get("slab", 0), o.get("point", -1))
+            elif kind == "pf":
+                ctx.k2_config(o.get("slab", 0), o.get("point", -1)); ctx.k2_pipe(1)
             elif kind == "pipe":
                 ctx.k2_config(o.get("slab", 0), -1); ctx.k2_pipe(o.get("d", 4)); ctx.k2_l2(o.get("l2", 0))
             elif kind == "hub":
