@@ -98,9 +98,11 @@ def test_driver_spmv_on_a_process_grid():
     build()
     n = 4 if torch.cuda.device_count() >= 4 else 2
     grid = ["2", "2"] if n == 4 else ["1", "2"]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", str(free_port()), DRIVER, "spmv", "12"] + grid
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    def cmd(port):
+        return [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), DRIVER, "spmv", "12"] + grid
+    from tests.test_summa_cpu import run_retrying_ports
+    r = run_retrying_ports(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SpMV and dense epilogues working correctly" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -183,9 +185,11 @@ def test_reference_betwcent_application_unmodified_on_2x2_gpus(tmp_path):
     from tests.golden.make_golden_grid import BC_BATCH, BC_K4APPROX, betwcent_input
     betwcent_input(str(tmp_path))
     out = str(tmp_path / "bc.txt")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), exe, str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    def cmd(port):
+        return [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), exe, str(tmp_path), str(BC_K4APPROX), str(BC_BATCH), out]
+    from tests.test_summa_cpu import run_retrying_ports
+    r = run_retrying_ports(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "Computation finished" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     gold = np.load(os.path.join(G, "grid_ref.npz"))["betwcent_p4"]
     got = np.loadtxt(out, skiprows=1)[:, 2]
@@ -249,9 +253,11 @@ def test_driver_spmmerror_program_on_a_2x2_grid():
     if torch.cuda.device_count() < 4:
         pytest.skip("needs 4 GPUs")
     build()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
-           "127.0.0.1", "--master-port", str(free_port()), DRIVER, "torus"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    def cmd(port):
+        return [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), DRIVER, "torus"]
+    from tests.test_summa_cpu import run_retrying_ports
+    r = run_retrying_ports(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.count("112 nonzeros") == 3 and "working correctly" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -264,7 +270,9 @@ def test_driver_multi_process_grid():
     build()
     n = 4 if torch.cuda.device_count() >= 4 else 2
     grid = ["2", "2"] if n == 4 else ["1", "2"]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", str(free_port()), DRIVER, "rmat", "14", "32", "mp_i32"] + grid
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    def cmd(port):
+        return [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), DRIVER, "rmat", "14", "32", "mp_i32"] + grid
+    from tests.test_summa_cpu import run_retrying_ports
+    r = run_retrying_ports(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "As a whole: 16384 rows" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

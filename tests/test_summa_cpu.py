@@ -21,11 +21,24 @@ def free_port():
         return s.getsockname()[1]
 
 
+def run_retrying_ports(make_cmd, **kw):
+    """subprocess.run(make_cmd(port)) with a fresh free port, again if the launcher found the port taken after all"""
+    for attempt in range(4):
+        r = subprocess.run(make_cmd(free_port()), **kw)
+        if r.returncode == 0 or "EADDRINUSE" not in (r.stderr or ""):
+            return r
+    return r
+
+
 def torchrun(n, args, timeout=600, extra_env=None):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), os.path.join(ROOT, "tests", "summa_worker.py")] + args
     env = dict(os.environ, OMP_NUM_THREADS="2", **(extra_env or {}))
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    for attempt in range(4):        # a port that was free a moment ago can be taken by the time the launcher binds it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+               "--master-port", str(free_port()), os.path.join(ROOT, "tests", "summa_worker.py")] + args
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            return r
+    return r
 
 
 @pytest.mark.parametrize("pr,pc,gn", [(1, 1, 10), (2, 2, 10), (2, 2, 11), (2, 4, 16), (2, 4, 1000003), (3, 2, 10), (4, 1, 7), (1, 4, 7),
