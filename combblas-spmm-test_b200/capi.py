@@ -23,7 +23,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
-           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe", "cb_spmm_k2_l2", "cb_spgemm_local", "cb_spgemm_summa", "cb_coo_info", "cb_coo_download", "cb_coo_free"]
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe", "cb_spmm_k2_l2", "cb_spgemm_local", "cb_spgemm_summa", "cb_coo_info", "cb_coo_download", "cb_coo_free", "cb_spmv_grid", "cb_gen_graph500_edges", "cb_gen_graph500_tile"]
 
 
 class CBError(RuntimeError):
@@ -112,6 +112,10 @@ def lib():
         L.cb_coo_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]
         L.cb_coo_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
         L.cb_coo_free.argtypes = [c_void_p]
+        L.cb_spmv_grid.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_int64]
+        L.cb_gen_graph500_edges.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int64, c_int64, c_void_p, c_void_p]
+        L.cb_gen_graph500_tile.argtypes = [c_void_p, c_int, c_int, c_uint64, c_uint64, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
+                                           c_uint64, POINTER(c_void_p)]
         L.cb_tile_row_lengths.argtypes = [c_void_p, c_void_p]
         L.cb_tile_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
         L.cb_dense_download_rows.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
@@ -260,6 +264,30 @@ class Context:
         _check(lib().cb_gen_rmat_tile(self.h, scale, edgefactor, seed, init, int(symmetric), row0, m, col0, n, val_dtype,
                                       val_seed, byref(t)), self.h)
         return Tile(self, t)
+
+    def graph500_edges(self, log_numverts, first, count, userseed=(0, 0)):
+        """edges [first, first+count) of the reference's packed Graph500 stream (RefGen21) -> (src, dst)"""
+        src, dst = np.empty(count, np.int64), np.empty(count, np.int64)
+        _check(lib().cb_gen_graph500_edges(self.h, log_numverts, userseed[0], userseed[1], first, count, _ptr(src), _ptr(dst)), self.h)
+        return src, dst
+
+    def gen_graph500_tile(self, scale, edgefactor=16, symmetric=True, remove_loops=True, row0=0, m=None, col0=0, n=None, val_dtype=PATTERN,
+                          val_seed=0, userseed=(0, 0)):
+        """the block of the matrix ReleaseTests/GenWriteMatrix.cpp builds (val_seed 0: values are edge multiplicities)"""
+        N = 1 << scale
+        m = N if m is None else m
+        n = N if n is None else n
+        t = c_void_p()
+        _check(lib().cb_gen_graph500_tile(self.h, scale, edgefactor, userseed[0], userseed[1], int(symmetric), int(remove_loops), row0, m, col0, n,
+                                          val_dtype, val_seed, byref(t)), self.h)
+        return Tile(self, t)
+
+    def spmv_grid(self, tile, x_piece, x_off, y_off, y_len, semiring, gm, gn):
+        """y = A (x).(+) x with the vector exchange on the device; collective.  -> this rank's piece of y"""
+        x_piece = np.ascontiguousarray(x_piece)
+        y = np.empty(y_len, x_piece.dtype)
+        _check(lib().cb_spmv_grid(self.h, tile.h, _ptr(x_piece), x_off, len(x_piece), _ptr(y), y_off, y_len, semiring, CODE_OF[x_piece.dtype], gm, gn), self.h)
+        return y
 
     # ---- dense panels
     def dense(self, rows, cols, dtype):

@@ -820,6 +820,110 @@ int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semirin
     return cb_spgemm_finish(ctx, &acc, semiring, dtype, rl, kl, C);
 }
 
+// ---- dense-vector multiply with the vector exchange on the device
+}  // extern "C"
+namespace {
+// compact vector <-> one-column panel (rows padded to 16 bytes, the layout every panel of K2 has)
+__global__ void __launch_bounds__(256)
+vec_to_panel_kernel(const char* __restrict__ vec, int64_t n, int es, char* __restrict__ panel) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        for (int b = 0; b < es; ++b) panel[i * 16 + b] = vec[i * es + b];
+}
+// panel -> compact vector, folding in SR::id() the way the reference's y does (it starts as id(): ParFriends.h:1960-1963; this
+// matters for SelectMax, where max(id, v) clips values below the identity)
+template <typename T>
+__global__ void __launch_bounds__(256)
+panel_to_vec_kernel(const char* __restrict__ panel, int64_t n, int semiring, T* __restrict__ vec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        T v = *reinterpret_cast<const T*>(panel + i * 16);
+        if (semiring == CB_MAX_SEL2ND && v < T(-1)) v = T(-1);
+        vec[i] = v;
+    }
+}
+template <>
+__global__ void __launch_bounds__(256)
+panel_to_vec_kernel<uint8_t>(const char* __restrict__ panel, int64_t n, int, uint8_t* __restrict__ vec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) vec[i] = (uint8_t)panel[i * 16];
+}
+}  // namespace
+extern "C" {
+
+// y = A (x).(+) x for a distributed dense vector, collective over the grid.  Replaces SpMV<SR>(SpParMat, FullyDistVec)
+// (include/CombBLAS/ParFriends.h:1924-1996): the reference moves x to the transposed process, MPI_Allgatherv's it along the
+// processor column, runs dcsc_gespmv on an id()-filled y (Friends.h:63-78) and MPI_Reduce's y along the processor row with
+// SR::mpi_op.  Here the pieces of x go up once, are gathered between the GPUs (one NCCL broadcast per piece, grouped), the local
+// multiply is K2 on a one-column panel, the partial results are combined along the processor row with ncclAllReduce
+// (sum / min / max = SR::mpi_op) and every rank takes its piece of y down.  No vector travels through host memory in between.
+//   x_piece / y_piece : this rank's pieces (host), at global offsets x_off / y_off with x_len / y_len elements; the pieces of x
+//                       tile [0, gn) in rank order, y_piece must lie inside this rank's row block of gm
+int cb_spmv_grid(cb_ctx* ctx, const cb_tile* tile, const void* x_piece, int64_t x_off, int64_t x_len, void* y_piece, int64_t y_off, int64_t y_len,
+                 int semiring, int dtype, int64_t gm, int64_t gn) {
+    if (!ctx || !tile) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmv_grid: null argument");
+    const size_t es = cb_dtype_size(dtype);
+    if (!es) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_spmv_grid: dtype %d", dtype);
+    const int pr = ctx->pr, pc = ctx->pc;
+    int64_t r0, rl, c0, cl;
+    block_range(gm, pr, ctx->myprocrow, &r0, &rl);
+    block_range(gn, pc, ctx->myproccol, &c0, &cl);
+    if (tile->m != rl || tile->n != cl) return cb_fail(ctx, CB_ERR_DIMMISMATCH, "cb_spmv_grid: local A %lldx%lld, want %lldx%lld", (long long)tile->m, (long long)tile->n, (long long)rl, (long long)cl);
+    if (x_off < 0 || x_len < 0 || x_off + x_len > gn || y_off < r0 || y_len < 0 || y_off + y_len > r0 + rl || (x_len > 0 && !x_piece) || (y_len > 0 && !y_piece))
+        return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmv_grid: vector piece outside its range");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    cb_scratch sc;
+    char *xfull = nullptr, *xpanel = nullptr, *ypanel = nullptr, *yvec = nullptr;
+    CB_CUDA(ctx, sc.alloc(&xfull, (size_t)std::max<int64_t>(gn, 1) * es));
+    CB_CUDA(ctx, sc.alloc(&xpanel, (size_t)std::max<int64_t>(cl, 1) * 16));
+    CB_CUDA(ctx, sc.alloc(&ypanel, (size_t)std::max<int64_t>(rl, 1) * 16));
+    CB_CUDA(ctx, sc.alloc(&yvec, (size_t)std::max<int64_t>(rl, 1) * es));
+    if (x_len > 0) CB_CUDA(ctx, cudaMemcpyAsync(xfull + (size_t)x_off * es, x_piece, (size_t)x_len * es, cudaMemcpyHostToDevice, st));
+    if (ctx->nranks > 1) {
+        // where every rank's piece sits: one small allgather, then one broadcast per piece in a group (an allgatherv)
+        int64_t mine[2] = {x_off, x_len};
+        int64_t* d_meta = nullptr;
+        CB_CUDA(ctx, sc.alloc(&d_meta, (size_t)2 * (ctx->nranks + 1)));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_meta, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+        CB_NCCL(ctx, nccl().AllGather(d_meta, d_meta + 2, sizeof mine, ncclInt8, (ncclComm_t)ctx->nccl_world, st));
+        std::vector<int64_t> all((size_t)2 * ctx->nranks);
+        CB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_meta + 2, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        CB_NCCL(ctx, nccl().GroupStart());
+        for (int q = 0; q < ctx->nranks; ++q) {
+            const int64_t off = all[(size_t)2 * q], len = all[(size_t)2 * q + 1];
+            if (off < 0 || len < 0 || off + len > gn) { nccl().GroupEnd(); return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmv_grid: rank %d announced a piece outside [0, %lld)", q, (long long)gn); }
+            if (len > 0) CB_NCCL(ctx, nccl().Broadcast(xfull + (size_t)off * es, xfull + (size_t)off * es, (size_t)len * es, ncclInt8, q, (ncclComm_t)ctx->nccl_world, st));
+        }
+        CB_NCCL(ctx, nccl().GroupEnd());
+    }
+    if (cl > 0) {
+        vec_to_panel_kernel<<<grid_for(cl, ctx->sm_count), 256, 0, st>>>(xfull + (size_t)c0 * es, cl, (int)es, xpanel);
+        CB_LAUNCHED(ctx);
+    }
+    const int64_t ld = 16 / (int64_t)es;
+    CB_TRY(cb_spmm_launch(ctx, st, tile, xpanel, ld, ypanel, ld, 1, dtype, semiring, 0));
+    if (rl > 0) {
+        const int g = grid_for(rl, ctx->sm_count);
+        switch (dtype) {
+            case CB_F32: panel_to_vec_kernel<float><<<g, 256, 0, st>>>(ypanel, rl, semiring, (float*)yvec); break;
+            case CB_F64: panel_to_vec_kernel<double><<<g, 256, 0, st>>>(ypanel, rl, semiring, (double*)yvec); break;
+            case CB_I32: panel_to_vec_kernel<int32_t><<<g, 256, 0, st>>>(ypanel, rl, semiring, (int32_t*)yvec); break;
+            case CB_I64: panel_to_vec_kernel<int64_t><<<g, 256, 0, st>>>(ypanel, rl, semiring, (int64_t*)yvec); break;
+            default: panel_to_vec_kernel<uint8_t><<<g, 256, 0, st>>>(ypanel, rl, semiring, (uint8_t*)yvec); break;
+        }
+        CB_LAUNCHED(ctx);
+        CB_CUDA(ctx, cudaGetLastError());
+        if (pc > 1) {
+            // MPI_Reduce with SR::mpi_op on RowWorld (ParFriends.h:1985-1993): sum, min or max; OR of booleans is max of bytes
+            const int op = (semiring == CB_MIN_PLUS) ? 3 /*ncclMin*/ : (semiring == CB_PLUS_TIMES && dtype != CB_U8) ? 0 /*ncclSum*/ : 2 /*ncclMax*/;
+            const int nt = dtype == CB_F32 ? 7 : dtype == CB_F64 ? 8 : dtype == CB_I32 ? 2 : dtype == CB_I64 ? 4 : 1 /*ncclUint8*/;
+            CB_NCCL(ctx, nccl().AllReduce(yvec, yvec, (size_t)rl, nt, op, (ncclComm_t)ctx->nccl_row, st));
+        }
+    }
+    if (y_len > 0) CB_CUDA(ctx, cudaMemcpyAsync(y_piece, yvec + (size_t)(y_off - r0) * es, (size_t)y_len * es, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    return CB_OK;
+}
+
 // byte allgather over the processor column with host buffers (set-up traffic of the peer transport)
 }  // extern "C"
 int cb_nccl_allgather_col(cb_ctx* ctx, const void* send_host, void* recv_host, size_t bytes) {

@@ -91,39 +91,17 @@ FullyDistVec<IU, typename promote_trait<NUM, NUV>::T_promote> SpMV(const SpParMa
     cb_ctx* ctx = grid->GetContext();
     const int pr = grid->GetGridRows(), pc = grid->GetGridCols(), myrow = grid->GetRankInProcCol(), mycol = grid->GetRankInProcRow();
     const IU gm = A.getnrow(), gn = A.getncol();
-    // the reference's own 2D algorithm (ParFriends.h:1924-1996): every process multiplies ITS tile with the piece of x that
-    // matches its columns, then the partial results are folded along the processor row with SR::add
-    IU c0, cl, r0, rl;
-    DenseParMat<IU, NUV>::Block(gn, pc, mycol, c0, cl);
-    DenseParMat<IU, NUV>::Block(gm, pr, myrow, r0, rl);
-    const std::vector<NUV> xw = x.Gather();                                   // TransposeVector + Allgatherv of the reference
-    cb_dense *dX = nullptr, *dY = nullptr;
-    const int dt = cb_dtype_of<NUV>::value;
-    cb_check(cb_dense_alloc(ctx, cl, 1, dt, &dX), ctx, "cb_dense_alloc");
-    cb_check(cb_dense_alloc(ctx, rl, 1, dt, &dY), ctx, "cb_dense_alloc");
-    if (cl > 0) cb_check(cb_dense_upload(dX, xw.data() + c0, 1), ctx, "cb_dense_upload");
-    std::vector<ST> part((size_t)rl, (ST)SR::id());
-    cb_check(cb_spmm_local(ctx, A.DeviceTile(), dX, dY, semiring_traits<SR>::op, 0), ctx, "cb_spmm_local");       // dcsc_gespmv on the GPU
-    if (rl > 0) cb_check(cb_dense_download(dY, part.data(), 1), ctx, "cb_dense_download");
-    cb_check(cb_ctx_sync(ctx), ctx, "cb_ctx_sync");
-    cb_dense_free(dX);
-    cb_dense_free(dY);
-    // MPI_Reduce with SR::mpi_op along the processor row; y started as id(), so the fold does too
-    std::vector<std::vector<char>> all;
-    cb_host_allgatherv(part.data(), part.size() * sizeof(ST), all);
-    std::vector<T_promote> yw((size_t)gm, SR::id());
-    for (int i = 0; i < pr; ++i) {
-        IU b0, bl;
-        DenseParMat<IU, NUV>::Block(gm, pr, i, b0, bl);
-        for (int j = 0; j < pc; ++j) {
-            const std::vector<char>& b = all[(size_t)grid->GetRank(i, j)];
-            const ST* v = reinterpret_cast<const ST*>(b.data());
-            for (size_t q = 0; q < b.size() / sizeof(ST); ++q) yw[(size_t)b0 + q] = SR::add(yw[(size_t)b0 + q], (T_promote)v[q]);
-        }
-    }
-    (void)r0; (void)myrow;
-    FullyDistVec<IU, T_promote> y(grid);
-    y.Scatter(yw);
+    // the reference's own 2D algorithm (ParFriends.h:1924-1996) with the vector exchange on the devices (cb_spmv_grid): my
+    // piece of x goes up, the pieces are gathered between the GPUs, every process multiplies ITS tile with the part of x that
+    // matches its columns, the partial results are combined along the processor row with SR's reduction, my piece of y comes down
+    (void)pr; (void)pc; (void)myrow; (void)mycol;
+    FullyDistVec<IU, T_promote> y(grid, gm, SR::id());
+    static_assert(sizeof(ST) == sizeof(T_promote) || std::is_same<T_promote, bool>::value, "vector elements are stored as they travel");
+    std::vector<ST> xin((size_t)x.MyLocLength()), yout((size_t)y.MyLocLength());
+    for (size_t q = 0; q < xin.size(); ++q) xin[q] = (ST)x.GetLocArr()[q];
+    cb_check(cb_spmv_grid(ctx, A.DeviceTile(), xin.data(), x.LengthUntil(), x.MyLocLength(), yout.data(), y.LengthUntil(), y.MyLocLength(),
+                          semiring_traits<SR>::op, cb_dtype_of<NUV>::value, gm, gn), ctx, "cb_spmv_grid");
+    for (size_t q = 0; q < yout.size(); ++q) y.SetLocalElement((IU)q, (T_promote)yout[q]);
     return y;
 }
 

@@ -32,15 +32,31 @@ struct cb_sum { T operator()(const T& x, const T& y) const { return x + y; } };
 // DistEdgeList<IT>: the reference's distributed Graph500 edge list (include/CombBLAS/DistEdgeList.h:90-140).  Here it is a
 // recipe, not a container: GenGraph500Data records scale / edge factor / initiator, and SpParMat(const DistEdgeList&, bool)
 // has the device generator (csrc/cb_gen.cu) build the tiles directly in HBM - the edges never exist on the host.
-// Differences from the reference, by construction of that generator: vertex ids are always scrambled, self loops are always
-// dropped, duplicate edges are merged (values are hashed weights, not multiplicities).
+// packed = true (what ReleaseTests/GenWriteMatrix.cpp asks for) is the reference's own stream: the Graph500 2.1 generator of
+// RefGen21.h, restated for the device (cb_gen_graph500_tile) and pinned to the reference's generator bit for bit, seeded like the
+// reference's -DDETERMINISTIC build; SpParMat(DEL, removeloops) then keeps or drops self loops as asked and sums duplicate edges
+// (values are multiplicities), like SpParMat.cpp:3138-3254.  The initiator argument is ignored on that path, as the reference
+// ignores it (RefGen21.h:69-76 fixes .57 / .19 / .19 / .05).
+// packed = false: the reference seeds that generator by rank and wall clock (DistEdgeList.cpp:239-251), so its matrix depends on
+// the process count; it is NOT reproduced.  The edges then come from this library's counter-based generator (same recipe, the
+// given initiator, vertex ids always scrambled, self loops dropped, hashed weights) and rank 0 says so once on stderr.
 template <class IT>
 class DistEdgeList {
 public:
     DistEdgeList() : commGrid(new CommGrid(MPI_COMM_WORLD, 0, 0)) {}
     explicit DistEdgeList(std::shared_ptr<CommGrid> grid) : commGrid(grid) {}
     void GenGraph500Data(double initiator[4], int log_numverts, int edgefactor, bool scramble = false, bool packed = false) {   // DistEdgeList.cpp:223-
-        (void)scramble; (void)packed;
+        this->packed = packed;
+        if (packed && !scramble) SpParHelper::Print("WARNING: Packed version does always generate scrambled vertex identifiers\n");   // DistEdgeList.cpp:225-228
+        if (!packed) {
+            static bool told = false;
+            if (!told && commGrid->GetRank() == 0) {
+                std::fprintf(stderr, "GenGraph500Data(packed = false): the reference's rank- and clock-seeded edge stream is not reproduced; edges come from "
+                                     "the counter-based generator of this library (scrambled ids%s, self loops dropped, hashed weights)\n",
+                             scramble ? "" : " although scramble = false was asked for");
+                told = true;
+            }
+        }
         for (int i = 0; i < 4; ++i) init[i] = initiator[i];
         scale = log_numverts;
         ef = edgefactor;
@@ -51,6 +67,7 @@ public:
     std::shared_ptr<CommGrid> commGrid;
     double init[4] = {0.57, 0.19, 0.19, 0.05};
     int scale = 0, ef = 16;
+    bool packed = false;
     IT globalV = 0;
 };
 
@@ -74,8 +91,22 @@ public:
     // conversion from a distributed edge list (reference SpParMat.cpp:3138-3254): generated on the device, see DistEdgeList
     template <class DELIT>
     SpParMat(const DistEdgeList<DELIT>& rhs, bool removeloops = true) : commGrid(rhs.commGrid), spSeq(nullptr) {
-        (void)removeloops;                                        // the device generator never emits self loops
-        GenGraph500(rhs.scale, rhs.ef, false, 0, !std::is_same<NT, bool>::value, 1, rhs.init);
+        if (rhs.packed) {
+            // the reference's own stream and its own conversion: duplicates summed, loops kept unless asked otherwise
+            gm = gn = (IT)1 << rhs.scale;
+            IT r0, rl, c0, cl;
+            BlockRange(gm, commGrid->GetGridRows(), commGrid->GetRankInProcCol(), r0, rl);
+            BlockRange(gn, commGrid->GetGridCols(), commGrid->GetRankInProcRow(), c0, cl);
+            const int vd = std::is_same<NT, bool>::value ? CB_PATTERN : cb_dtype_of<NT>::value;
+            cb_ctx* ctx = commGrid->GetContext();
+            cb_check(cb_gen_graph500_tile(ctx, rhs.scale, rhs.ef, 0, 0, 0, removeloops ? 1 : 0, r0, rl, c0, cl, vd, 0, &dtile), ctx, "cb_gen_graph500_tile");
+            int64_t info[8];
+            cb_tile_info(dtile, info);
+            dnnz = info[0];
+            devvals = vd != CB_PATTERN;
+        } else {
+            GenGraph500(rhs.scale, rhs.ef, false, 0, !std::is_same<NT, bool>::value, 1, rhs.init);      // never emits self loops
+        }
     }
     // value-type conversion (reference SpParMat.h converting constructor / operator SpParMat<IT,NNT,NDER>()): same structure,
     // every value cast to NT (a nonzero becomes true for bool)

@@ -195,6 +195,16 @@ int cb_spmm_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t l
 int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int semiring,
                        int64_t gm, int64_t gn, int64_t gk, int dtype);
 
+/* y = A (x).(+) x for a dense vector distributed over the grid, with the vector exchange on the device.  Replaces
+ * SpMV<SR>(SpParMat, FullyDistVec) (include/CombBLAS/ParFriends.h:1924-1996): TransposeVector + MPI_Allgatherv on the processor
+ * column, dcsc_gespmv on an id()-filled y (Friends.h:63-78), MPI_Reduce with SR::mpi_op on the processor row.  The pieces of x
+ * (host, at global offset x_off, x_len elements; the pieces of all ranks tile [0, gn) in any order) go up once, travel between
+ * the GPUs over NCCL, the local multiply is the SpMM kernel on a one-column panel, the partial results are combined along the
+ * processor row with ncclAllReduce (sum / min / max) and this rank's piece of y (inside its row block of gm) comes down.
+ * Collective over the grid. */
+int cb_spmv_grid(cb_ctx* ctx, const cb_tile* tile, const void* x_piece, int64_t x_off, int64_t x_len, void* y_piece, int64_t y_off, int64_t y_len,
+                 int semiring, int dtype, int64_t gm, int64_t gn);
+
 /* ------------------------------------------------------------------ sparse x SPARSE (tall-skinny right-hand side)
  * The literal Mult_AnXBn_Synch<SR,NUO,UDERO>(A, B) / PSpGEMM<SR>(A, B) of the reference (include/CombBLAS/ParFriends.h:1004-1108,
  * SpParMat.h:454-467) - the call of Applications/SpMMError.cpp:83 and Applications/BetwCent.cpp:185,204 - on the device.
@@ -267,6 +277,18 @@ int cb_profile_read(cb_ctx* ctx, double ms[3], int64_t launches[3]);
  * val_dtype: CB_PATTERN, or a dtype whose values come from the counter hash with val_seed. */
 int cb_gen_rmat_tile(cb_ctx* ctx, int scale, int edgefactor, uint64_t seed, const double initiator[4], int symmetric,
                      int64_t row0, int64_t m, int64_t col0, int64_t n, int val_dtype, uint64_t val_seed, cb_tile** tile);
+/* The reference's OWN edge stream: the Graph500 2.1 Kronecker generator as DistEdgeList::GenGraph500Data drives it with
+ * packed = true (include/CombBLAS/RefGen21.h:88-301, DistEdgeList.cpp:223-236) - the stream ReleaseTests/GenWriteMatrix.cpp
+ * builds its matrices from - restated for the device and checked bit for bit against the reference's generator.
+ * (userseed1, userseed2) = (0, 0) is the reference's -DDETERMINISTIC seed (RefGen21.h:274-275).
+ * cb_gen_graph500_edges: edges [first, first+count) as they leave the generator (global ids, duplicates and loops included).
+ * cb_gen_graph500_tile : the block of the matrix SpParMat(DistEdgeList, removeloops) [+ Symmetricize] builds from
+ *   edgefactor * 2^scale such edges; val_seed == 0 gives the reference's values (duplicates summed: multiplicities),
+ *   any other val_seed hashed weights as cb_gen_rmat_tile does. */
+int cb_gen_graph500_edges(cb_ctx* ctx, int log_numverts, uint64_t userseed1, uint64_t userseed2, int64_t first, int64_t count,
+                          int64_t* src_host, int64_t* dst_host);
+int cb_gen_graph500_tile(cb_ctx* ctx, int scale, int edgefactor, uint64_t userseed1, uint64_t userseed2, int symmetric, int remove_loops,
+                         int64_t row0, int64_t m, int64_t col0, int64_t n, int val_dtype, uint64_t val_seed, cb_tile** tile);
 /* X[i,j] = value(seed, (row0+i)*gk + col0+j); kind 0 = uniform (0,1) / [1,100] / Bernoulli, kind 1 = MinPlus operand
  * with ~1% entries at numeric max */
 int cb_gen_dense(cb_dense* d, uint64_t seed, int64_t row0, int64_t col0, int64_t gk, int kind);

@@ -197,6 +197,41 @@ int cbref_matrix_mult(void* h, int64_t k, const void* X, void* Y, double* second
 }
 void cbref_matrix_free(void* h) { delete static_cast<RefMatBase*>(h); }
 
+// The matrix ReleaseTests/GenWriteMatrix.cpp writes, built by the reference's own classes with the calls of its lines 96-124:
+// packed Graph500 edges, SpParMat(DEL, false) (keeps loops, sums duplicates: values are multiplicities), RemoveLoops, and for
+// symmetric != 0 the program's own Symmetricize (A += A^T).  Call with I == NULL for the size.
+int cbref_genwrite(int scale, int edgefactor, int symmetric, int64_t* nnz, int64_t* I, int64_t* J, int32_t* V) {
+    typedef SpParMat<int64_t, int, SpDCCols<int32_t, int>> PSpMat;
+    double initiator[4] = {.57, .19, .19, .05};
+    DistEdgeList<int64_t>* DEL = new DistEdgeList<int64_t>();
+    DEL->GenGraph500Data(initiator, scale, edgefactor, true, true);
+    PSpMat G(*DEL, false);
+    delete DEL;
+    G.RemoveLoops();
+    if (symmetric) { PSpMat GT = G; GT.Transpose(); G += GT; }
+    *nnz = G.getnnz();
+    if (I) {
+        Dcsc<int32_t, int>* d = G.seq().GetDCSC();
+        int64_t q = 0;
+        if (d)
+            for (int32_t c = 0; c < d->nzc; ++c)
+                for (int32_t p = d->cp[c]; p < d->cp[c + 1]; ++p, ++q) { I[q] = d->ir[p]; J[q] = d->jc[c]; V[q] = d->numx[p]; }
+    }
+    return 0;
+}
+
+// Edges [first, first + count) of the reference's own packed Graph500 stream (RefGen21::generate_kronecker_range,
+// include/CombBLAS/RefGen21.h:246-262, seeded as make_graph does under -DDETERMINISTIC: make_mrg_seed(0, 0)), for the goldens the
+// device generator csrc/cb_gen.cu (cb_gen_graph500_edges) is pinned to.
+int cbref_graph500_edges(int log_numverts, int64_t first, int64_t count, int64_t* src, int64_t* dst) {
+    uint_fast32_t seed[5];
+    make_mrg_seed(0, 0, seed);
+    std::vector<packed_edge> e((size_t)(count > 0 ? count : 1));
+    RefGen21::generate_kronecker_range(seed, log_numverts, first, first + count, e.data());
+    for (int64_t q = 0; q < count; ++q) { src[q] = get_v0_from_edge(&e[(size_t)q]); dst[q] = get_v1_from_edge(&e[(size_t)q]); }
+    return 0;
+}
+
 int cbref_num_threads() { return omp_get_max_threads(); }
 void cbref_set_num_threads(int t) { omp_set_num_threads(t); }
 

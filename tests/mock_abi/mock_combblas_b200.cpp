@@ -23,6 +23,7 @@
 #include <thread>
 #include <vector>
 #include "combblas_b200.h"
+#include "../../combblas-spmm-test_b200/csrc/cb_gen500.cuh"       // host side of the Graph500 stream: the mock makes the same matrix as the device
 
 struct cb_ctx { std::string err; int64_t launches = 0; int rank = 0, nranks = 1, pr = 1, pc = 1; };
 
@@ -298,6 +299,65 @@ int cb_gen_rmat_tile(cb_ctx*, int scale, int edgefactor, uint64_t seed, const do
     return CB_OK;
 }
 
+int cb_gen_graph500_edges(cb_ctx*, int lgN, uint64_t u1, uint64_t u2, int64_t first, int64_t count, int64_t* src, int64_t* dst) {
+    static g500::Tables t;
+    g500::build_tables(u1, u2, &t);
+    for (int64_t q = 0; q < count; ++q) {
+        const uint64_t ei = (uint64_t)(first + q);
+        g500::State s = t.seed;
+        for (int b = 0; b < 4; ++b) { const unsigned v = (unsigned)((ei >> (8 * b)) & 0xFF); if (v) s = g500::apply(t.edge[b][v], s); }
+        uint64_t a, c;
+        g500::one_edge(s, lgN, t.val0, t.val1, &a, &c);
+        src[q] = (int64_t)a; dst[q] = (int64_t)c;
+    }
+    return CB_OK;
+}
+int cb_gen_graph500_tile(cb_ctx* ctx, int scale, int edgefactor, uint64_t u1, uint64_t u2, int symmetric, int remove_loops, int64_t row0, int64_t m,
+                         int64_t col0, int64_t n, int val_dtype, uint64_t val_seed, cb_tile** tile) {
+    const int64_t nedges = (int64_t)edgefactor << scale, N = (int64_t)1 << scale;
+    std::vector<int64_t> src((size_t)nedges), dst((size_t)nedges);
+    cb_gen_graph500_edges(ctx, scale, u1, u2, 0, nedges, src.data(), dst.data());
+    std::map<std::pair<int64_t, int64_t>, int64_t> mult;
+    for (int64_t e = 0; e < nedges; ++e) {
+        if (remove_loops && src[(size_t)e] == dst[(size_t)e]) continue;
+        ++mult[{src[(size_t)e], dst[(size_t)e]}];
+        if (symmetric) ++mult[{dst[(size_t)e], src[(size_t)e]}];
+    }
+    cb_tile* t = new cb_tile();
+    t->m = m; t->n = n; t->val_dtype = val_dtype;
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip;
+    for (auto& kv : mult) {
+        const int64_t i = kv.first.first, j = kv.first.second;
+        if (i < row0 || i >= row0 + m || j < col0 || j >= col0 + n) continue;
+        std::vector<unsigned char> v;
+        auto putv = [&](auto x) { const unsigned char* p = (const unsigned char*)&x; v.insert(v.end(), p, p + sizeof x); };
+        if (val_seed == 0) {
+            switch (val_dtype) {
+                case CB_F32: putv((float)kv.second); break;
+                case CB_F64: putv((double)kv.second); break;
+                case CB_I32: putv((int32_t)kv.second); break;
+                case CB_I64: putv((int64_t)kv.second); break;
+                case CB_U8: putv((uint8_t)kv.second); break;
+                default: break;
+            }
+        } else {
+            const uint64_t h = splitmix64(val_seed * 0x100000001B3ULL ^ (uint64_t)(i * N + j));
+            switch (val_dtype) {
+                case CB_F32: put_value<float>(v, h); break;
+                case CB_F64: put_value<double>(v, h); break;
+                case CB_I32: put_value<int32_t>(v, h); break;
+                case CB_I64: put_value<int64_t>(v, h); break;
+                case CB_U8: v.push_back(1); break;
+                default: break;
+            }
+        }
+        trip.push_back({{i - row0, j - col0}, v});
+    }
+    build_csr(t, trip);
+    *tile = t;
+    return CB_OK;
+}
+
 int cb_dense_alloc(cb_ctx*, int64_t rows, int64_t cols, int dtype, cb_dense** d) {
     cb_dense* x = new cb_dense();
     x->rows = rows; x->cols = cols; x->dtype = dtype;
@@ -487,6 +547,55 @@ int cb_coo_download(cb_coo* c, int64_t* rows, int64_t* cols, void* vals) {
     return CB_OK;
 }
 int cb_coo_free(cb_coo* c) { delete c; return CB_OK; }
+int cb_spmv_grid(cb_ctx* ctx, const cb_tile* t, const void* x_piece, int64_t x_off, int64_t x_len, void* y_piece, int64_t y_off, int64_t y_len,
+                 int sr, int dtype, int64_t gm, int64_t gn) {
+    // every rank publishes its piece of x; everyone assembles x, multiplies its tile with its column block, publishes the
+    // partial result and folds the partials of its processor row (starting from SR::id() like the reference's y)
+    const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;
+    const size_t es = esize(dtype);
+    int64_t r0, rl, c0, cl;
+    block_range(gm, pr, myrow, &r0, &rl); block_range(gn, pc, mycol, &c0, &cl);
+    if (t->m != rl || t->n != cl) return fail(ctx, CB_ERR_DIMMISMATCH, "mock ABI: spmv block mismatch");
+    std::vector<unsigned char> mine;
+    put<int64_t>(mine, x_off); put<int64_t>(mine, x_len);
+    mine.insert(mine.end(), (const unsigned char*)x_piece, (const unsigned char*)x_piece + (size_t)x_len * es);
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(ctx, mine, all);
+    std::vector<unsigned char> xfull((size_t)gn * es, 0);
+    for (int q = 0; q < ctx->nranks; ++q) {
+        size_t off = 0;
+        const int64_t o = take<int64_t>(all[(size_t)q], off), l = take<int64_t>(all[(size_t)q], off);
+        if (l > 0) std::memcpy(xfull.data() + (size_t)o * es, all[(size_t)q].data() + off, (size_t)l * es);
+    }
+    cb_dense *X = nullptr, *Y = nullptr;
+    cb_dense_alloc(ctx, cl, 1, dtype, &X);
+    cb_dense_alloc(ctx, rl, 1, dtype, &Y);
+    if (cl > 0) std::memcpy(X->data.data(), xfull.data() + (size_t)c0 * es, (size_t)cl * es);
+    int st = cb_spmm_local(ctx, t, X, Y, sr, 0);
+    if (st != CB_OK) { cb_dense_free(X); cb_dense_free(Y); return st; }
+    std::vector<std::vector<unsigned char>> parts;
+    mock_allgatherv(ctx, Y->data, parts);
+    if (sr == CB_PLUS_TIMES && dtype == CB_U8) sr = CB_OR_AND;
+    auto fold = [&](auto tag) {
+        typedef decltype(tag) T;
+        std::vector<T> acc((size_t)rl, sr_id<T>(sr));
+        for (int q = 0; q < ctx->nranks; ++q) {
+            if (q / pc != myrow) continue;
+            const T* v = (const T*)parts[(size_t)q].data();
+            for (int64_t i = 0; i < rl; ++i) acc[(size_t)i] = sr_add<T>(sr, acc[(size_t)i], v[i]);
+        }
+        if (y_len > 0) std::memcpy(y_piece, acc.data() + (y_off - r0), (size_t)y_len * sizeof(T));
+    };
+    switch (dtype) {
+        case CB_F32: fold(float()); break;
+        case CB_F64: fold(double()); break;
+        case CB_I32: fold(int32_t()); break;
+        case CB_I64: fold(int64_t()); break;
+        default: fold(uint8_t()); break;
+    }
+    cb_dense_free(X); cb_dense_free(Y);
+    return CB_OK;
+}
 int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* t, const void* X_host, int64_t ldx, void* Y_host, int64_t ldy, int sr,
                        int64_t gm, int64_t gn, int64_t gk, int dtype) {
     const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;

@@ -60,3 +60,40 @@ def test_dense_panel_equals_numpy_recipe(ctx, dt, kind):
     full = O.dense_operand(400, k, 42, dt, "x_minplus" if kind else "value")
     assert np.array_equal(d.download(), full[17:317, 5:15])
     d.free()
+
+
+def test_graph500_stream_is_the_references_own(ctx):
+    """cb_gen_graph500_edges against edges made by the UNMODIFIED reference generator (RefGen21::generate_kronecker_range,
+    -DDETERMINISTIC seed; tests/golden/graph500_ref.npz): bit for bit, also far into the stream at scale 24."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph500_ref.npz"))
+    for key in [k for k in gold.files if k.startswith("edges_")]:
+        _, s, first = key.split("_")
+        scale, first = int(s[1:]), int(first)
+        src, dst = ctx.graph500_edges(scale, first, gold[key].shape[1])
+        assert np.array_equal(src, gold[key][0]) and np.array_equal(dst, gold[key][1]), key
+
+
+def test_graph500_tile_is_the_matrix_genwritematrix_builds(ctx):
+    """cb_gen_graph500_tile (loops removed, duplicates summed, optionally A + A^T) against the matrix the reference's own classes
+    build with the calls of ReleaseTests/GenWriteMatrix.cpp:96-124 - structure and multiplicity values; whole and as 2 x 2 blocks."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph500_ref.npz"))
+    for scale, ef, sym in [(10, 16, 1), (10, 16, 0), (9, 8, 1)]:
+        want = gold[f"genwrite_s{scale}_ef{ef}_sym{sym}"]
+        n = 1 << scale
+        t = ctx.gen_graph500_tile(scale, ef, symmetric=bool(sym), remove_loops=True, val_dtype=cb.I32)
+        rowptr, col, vals = t.to_csr(np.int32)
+        rows = np.repeat(np.arange(n), np.diff(rowptr))
+        assert np.array_equal(rows, want[0]) and np.array_equal(col, want[1]) and np.array_equal(vals.astype(np.int64), want[2])
+        t.free()
+        got = []
+        for i in range(2):
+            for j in range(2):
+                tb = ctx.gen_graph500_tile(scale, ef, symmetric=bool(sym), remove_loops=True, row0=i * n // 2, m=n // 2, col0=j * n // 2, n=n // 2,
+                                           val_dtype=cb.I32)
+                rp, c, v = tb.to_csr(np.int32)
+                r = np.repeat(np.arange(n // 2), np.diff(rp))
+                got += list(zip((r + i * n // 2).tolist(), (c + j * n // 2).tolist(), v.tolist()))
+                tb.free()
+        assert sorted(got) == sorted(zip(want[0].tolist(), want[1].tolist(), want[2].tolist()))

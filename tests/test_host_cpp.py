@@ -244,6 +244,9 @@ def test_reference_genwritematrix_driver_unmodified_on_the_gpu(tmp_path):
     assert m == n == 1024 and len(ent) > 10000 and all(i != j for i, j, _ in ent)
     pairs = {(i, j): v for i, j, v in ent}
     assert all(pairs.get((j, i)) == v for (i, j), v in pairs.items())
+    # the matrix the reference's own build of this program writes for the same arguments (tests/golden/make_golden_graph500.py)
+    gold = np.load(os.path.join(G, "graph500_ref.npz"))["genwrite_s10_ef16_sym1"]
+    assert sorted((i, j, float(v)) for i, j, v in ent) == sorted(zip(gold[0].tolist(), gold[1].tolist(), [float(v) for v in gold[2]]))
 
 
 @pytest.mark.gpu

@@ -203,14 +203,19 @@ def test_reference_genwritematrix_driver_compiles_unmodified_and_runs(driver, tm
                            "-o", exe, "/root/reference/ReleaseTests/GenWriteMatrix.cpp", f"-L{d}", "-lcombblas_b200", f"-Wl,-rpath,{d}", "-lpthread"],
                           timeout=600)
     one = str(tmp_path / "one.mtx")
-    r = run(exe, 7, 8, 1, one)
-    assert "Symmetricized" in r.stderr and "Removed 0 loops" in r.stderr
+    r = run(exe, 9, 8, 1, one)
+    assert "Symmetricized" in r.stderr and "Removed " in r.stderr
     m, n, ent = read_mm_file(one)
-    assert m == n == 128 and all(i != j for i, j, _ in ent)
+    assert m == n == 512 and all(i != j for i, j, _ in ent)
     pairs = {(i, j): v for i, j, v in ent}
     assert all(pairs.get((j, i)) == v for (i, j), v in pairs.items())             # A == A^T after Symmetricize
+    # ... and it is THE matrix the reference's own build of this program makes (packed Graph500 stream, duplicates summed):
+    # tests/golden/graph500_ref.npz holds the reference's result for `GenWriteMatrix 9 8 1`
+    gold = np.load(os.path.join(G, "graph500_ref.npz"))["genwrite_s9_ef8_sym1"]
+    want = sorted(zip(gold[0].tolist(), gold[1].tolist(), [float(v) for v in gold[2]]))
+    assert sorted((i, j, float(v)) for i, j, v in ent) == want
     four = str(tmp_path / "four.mtx")
-    run_grid(exe, 4, tmp_path / "rdv", 7, 8, 1, four)
+    run_grid(exe, 4, tmp_path / "rdv", 9, 8, 1, four)
     assert read_mm_file(four) == (m, n, ent)                                      # the same matrix from a 2 x 2 process grid
 
 
