@@ -37,6 +37,8 @@ struct NcclApi {
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -67,6 +69,8 @@ bool nccl_load() {
     SYM(Broadcast, "ncclBroadcast")
     SYM(AllGather, "ncclAllGather")
     SYM(AllReduce, "ncclAllReduce")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -922,6 +926,221 @@ int cb_spmv_grid(cb_ctx* ctx, const cb_tile* tile, const void* x_piece, int64_t 
     if (y_len > 0) CB_CUDA(ctx, cudaMemcpyAsync(y_piece, yvec + (size_t)(y_off - r0) * es, (size_t)y_len * es, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     return CB_OK;
+}
+
+// ---- distributed ingestion: triples parsed anywhere travel to the rank that owns them, between the GPUs
+}  // extern "C"
+namespace {
+// owner rank and local key of every triple (Owner rule of SpParMat.cpp:5066-5096: floor blocks, the last one takes the remainder)
+__global__ void __launch_bounds__(256)
+owner_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t nz, int64_t gm, int64_t gn, int pr, int pc,
+             uint32_t* __restrict__ owner, uint64_t* __restrict__ key, unsigned int* __restrict__ bad) {
+    const int64_t mper = gm / pr, nper = gn / pc;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = rows[p], c = cols[p];
+        if (r < 0 || r >= gm || c < 0 || c >= gn) { atomicOr(bad, 1u); owner[p] = 0; key[p] = 0; continue; }
+        const int orow = mper ? (int)min((int64_t)(r / mper), (int64_t)(pr - 1)) : pr - 1;
+        const int ocol = nper ? (int)min((int64_t)(c / nper), (int64_t)(pc - 1)) : pc - 1;
+        owner[p] = (uint32_t)(orow * pc + ocol);
+        key[p] = ((uint64_t)(r - (int64_t)orow * mper) << 32) | (uint64_t)(c - (int64_t)ocol * nper);
+    }
+}
+template <typename V>
+__global__ void __launch_bounds__(256)
+permute_kernel(const uint64_t* __restrict__ key, const V* __restrict__ val, const uint32_t* __restrict__ perm, int64_t nz, uint64_t* __restrict__ key_out, V* __restrict__ val_out) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nz; p += (int64_t)gridDim.x * blockDim.x) {
+        key_out[p] = key[perm[p]];
+        if (val) val_out[p] = val[perm[p]];
+    }
+}
+__global__ void __launch_bounds__(256)
+iota32_kernel(uint32_t* p, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256)
+count_owner_kernel(const uint32_t* __restrict__ owner_sorted, int64_t nz, int nranks, int64_t* __restrict__ start) {
+    // owner_sorted is ascending: start[q] = first position with owner >= q (start[nranks] = nz)
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nranks; q += gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nz;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (owner_sorted[mid] < (uint32_t)q) lo = mid + 1; else hi = mid; }
+        start[q] = lo;
+    }
+}
+// duplicates merged the way SpTuples::RemoveDuplicates(BinOp) does it (SpParMat.cpp:2962-2967); op: 0 keep the first, 1 sum, 2 max, 3 min
+template <typename T>
+struct DupOp {
+    int op;
+    __host__ __device__ T operator()(const T& a, const T& b) const { return op == 1 ? (T)(a + b) : op == 2 ? (a < b ? b : a) : op == 3 ? (b < a ? b : a) : a; }
+};
+template <typename T>
+int merge_duplicates(cb_ctx* ctx, cb_scratch& sc, uint64_t* keys_sorted, T* vals_sorted, int64_t n, int op, uint64_t* keys_out, T* vals_out, int64_t* n_out) {
+    int* d_runs = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_runs, 1));
+    size_t b = 0;
+    DupOp<T> f{op};
+    CB_CUDA(ctx, cub::DeviceReduce::ReduceByKey(nullptr, b, keys_sorted, keys_out, vals_sorted, vals_out, d_runs, f, (int)n, ctx->compute));
+    char* tmp = nullptr;
+    CB_CUDA(ctx, sc.alloc(&tmp, b));
+    CB_CUDA(ctx, cub::DeviceReduce::ReduceByKey(tmp, b, keys_sorted, keys_out, vals_sorted, vals_out, d_runs, f, (int)n, ctx->compute));
+    int runs = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&runs, d_runs, sizeof runs, cudaMemcpyDeviceToHost, ctx->compute));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    *n_out = runs;
+    return CB_OK;
+}
+}  // namespace
+extern "C" {
+
+// Replaces the distribution half of SpParMat::ParallelReadMM / SparseCommon (include/CombBLAS/SpParMat.cpp:3978-4115, :2891-2968):
+// every rank hands in the triples IT parsed from its share of the input (global 0-based coordinates, owned by anybody); they are
+// routed to their owners between the GPUs (the reference's MPI_Alltoallv: one grouped ncclSend / ncclRecv exchange), duplicates are
+// merged with dup_op (0 keep the first, 1 sum, 2 max, 3 min: SpTuples::RemoveDuplicates(BinOp)), and this rank's tile is built on
+// the device.  rows / cols / vals are host arrays; val_dtype CB_PATTERN takes no values.  Collective over the grid.
+int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* rows, const int64_t* cols, const void* vals,
+                                 int val_dtype, int dup_op, cb_tile** out) {
+    if (!ctx || !out || nz < 0 || (nz > 0 && (!rows || !cols))) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: null argument");
+    *out = nullptr;
+    const size_t vs = val_dtype == CB_PATTERN ? 0 : cb_dtype_size(val_dtype);
+    if (val_dtype != CB_PATTERN && !vs) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_tile_from_distributed_coo: value dtype %d", val_dtype);
+    if (vs && nz > 0 && !vals) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: null values");
+    if (nz >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_distributed_coo: %lld triples on one rank", (long long)nz);
+    if (dup_op < 0 || dup_op > 3) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: duplicate rule %d", dup_op);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    const int pr = ctx->pr, pc = ctx->pc, np = ctx->nranks, sm = ctx->sm_count;
+    int64_t r0, rl, c0, cl;
+    block_range(gm, pr, ctx->myprocrow, &r0, &rl);
+    block_range(gn, pc, ctx->myproccol, &c0, &cl);
+    cb_scratch sc;
+    const int64_t cap = std::max<int64_t>(nz, 1);
+    int64_t *d_rows = nullptr, *d_cols = nullptr, *d_start = nullptr;
+    char *d_vals = nullptr, *d_vals_routed = nullptr;
+    uint32_t *d_owner = nullptr, *d_owner_sorted = nullptr, *d_perm = nullptr, *d_perm_sorted = nullptr;
+    uint64_t *d_key = nullptr, *d_key_routed = nullptr;
+    unsigned int* d_bad = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_rows, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_cols, (size_t)cap));
+    CB_CUDA(ctx, sc.alloc(&d_owner, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_owner_sorted, (size_t)cap));
+    CB_CUDA(ctx, sc.alloc(&d_perm, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_perm_sorted, (size_t)cap));
+    CB_CUDA(ctx, sc.alloc(&d_key, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_key_routed, (size_t)cap));
+    CB_CUDA(ctx, sc.alloc(&d_start, (size_t)np + 1)); CB_CUDA(ctx, sc.alloc(&d_bad, 1));
+    if (vs) { CB_CUDA(ctx, sc.alloc(&d_vals, (size_t)cap * vs)); CB_CUDA(ctx, sc.alloc(&d_vals_routed, (size_t)cap * vs)); }
+    CB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), st));
+    if (nz > 0) {
+        CB_CUDA(ctx, cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_cols, cols, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
+        if (vs) CB_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, vs * (size_t)nz, cudaMemcpyHostToDevice, st));
+        owner_kernel<<<grid_for(nz, sm), 256, 0, st>>>(d_rows, d_cols, nz, gm, gn, pr, pc, d_owner, d_key, d_bad);
+        iota32_kernel<<<grid_for(nz, sm), 256, 0, st>>>(d_perm, nz);
+        CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+        size_t b = 0;
+        int obits = 1;
+        while ((1 << obits) < np) ++obits;
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, b, d_owner, d_owner_sorted, d_perm, d_perm_sorted, (int)nz, 0, obits, st));
+        char* tmp = nullptr;
+        CB_CUDA(ctx, sc.alloc(&tmp, b));
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, b, d_owner, d_owner_sorted, d_perm, d_perm_sorted, (int)nz, 0, obits, st));
+        switch (vs) {
+            case 0: permute_kernel<uint8_t><<<grid_for(nz, sm), 256, 0, st>>>(d_key, nullptr, d_perm_sorted, nz, d_key_routed, nullptr); break;
+            case 1: permute_kernel<uint8_t><<<grid_for(nz, sm), 256, 0, st>>>(d_key, (const uint8_t*)d_vals, d_perm_sorted, nz, d_key_routed, (uint8_t*)d_vals_routed); break;
+            case 4: permute_kernel<uint32_t><<<grid_for(nz, sm), 256, 0, st>>>(d_key, (const uint32_t*)d_vals, d_perm_sorted, nz, d_key_routed, (uint32_t*)d_vals_routed); break;
+            default: permute_kernel<uint64_t><<<grid_for(nz, sm), 256, 0, st>>>(d_key, (const uint64_t*)d_vals, d_perm_sorted, nz, d_key_routed, (uint64_t*)d_vals_routed); break;
+        }
+        CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+    }
+    count_owner_kernel<<<1, 256, 0, st>>>(d_owner_sorted, nz, np, d_start);
+    CB_LAUNCHED(ctx);
+    CB_CUDA(ctx, cudaGetLastError());
+    std::vector<int64_t> start((size_t)np + 1, 0);
+    unsigned int bad = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(start.data(), d_start, sizeof(int64_t) * (size_t)(np + 1), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    // every rank must learn about a bad triple anywhere before anyone blocks in the exchange
+    int64_t anybad = bad;
+    CB_TRY(cb_comm_allreduce_i64(ctx, 0, 1, &anybad, 1));
+    if (anybad) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: a triple lies outside the %lld x %lld matrix", (long long)gm, (long long)gn);
+    // counts[q * np + r] = triples rank q holds for rank r
+    std::vector<int64_t> counts((size_t)np * np, 0);
+    for (int q = 0; q < np; ++q) counts[(size_t)ctx->rank * np + q] = start[(size_t)q + 1] - start[(size_t)q];
+    if (np > 1) {
+        int64_t *d_c = nullptr, *d_call = nullptr;
+        CB_CUDA(ctx, sc.alloc(&d_c, (size_t)np));
+        CB_CUDA(ctx, sc.alloc(&d_call, (size_t)np * np));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_c, counts.data() + (size_t)ctx->rank * np, sizeof(int64_t) * (size_t)np, cudaMemcpyHostToDevice, st));
+        CB_NCCL(ctx, nccl().AllGather(d_c, d_call, sizeof(int64_t) * (size_t)np, ncclInt8, (ncclComm_t)ctx->nccl_world, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_call, sizeof(int64_t) * (size_t)np * np, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    int64_t nrecv = 0;
+    std::vector<int64_t> roff((size_t)np + 1, 0);
+    for (int q = 0; q < np; ++q) { roff[(size_t)q] = nrecv; nrecv += counts[(size_t)q * np + ctx->rank]; }
+    if (nrecv >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_distributed_coo: %lld triples for one tile", (long long)nrecv);
+    const int64_t rcap = std::max<int64_t>(nrecv, 1);
+    uint64_t *d_rkey = nullptr, *d_rkey_sorted = nullptr;
+    char *d_rval = nullptr, *d_rval_sorted = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_rkey, (size_t)rcap)); CB_CUDA(ctx, sc.alloc(&d_rkey_sorted, (size_t)rcap));
+    if (vs) { CB_CUDA(ctx, sc.alloc(&d_rval, (size_t)rcap * vs)); CB_CUDA(ctx, sc.alloc(&d_rval_sorted, (size_t)rcap * vs)); }
+    // the exchange: what I hold for q goes to q, what q holds for me arrives at roff[q]
+    if (np > 1) CB_NCCL(ctx, nccl().GroupStart());
+    for (int q = 0; q < np; ++q) {
+        const int64_t sn = counts[(size_t)ctx->rank * np + q], rn = counts[(size_t)q * np + ctx->rank];
+        if (q == ctx->rank) {
+            if (sn) {
+                CB_CUDA(ctx, cudaMemcpyAsync(d_rkey + roff[(size_t)q], d_key_routed + start[(size_t)q], sizeof(uint64_t) * (size_t)sn, cudaMemcpyDeviceToDevice, st));
+                if (vs) CB_CUDA(ctx, cudaMemcpyAsync(d_rval + (size_t)roff[(size_t)q] * vs, d_vals_routed + (size_t)start[(size_t)q] * vs, vs * (size_t)sn, cudaMemcpyDeviceToDevice, st));
+            }
+            continue;
+        }
+        if (sn) {
+            CB_NCCL(ctx, nccl().Send(d_key_routed + start[(size_t)q], sizeof(uint64_t) * (size_t)sn, ncclInt8, q, (ncclComm_t)ctx->nccl_world, st));
+            if (vs) CB_NCCL(ctx, nccl().Send(d_vals_routed + (size_t)start[(size_t)q] * vs, vs * (size_t)sn, ncclInt8, q, (ncclComm_t)ctx->nccl_world, st));
+        }
+        if (rn) {
+            CB_NCCL(ctx, nccl().Recv(d_rkey + roff[(size_t)q], sizeof(uint64_t) * (size_t)rn, ncclInt8, q, (ncclComm_t)ctx->nccl_world, st));
+            if (vs) CB_NCCL(ctx, nccl().Recv(d_rval + (size_t)roff[(size_t)q] * vs, vs * (size_t)rn, ncclInt8, q, (ncclComm_t)ctx->nccl_world, st));
+        }
+    }
+    if (np > 1) CB_NCCL(ctx, nccl().GroupEnd());
+    if (nrecv == 0) return cb_tile_build_from_keys(ctx, rl, cl, 0, d_rkey, nullptr, val_dtype, true, sc, out);
+    // sort by (row, column) - stable, so "keep the first" means first in rank order, then in the order handed in - and merge
+    {
+        size_t b = 0;
+        char* tmp = nullptr;
+        const int end_bit = 64;
+        if (vs == 0) {
+            CB_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, b, d_rkey, d_rkey_sorted, (int)nrecv, 0, end_bit, st));
+            CB_CUDA(ctx, sc.alloc(&tmp, b));
+            CB_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp, b, d_rkey, d_rkey_sorted, (int)nrecv, 0, end_bit, st));
+            int64_t* d_n = nullptr;
+            CB_CUDA(ctx, sc.alloc(&d_n, 1));
+            size_t b2 = 0;
+            CB_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, b2, d_rkey_sorted, d_rkey, d_n, (int)nrecv, st));
+            char* tmp2 = nullptr;
+            CB_CUDA(ctx, sc.alloc(&tmp2, b2));
+            CB_CUDA(ctx, cub::DeviceSelect::Unique(tmp2, b2, d_rkey_sorted, d_rkey, d_n, (int)nrecv, st));
+            int64_t nu = 0;
+            CB_CUDA(ctx, cudaMemcpyAsync(&nu, d_n, sizeof nu, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->launches += 4;
+            return cb_tile_build_from_keys(ctx, rl, cl, nu, d_rkey, nullptr, val_dtype, true, sc, out);
+        }
+        int64_t nu = 0;
+#define SORT_MERGE(T)                                                                                                                                   \
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, b, d_rkey, d_rkey_sorted, (const T*)d_rval, (T*)d_rval_sorted, (int)nrecv, 0, end_bit, st)); \
+        CB_CUDA(ctx, sc.alloc(&tmp, b));                                                                                                                \
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, b, d_rkey, d_rkey_sorted, (const T*)d_rval, (T*)d_rval_sorted, (int)nrecv, 0, end_bit, st));     \
+        CB_TRY(merge_duplicates<T>(ctx, sc, d_rkey_sorted, (T*)d_rval_sorted, nrecv, dup_op, d_rkey, (T*)d_rval, &nu));
+        switch (val_dtype) {
+            case CB_F32: { SORT_MERGE(float) break; }
+            case CB_F64: { SORT_MERGE(double) break; }
+            case CB_I32: { SORT_MERGE(int32_t) break; }
+            case CB_I64: { SORT_MERGE(int64_t) break; }
+            default: { SORT_MERGE(uint8_t) break; }
+        }
+#undef SORT_MERGE
+        ctx->launches += 4;
+        return cb_tile_build_from_keys(ctx, rl, cl, nu, d_rkey, d_rval, val_dtype, true, sc, out);
+    }
 }
 
 // byte allgather over the processor column with host buffers (set-up traffic of the peer transport)

@@ -8,13 +8,15 @@
 //     seq()/seqptr(), PrintInfo (:2853-2875), LoadImbalance (:762-770), operator== (:2877-2884).
 // B200-first differences, all behind the same calls:
 //   * the tile is uploaded once (lazily) into HBM as doubly compressed rows and stays there (DeviceTile());
-//   * triple / file ingestion is replicated: every process sees the whole input and keeps what it owns, instead of
-//     MPI-IO + MPI_Alltoallv (one box, no network between the ranks);
+//   * ParallelReadMM splits the file by byte ranges like the reference; the triples are routed to their owners and merged on
+//     the devices (cb_tile_from_distributed_coo).  The other ingestion paths (global triples, ReadDistribute) are replicated:
+//     every process sees the whole input and keeps what it owns;
 //   * GenGraph500() builds the tile directly on the GPU and never materialises it on the host.
 #ifndef CB_SPPARMAT_H
 #define CB_SPPARMAT_H
 
 #include <fstream>
+#include <functional>
 #include <memory>
 #include <sstream>
 #include "CommGrid.h"
@@ -163,8 +165,89 @@ public:
         }
         return true;
     }
+    // this process's share of a Matrix Market file: the lines that START inside its byte range of the data section
+    // (the reference's split, SpParMat.cpp:4010-4080: every process reads fsize / nprocs bytes and finishes its last line)
+    static bool ReadMMShare(const std::string& filename, bool onebased, int rank, int nranks, IT& tm, IT& tn, std::vector<int64_t>& rows,
+                            std::vector<int64_t>& cols, std::vector<ST>& vals) {
+        std::ifstream in(filename, std::ios::binary);
+        if (!in) return false;
+        std::string line;
+        std::getline(in, line);
+        std::string banner = line;
+        for (auto& ch : banner) ch = (char)std::tolower(ch);
+        const bool hasbanner = banner.compare(0, 14, "%%matrixmarket") == 0;
+        const bool pattern = hasbanner && banner.find("pattern") != std::string::npos;
+        const bool symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
+        if (hasbanner) std::getline(in, line);
+        while (!line.empty() && line[0] == '%' && std::getline(in, line)) {}
+        long long m_ = 0, n_ = 0, nz_ = 0;
+        std::istringstream(line) >> m_ >> n_ >> nz_;
+        tm = (IT)m_; tn = (IT)n_;
+        const std::streamoff data0 = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streamoff fsize = in.tellg();
+        const std::streamoff len = fsize - data0;
+        const std::streamoff lo = data0 + len * rank / nranks, hi = data0 + len * (rank + 1) / nranks;
+        in.clear();
+        in.seekg(lo);
+        if (lo > data0) {                       // a line that started before lo belongs to the previous process
+            in.seekg(lo - 1);
+            char c;
+            in.get(c);
+            if (c != '\n') std::getline(in, line);
+        }
+        long long ii, jj;
+        double vv = 1;
+        while (in && (std::streamoff)in.tellg() < hi && std::getline(in, line)) {
+            if (line.empty()) continue;
+            std::istringstream ls(line);
+            if (!(ls >> ii >> jj)) continue;
+            if (!pattern) ls >> vv;
+            if (onebased) { --ii; --jj; }
+            rows.push_back(ii); cols.push_back(jj); vals.push_back((ST)(NT)vv);
+            if (symmetric && ii != jj) { rows.push_back(jj); cols.push_back(ii); vals.push_back((ST)(NT)vv); }   // SpHelper.h:85-90
+        }
+        return true;
+    }
+    template <typename BinOp> struct dup_rule { static const int value = -1; };
+    template <typename T> struct dup_rule<maximum<T>> { static const int value = 2; };
+    template <typename T> struct dup_rule<cb_sum<T>> { static const int value = 1; };
+    template <typename T> struct dup_rule<std::plus<T>> { static const int value = 1; };
+
+    // ParallelReadMM (SpParMat.cpp:3978-4115): every process parses its own byte range of the file; the triples travel to
+    // their owners between the GPUs and are merged and turned into the tile there (cb_tile_from_distributed_coo) - the host
+    // tile is only materialised when somebody asks for seq().  A merge rule the device does not know (anything but maximum /
+    // plus) takes the replicated host path: every process reads the whole file and keeps what it owns.
     template <typename BinOp = maximum<NT>>
     void ParallelReadMM(const std::string& filename, bool onebased, BinOp binop = BinOp()) {
+        static const bool replicated = std::getenv("CB_READMM_REPLICATED") && std::atoi(std::getenv("CB_READMM_REPLICATED")) != 0;
+        if (dup_rule<BinOp>::value >= 0 && !replicated) {
+            IT tm = 0, tn = 0;
+            std::vector<int64_t> rows, cols;
+            std::vector<ST> vals;
+            const bool found = ReadMMShare(filename, onebased, commGrid->GetRank(), commGrid->GetSize(), tm, tn, rows, cols, vals);
+            if (commGrid->MinWorld(found ? 1 : 0) == 0) {
+                SpParHelper::Print("COMBBLAS: Matrix-market file " + filename + " can not be found\n");
+                MPI_Abort(MPI_COMM_WORLD, NOFILE);
+            }
+            Release();
+            spSeq = nullptr;
+            gm = tm; gn = tn;
+            cb_ctx* ctx = commGrid->GetContext();
+            int vd = cb_dtype_of<NT>::value;
+            if (std::is_same<NT, bool>::value) {             // a boolean matrix whose stored entries are all true is a pattern
+                const bool alltrue = std::all_of(vals.begin(), vals.end(), [](ST v) { return v != 0; });
+                if (commGrid->MinWorld(alltrue ? 1 : 0) == 1) vd = CB_PATTERN;
+            }
+            cb_check(cb_tile_from_distributed_coo(ctx, (int64_t)gm, (int64_t)gn, (int64_t)rows.size(), rows.data(), cols.data(),
+                                                  vd == CB_PATTERN ? nullptr : (const void*)vals.data(), vd, dup_rule<BinOp>::value, &dtile),
+                     ctx, "cb_tile_from_distributed_coo");
+            int64_t info[8];
+            cb_tile_info(dtile, info);
+            dnnz = info[0];
+            devvals = vd != CB_PATTERN;
+            return;
+        }
         IT tm = 0, tn = 0;
         std::vector<IT> rows, cols;
         std::vector<NT> vals;

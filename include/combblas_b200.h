@@ -103,6 +103,14 @@ int cb_tile_upload_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const void
 /* same from COO triples that already live on the device (int64 indices); used by the generators */
 int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const int64_t* d_rows, const int64_t* d_cols,
                             const void* d_vals, int val_dtype, cb_tile** tile);
+/* distributed ingestion.  Replaces the distribution half of SpParMat::ParallelReadMM and SparseCommon
+ * (include/CombBLAS/SpParMat.cpp:3978-4115, :2891-2968: every process parses its byte range of the file, MPI_Alltoallv sends the
+ * triples to their owners, SpTuples::RemoveDuplicates(BinOp) merges, the local tile is built): every rank hands in the triples IT
+ * parsed (host arrays, global 0-based coordinates, int64; owned by anybody), they are routed to their owners between the GPUs
+ * (one grouped ncclSend / ncclRecv exchange), duplicates are merged with dup_op (0 keep the first, 1 sum, 2 max, 3 min) and this
+ * rank's tile is built on the device.  Collective over the grid. */
+int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* rows, const int64_t* cols, const void* vals,
+                                 int val_dtype, int dup_op, cb_tile** tile);
 int cb_tile_free(cb_tile* tile);
 /* {nnz, m, n, nonempty rows, nonempty columns, work chunks, split rows, bytes resident} */
 int cb_tile_info(const cb_tile* tile, int64_t info[8]);

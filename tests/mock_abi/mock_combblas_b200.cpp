@@ -229,6 +229,52 @@ int cb_tile_upload_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const void
     *tile = t;
     return CB_OK;
 }
+int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* rows, const int64_t* cols, const void* vals,
+                                 int vdt, int dup_op, cb_tile** tile) {
+    // everyone publishes its triples; every rank keeps what it owns, merges duplicates in (rank, input) order and builds its tile
+    const int pr = ctx->pr, pc = ctx->pc, myrow = ctx->rank / pc, mycol = ctx->rank % pc;
+    const size_t es = vdt == CB_PATTERN ? 0 : esize(vdt);
+    std::vector<unsigned char> mine;
+    put<int64_t>(mine, nz);
+    for (int64_t p = 0; p < nz; ++p) { put<int64_t>(mine, rows[p]); put<int64_t>(mine, cols[p]); }
+    if (es) mine.insert(mine.end(), (const unsigned char*)vals, (const unsigned char*)vals + (size_t)nz * es);
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(ctx, mine, all);
+    int64_t r0, rl, c0, cl;
+    block_range(gm, pr, myrow, &r0, &rl); block_range(gn, pc, mycol, &c0, &cl);
+    std::map<std::pair<int64_t, int64_t>, std::vector<unsigned char>> acc;
+    auto merge = [&](std::vector<unsigned char>& into, const unsigned char* v) {
+        auto f = [&](auto tag) {
+            typedef decltype(tag) T;
+            T a, b;
+            std::memcpy(&a, into.data(), sizeof(T)); std::memcpy(&b, v, sizeof(T));
+            const T r = dup_op == 1 ? (T)(a + b) : dup_op == 2 ? std::max(a, b) : dup_op == 3 ? std::min(a, b) : a;
+            std::memcpy(into.data(), &r, sizeof(T));
+        };
+        switch (vdt) { case CB_F32: f(float()); break; case CB_F64: f(double()); break; case CB_I32: f(int32_t()); break; case CB_I64: f(int64_t()); break; default: f(uint8_t()); }
+    };
+    for (int q = 0; q < ctx->nranks; ++q) {
+        size_t off = 0;
+        const std::vector<unsigned char>& b = all[(size_t)q];
+        const int64_t n = take<int64_t>(b, off);
+        const size_t voff = off + (size_t)n * 16;
+        for (int64_t p = 0; p < n; ++p) {
+            const int64_t r = take<int64_t>(b, off), c = take<int64_t>(b, off);
+            if (r < 0 || r >= gm || c < 0 || c >= gn) return fail(ctx, CB_ERR_INVALIDPARAMS, "mock ABI: triple outside the matrix");
+            if (r < r0 || r >= r0 + rl || c < c0 || c >= c0 + cl) continue;
+            const unsigned char* v = es ? b.data() + voff + (size_t)p * es : nullptr;
+            auto it = acc.find({r - r0, c - c0});
+            if (it == acc.end()) acc[{r - r0, c - c0}] = es ? std::vector<unsigned char>(v, v + es) : std::vector<unsigned char>();
+            else if (es) merge(it->second, v);
+        }
+    }
+    cb_tile* t = new cb_tile();
+    t->m = rl; t->n = cl; t->val_dtype = vdt;
+    std::vector<std::pair<std::pair<int64_t, int64_t>, std::vector<unsigned char>>> trip(acc.begin(), acc.end());
+    build_csr(t, trip);
+    *tile = t;
+    return CB_OK;
+}
 int cb_tile_free(cb_tile* t) { delete t; return CB_OK; }
 int cb_tile_info(const cb_tile* t, int64_t info[8]) {
     std::memset(info, 0, 8 * sizeof(int64_t));

@@ -74,6 +74,39 @@ def main():
         if a.no_cache_a:
             ctx.summa_cache_a(False)
     failures = 0
+    if a.mode == "gpu":
+        # distributed ingestion (cb_tile_from_distributed_coo): every rank hands in a slice of the triples - owned by anybody, with
+        # duplicates across ranks - and must end up with exactly its block, duplicates merged by the rule asked for
+        Vg = O.matrix_values(I, J, n, 5, np.float64)
+        dupI, dupJ = I[::7], J[::7]                                           # every 7th entry a second time, with another value
+        allI, allJ = np.concatenate([I, dupI]), np.concatenate([J, dupJ])
+        allV = np.concatenate([Vg, Vg[::7] + 1.0])
+        r0_, rl_ = cb.capi.block_range(m, pr, myrow)
+        c0_, cl_ = cb.capi.block_range(n, pc, mycol)
+        for dup_op, name in ((2, "max"), (1, "sum")):
+            t = ctx.tile_from_distributed_coo(m, n, allI[rank::world], allJ[rank::world], allV[rank::world], dup_op)
+            rp, cc, vv = t.to_csr(np.float64)
+            t.free()
+            want = {}
+            for i_, j_, v_ in zip(allI.tolist(), allJ.tolist(), allV.tolist()):
+                if r0_ <= i_ < r0_ + rl_ and c0_ <= j_ < c0_ + cl_:
+                    k_ = (i_ - r0_, j_ - c0_)
+                    want[k_] = v_ if k_ not in want else (max(want[k_], v_) if dup_op == 2 else want[k_] + v_)
+            got = dict(zip(zip(np.repeat(np.arange(rl_), np.diff(rp)).tolist(), cc.tolist()), vv.tolist()))
+            ok_ing = got == want
+            flags = [None] * world if rank == 0 else None
+            dist.gather_object(ok_ing, flags, dst=0)
+            if rank == 0:
+                print(f"[summa gpu {pr}x{pc}] distributed ingestion ({name} of duplicates): {'every block right' if all(flags) else 'WRONG'}", flush=True)
+                failures += 0 if all(flags) else 1
+        tp = ctx.tile_from_distributed_coo(m, n, allI[rank::world], allJ[rank::world], None, 0)
+        ok_pat = tp.nnz == len(set(k_ for k_ in zip(allI.tolist(), allJ.tolist()) if r0_ <= k_[0] < r0_ + rl_ and c0_ <= k_[1] < c0_ + cl_))
+        tp.free()
+        flags = [None] * world if rank == 0 else None
+        dist.gather_object(ok_pat, flags, dst=0)
+        if rank == 0 and not all(flags):
+            print(f"[summa gpu {pr}x{pc}] distributed ingestion (pattern): WRONG", flush=True)
+            failures += 1
     for case in a.cases.split(","):
         sr, adt, xdt, kind = CASES[case]
         V = None if adt is None else O.matrix_values(I, J, n, 7, adt)
