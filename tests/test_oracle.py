@@ -168,3 +168,32 @@ def test_live_reference_spmv_path_agrees():
     a, _ = O.ref_spmm(O.MIN_PLUS, 200, 180, I, J, V, X, via=0)
     b, _ = O.ref_spmm(O.MIN_PLUS, 200, 180, I, J, V, X, via=1)
     assert np.array_equal(a, b) and np.array_equal(a, O.spmm(O.MIN_PLUS, 200, 180, I, J, V, X))
+
+
+def test_c_restatement_of_the_generators_matches_numpy():
+    """oracle/gen_oracle.c (what bench.py's CPU legs build full-size operands with) against the numpy recipes, bit for bit:
+    matrices (symmetrised R-MAT, directed ER; row-major and column-major order), matrix values, panel columns."""
+    for sc, sym, init in [(11, True, (0.57, 0.19, 0.19, 0.05)), (12, False, (0.25, 0.25, 0.25, 0.25))]:
+        n, I, J = O.rmat_matrix(sc, 16, 3, init, symmetric=sym)
+        n2, I2, J2 = O.rmat_matrix_fast(sc, 16, 3, init, symmetric=sym)
+        assert n == n2 and np.array_equal(I, I2) and np.array_equal(J, J2)
+        _, I3, J3 = O.rmat_matrix_fast(sc, 16, 3, init, symmetric=sym, col_major=True)
+        o = np.lexsort((I, J))
+        assert np.array_equal(I[o], I3) and np.array_equal(J[o], J3)
+        for dt in (np.float32, np.float64, np.int32, np.int64):
+            assert np.array_equal(O.matrix_values(I, J, n, 1, dt), O.matrix_values_fast(I, J, n, 1, dt))
+        for dt, kind in ((np.float32, "value"), (np.float64, "value"), (np.int32, "x_minplus"), (np.uint8, "value")):
+            assert np.array_equal(O.dense_operand(n, 24, 42, dt, kind)[:, 8:16], O.dense_columns_fast(n, 24, 8, 8, 42, dt, kind))
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref (compiled reference) not present")
+def test_resident_reference_matrix_equals_the_one_shot_call():
+    """cbref_matrix_* (one SpParMat, many Mult_AnXBn_Synch calls: bench.py's CPU legs) gives what cbref_spmm gives."""
+    n, I, J = O.rmat_matrix_fast(10, 8, 0, col_major=True)
+    V = O.matrix_values_fast(I, J, n, 1, np.float64)
+    X = O.dense_operand(n, 5, 42, np.float64)
+    A = O.RefMatrix(O.PLUS_TIMES, n, n, I, J, V, np.float64, colmajor_sorted=True)
+    Y, sec, nnzc = A.mult(X)
+    A.free()
+    Y2, _ = O.ref_spmm(O.PLUS_TIMES, n, n, I, J, V, X)
+    assert np.array_equal(Y, Y2) and sec > 0 and nnzc == (Y2 != 0).sum()
