@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the hub variant declines tiles whose hub columns serve too few nonzeros; the small matrices of tests/test_new_variants_gpu.py must
+# run it anyway.  The library reads the threshold once per process, at its first multiply, so it is set before anything is loaded.
+os.environ.setdefault("CB_SPMM_HUB_MIN_COVER_PCT", "0")
 
 
 def pytest_configure(config):
