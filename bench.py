@@ -205,6 +205,7 @@ def reference_sample(w, total_budget_s, reps, log=None):
     sr = {"plus_times": O.PLUS_TIMES, "min_plus": O.MIN_PLUS, "or_and": O.OR_AND, "select_max": O.MAX_SEL2ND}[w["sr"]]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     xdt = NPDT[w["xdt"]]
+    O.set_num_threads(cores)                       # torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm uses the host's cores
     n, I, J = O.rmat_matrix_fast(w["scale"], w["ef"], SEED_GRAPH, INITIATOR[w["gen"]], symmetric=w["sym"], col_major=True)
     nnz_full = len(I)
     # the reference parallelises over the columns of the right-hand side (mtSpGEMM.h:292 omp for): give it one per thread

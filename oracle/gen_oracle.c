@@ -72,6 +72,8 @@ static int radix_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int bits) {
 }
 
 void oracle_free(void* p) { free(p); }
+/* launchers such as torch.distributed.run export OMP_NUM_THREADS=1: the CPU legs of bench.py ask for the host's cores explicitly */
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* oracle.py rmat_matrix(): n = 2^scale; edges -> drop self loops -> optional (A + A^T) -> merge duplicates.
  * thr[3] = the 16-bit quadrant thresholds round(a*65536), round((a+b)*65536), round((a+b+c)*65536) (computed by the caller

@@ -85,6 +85,8 @@ def lib():
                                         POINTER(c_void_p), POINTER(c_void_p)]
         L.oracle_free.restype = None
         L.oracle_free.argtypes = [c_void_p]
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [c_int]
         L.oracle_matrix_values.restype = None
         L.oracle_matrix_values.argtypes = [c_void_p, c_void_p, c_int64, c_int64, ctypes.c_uint64, c_int, c_void_p]
         L.oracle_dense_columns.restype = None
@@ -539,6 +541,11 @@ def rmat_matrix(scale, edgefactor=16, seed=0, initiator=(0.57, 0.19, 0.19, 0.05)
 def _thresholds(initiator):
     a, b, c, _ = initiator
     return np.array([int(round(a * 65536)), int(round((a + b) * 65536)), int(round((a + b + c) * 65536))], np.uint32)
+
+
+def set_num_threads(n):
+    """OpenMP threads of the C restatement (a launcher may have exported OMP_NUM_THREADS=1)"""
+    lib().oracle_set_num_threads(int(n))
 
 
 def rmat_matrix_fast(scale, edgefactor=16, seed=0, initiator=(0.57, 0.19, 0.19, 0.05), symmetric=True, remove_loops=True,
