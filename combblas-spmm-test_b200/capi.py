@@ -23,7 +23,7 @@ SYMBOLS = ["cb_abi_version", "cb_device_count", "cb_comm_unique_id", "cb_ctx_cre
            "cb_tile_free", "cb_tile_info", "cb_tile_pattern_view", "cb_tile_download_csr", "cb_dense_alloc", "cb_dense_wrap", "cb_dense_free",
            "cb_dense_upload", "cb_dense_download", "cb_dense_fill", "cb_dense_info", "cb_semiring_id", "cb_spmm_local",
            "cb_spmm_summa", "cb_summa_times", "cb_summa_plan", "cb_summa_cache_a", "cb_comm_allreduce_i64", "cb_spmm_host", "cb_launch_count", "cb_profile_enable", "cb_profile_read", "cb_gen_rmat_tile", "cb_gen_dense",
-           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe", "cb_spmm_k2_l2", "cb_spgemm_local", "cb_spgemm_summa", "cb_coo_info", "cb_coo_download", "cb_coo_free", "cb_spmv_grid", "cb_gen_graph500_edges", "cb_gen_graph500_tile", "cb_tile_from_distributed_coo"]
+           "cb_spmm_hub_config", "cb_spmm_hub_info", "cb_hub_select_host", "cb_spmm_ring_config", "cb_tile_filter_columns", "cb_spmm_k2_config", "cb_tile_row_lengths", "cb_tile_download_rows", "cb_dense_download_rows", "cb_spmm_summa_host", "cb_spmm_k2_pipe", "cb_spmm_k2_l2", "cb_spgemm_local", "cb_spgemm_summa", "cb_coo_info", "cb_coo_download", "cb_coo_free", "cb_spmv_grid", "cb_gen_graph500_edges", "cb_gen_graph500_tile", "cb_tile_from_distributed_coo", "cb_tile_from_mm_text"]
 
 
 class CBError(RuntimeError):
@@ -113,6 +113,7 @@ def lib():
         L.cb_coo_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
         L.cb_coo_free.argtypes = [c_void_p]
         L.cb_tile_from_distributed_coo.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]
+        L.cb_tile_from_mm_text.argtypes = [c_void_p, c_int64, c_int64, ctypes.c_char_p, c_int64, c_int, c_int, c_int, POINTER(c_void_p)]
         L.cb_spmv_grid.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_int64]
         L.cb_gen_graph500_edges.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int64, c_int64, c_void_p, c_void_p]
         L.cb_gen_graph500_tile.argtypes = [c_void_p, c_int, c_int, c_uint64, c_uint64, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int,
@@ -257,6 +258,13 @@ class Context:
         vd, v = _vals(vals)
         t = c_void_p()
         _check(lib().cb_tile_from_distributed_coo(self.h, gm, gn, len(rows), _ptr(rows), _ptr(cols), _ptr(v), vd, dup_op, byref(t)), self.h)
+        return Tile(self, t)
+
+    def tile_from_mm_text(self, gm, gn, text: bytes, onebased=True, pattern=False, symmetric=False, val_dtype=PATTERN, dup_op=2):
+        """collective: this rank's share of the data lines of a Matrix Market file, parsed, routed and merged on the GPUs"""
+        flags = (1 if onebased else 0) | (2 if pattern else 0) | (4 if symmetric else 0)
+        t = c_void_p()
+        _check(lib().cb_tile_from_mm_text(self.h, gm, gn, text, len(text), flags, val_dtype, dup_op, byref(t)), self.h)
         return Tile(self, t)
 
     def tile_from_device_coo(self, m, n, nz, d_rows, d_cols, d_vals=None, val_dtype=PATTERN):

@@ -213,3 +213,5 @@ int cb_p2p_finish(cb_ctx* ctx, cudaStream_t compute);
 void cb_p2p_release(cb_ctx* ctx);
 int cb_p2p_debug_times(cb_ctx* ctx, cudaEvent_t origin, float* t_start, float* t_end);
 int cb_nccl_allgather_col(cb_ctx* ctx, const void* send_host, void* recv_host, size_t bytes);
+int cb_ingest_device_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* d_rows, const int64_t* d_cols, const void* d_vals,
+                         int val_dtype, int dup_op, cb_tile** out);

@@ -1004,7 +1004,30 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
     if (val_dtype != CB_PATTERN && !vs) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_tile_from_distributed_coo: value dtype %d", val_dtype);
     if (vs && nz > 0 && !vals) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: null values");
     if (nz >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_distributed_coo: %lld triples on one rank", (long long)nz);
-    if (dup_op < 0 || dup_op > 3) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: duplicate rule %d", dup_op);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    cb_scratch sc;
+    const int64_t cap = std::max<int64_t>(nz, 1);
+    int64_t *d_rows = nullptr, *d_cols = nullptr;
+    char* d_vals = nullptr;
+    CB_CUDA(ctx, sc.alloc(&d_rows, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_cols, (size_t)cap));
+    if (vs) CB_CUDA(ctx, sc.alloc(&d_vals, (size_t)cap * vs));
+    if (nz > 0) {
+        CB_CUDA(ctx, cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_cols, cols, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
+        if (vs) CB_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, vs * (size_t)nz, cudaMemcpyHostToDevice, st));
+    }
+    return cb_ingest_device_coo(ctx, gm, gn, nz, d_rows, d_cols, d_vals, val_dtype, dup_op, out);
+}
+
+}  // extern "C"
+// the same with the triples already on the device (cb_tile_from_mm_text parses them there); d_vals may be NULL for CB_PATTERN
+int cb_ingest_device_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* d_rows, const int64_t* d_cols, const void* d_vals_in,
+                         int val_dtype, int dup_op, cb_tile** out) {
+    *out = nullptr;
+    const size_t vs = val_dtype == CB_PATTERN ? 0 : cb_dtype_size(val_dtype);
+    if (nz >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "distributed ingestion: %lld triples on one rank", (long long)nz);
+    if (dup_op < 0 || dup_op > 3) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "distributed ingestion: duplicate rule %d", dup_op);
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute;
     const int pr = ctx->pr, pc = ctx->pc, np = ctx->nranks, sm = ctx->sm_count;
@@ -1013,22 +1036,19 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
     block_range(gn, pc, ctx->myproccol, &c0, &cl);
     cb_scratch sc;
     const int64_t cap = std::max<int64_t>(nz, 1);
-    int64_t *d_rows = nullptr, *d_cols = nullptr, *d_start = nullptr;
-    char *d_vals = nullptr, *d_vals_routed = nullptr;
+    const char* d_vals = (const char*)d_vals_in;
+    int64_t* d_start = nullptr;
+    char* d_vals_routed = nullptr;
     uint32_t *d_owner = nullptr, *d_owner_sorted = nullptr, *d_perm = nullptr, *d_perm_sorted = nullptr;
     uint64_t *d_key = nullptr, *d_key_routed = nullptr;
     unsigned int* d_bad = nullptr;
-    CB_CUDA(ctx, sc.alloc(&d_rows, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_cols, (size_t)cap));
     CB_CUDA(ctx, sc.alloc(&d_owner, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_owner_sorted, (size_t)cap));
     CB_CUDA(ctx, sc.alloc(&d_perm, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_perm_sorted, (size_t)cap));
     CB_CUDA(ctx, sc.alloc(&d_key, (size_t)cap)); CB_CUDA(ctx, sc.alloc(&d_key_routed, (size_t)cap));
     CB_CUDA(ctx, sc.alloc(&d_start, (size_t)np + 1)); CB_CUDA(ctx, sc.alloc(&d_bad, 1));
-    if (vs) { CB_CUDA(ctx, sc.alloc(&d_vals, (size_t)cap * vs)); CB_CUDA(ctx, sc.alloc(&d_vals_routed, (size_t)cap * vs)); }
+    if (vs) CB_CUDA(ctx, sc.alloc(&d_vals_routed, (size_t)cap * vs));
     CB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), st));
     if (nz > 0) {
-        CB_CUDA(ctx, cudaMemcpyAsync(d_rows, rows, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
-        CB_CUDA(ctx, cudaMemcpyAsync(d_cols, cols, sizeof(int64_t) * (size_t)nz, cudaMemcpyHostToDevice, st));
-        if (vs) CB_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, vs * (size_t)nz, cudaMemcpyHostToDevice, st));
         owner_kernel<<<grid_for(nz, sm), 256, 0, st>>>(d_rows, d_cols, nz, gm, gn, pr, pc, d_owner, d_key, d_bad);
         iota32_kernel<<<grid_for(nz, sm), 256, 0, st>>>(d_perm, nz);
         CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
@@ -1058,7 +1078,7 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
     // every rank must learn about a bad triple anywhere before anyone blocks in the exchange
     int64_t anybad = bad;
     CB_TRY(cb_comm_allreduce_i64(ctx, 0, 1, &anybad, 1));
-    if (anybad) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_tile_from_distributed_coo: a triple lies outside the %lld x %lld matrix", (long long)gm, (long long)gn);
+    if (anybad) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "distributed ingestion: a triple lies outside the %lld x %lld matrix", (long long)gm, (long long)gn);
     // counts[q * np + r] = triples rank q holds for rank r
     std::vector<int64_t> counts((size_t)np * np, 0);
     for (int q = 0; q < np; ++q) counts[(size_t)ctx->rank * np + q] = start[(size_t)q + 1] - start[(size_t)q];
@@ -1074,7 +1094,7 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
     int64_t nrecv = 0;
     std::vector<int64_t> roff((size_t)np + 1, 0);
     for (int q = 0; q < np; ++q) { roff[(size_t)q] = nrecv; nrecv += counts[(size_t)q * np + ctx->rank]; }
-    if (nrecv >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_distributed_coo: %lld triples for one tile", (long long)nrecv);
+    if (nrecv >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "distributed ingestion: %lld triples for one tile", (long long)nrecv);
     const int64_t rcap = std::max<int64_t>(nrecv, 1);
     uint64_t *d_rkey = nullptr, *d_rkey_sorted = nullptr;
     char *d_rval = nullptr, *d_rval_sorted = nullptr;
@@ -1144,7 +1164,6 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
 }
 
 // byte allgather over the processor column with host buffers (set-up traffic of the peer transport)
-}  // extern "C"
 int cb_nccl_allgather_col(cb_ctx* ctx, const void* send_host, void* recv_host, size_t bytes) {
     const int np = ctx->pr;
     if (np == 1) { memcpy(recv_host, send_host, bytes); return CB_OK; }

@@ -165,10 +165,9 @@ public:
         }
         return true;
     }
-    // this process's share of a Matrix Market file: the lines that START inside its byte range of the data section
+    // this process's share of a Matrix Market file: the text of the lines that START inside its byte range of the data section
     // (the reference's split, SpParMat.cpp:4010-4080: every process reads fsize / nprocs bytes and finishes its last line)
-    static bool ReadMMShare(const std::string& filename, bool onebased, int rank, int nranks, IT& tm, IT& tn, std::vector<int64_t>& rows,
-                            std::vector<int64_t>& cols, std::vector<ST>& vals) {
+    static bool ReadMMShareText(const std::string& filename, int rank, int nranks, IT& tm, IT& tn, bool& pattern, bool& symmetric, std::string& text) {
         std::ifstream in(filename, std::ios::binary);
         if (!in) return false;
         std::string line;
@@ -176,8 +175,8 @@ public:
         std::string banner = line;
         for (auto& ch : banner) ch = (char)std::tolower(ch);
         const bool hasbanner = banner.compare(0, 14, "%%matrixmarket") == 0;
-        const bool pattern = hasbanner && banner.find("pattern") != std::string::npos;
-        const bool symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
+        pattern = hasbanner && banner.find("pattern") != std::string::npos;
+        symmetric = hasbanner && (banner.find("symmetric") != std::string::npos || banner.find("hermitian") != std::string::npos);
         if (hasbanner) std::getline(in, line);
         while (!line.empty() && line[0] == '%' && std::getline(in, line)) {}
         long long m_ = 0, n_ = 0, nz_ = 0;
@@ -187,18 +186,42 @@ public:
         in.seekg(0, std::ios::end);
         const std::streamoff fsize = in.tellg();
         const std::streamoff len = fsize - data0;
-        const std::streamoff lo = data0 + len * rank / nranks, hi = data0 + len * (rank + 1) / nranks;
+        std::streamoff lo = data0 + len * rank / nranks, hi = data0 + len * (rank + 1) / nranks;
         in.clear();
-        in.seekg(lo);
-        if (lo > data0) {                       // a line that started before lo belongs to the previous process
-            in.seekg(lo - 1);
+        // a line that started before a boundary belongs to the process on its left: move both ends to the next line start
+        auto next_line_start = [&](std::streamoff pos) -> std::streamoff {
+            if (pos <= data0) return data0;
+            if (pos >= fsize) return fsize;
+            in.clear();
+            in.seekg(pos - 1);
             char c;
             in.get(c);
-            if (c != '\n') std::getline(in, line);
+            if (c == '\n') return pos;
+            std::string skipped;
+            std::getline(in, skipped);
+            return in.eof() ? fsize : (std::streamoff)in.tellg();
+        };
+        lo = next_line_start(lo);
+        hi = next_line_start(hi);
+        text.assign((size_t)std::max<std::streamoff>(hi - lo, 0), '\0');
+        if (hi > lo) {
+            in.clear();
+            in.seekg(lo);
+            in.read(&text[0], hi - lo);
         }
+        return true;
+    }
+    // the same share as 0-based triples parsed on the host (lines without two integers are skipped, like the reference's sscanf loop)
+    static bool ReadMMShare(const std::string& filename, bool onebased, int rank, int nranks, IT& tm, IT& tn, std::vector<int64_t>& rows,
+                            std::vector<int64_t>& cols, std::vector<ST>& vals) {
+        bool pattern = false, symmetric = false;
+        std::string text;
+        if (!ReadMMShareText(filename, rank, nranks, tm, tn, pattern, symmetric, text)) return false;
+        std::istringstream in(text);
+        std::string line;
         long long ii, jj;
         double vv = 1;
-        while (in && (std::streamoff)in.tellg() < hi && std::getline(in, line)) {
+        while (std::getline(in, line)) {
             if (line.empty()) continue;
             std::istringstream ls(line);
             if (!(ls >> ii >> jj)) continue;
@@ -214,18 +237,22 @@ public:
     template <typename T> struct dup_rule<cb_sum<T>> { static const int value = 1; };
     template <typename T> struct dup_rule<std::plus<T>> { static const int value = 1; };
 
-    // ParallelReadMM (SpParMat.cpp:3978-4115): every process parses its own byte range of the file; the triples travel to
-    // their owners between the GPUs and are merged and turned into the tile there (cb_tile_from_distributed_coo) - the host
-    // tile is only materialised when somebody asks for seq().  A merge rule the device does not know (anything but maximum /
-    // plus) takes the replicated host path: every process reads the whole file and keeps what it owns.
+    // ParallelReadMM (SpParMat.cpp:3978-4115): every process reads its own byte range of the file; the text is cut into lines
+    // and parsed on its GPU, the triples travel to their owners between the GPUs and are merged and turned into the tile there
+    // (cb_tile_from_mm_text) - the host tile is only materialised when somebody asks for seq().  A file with numbers the device
+    // parser does not reproduce exactly (it says so on every rank), a boolean matrix read from a file with values, or
+    // CB_READMM_HOSTPARSE=1 parse on the host and hand the triples to the same routing (cb_tile_from_distributed_coo).  A merge
+    // rule the device does not know (anything but maximum / plus) takes the replicated host path: every process reads the
+    // whole file and keeps what it owns.
     template <typename BinOp = maximum<NT>>
     void ParallelReadMM(const std::string& filename, bool onebased, BinOp binop = BinOp()) {
         static const bool replicated = std::getenv("CB_READMM_REPLICATED") && std::atoi(std::getenv("CB_READMM_REPLICATED")) != 0;
+        static const bool hostparse = std::getenv("CB_READMM_HOSTPARSE") && std::atoi(std::getenv("CB_READMM_HOSTPARSE")) != 0;
         if (dup_rule<BinOp>::value >= 0 && !replicated) {
             IT tm = 0, tn = 0;
-            std::vector<int64_t> rows, cols;
-            std::vector<ST> vals;
-            const bool found = ReadMMShare(filename, onebased, commGrid->GetRank(), commGrid->GetSize(), tm, tn, rows, cols, vals);
+            bool pattern = false, symmetric = false;
+            std::string text;
+            const bool found = ReadMMShareText(filename, commGrid->GetRank(), commGrid->GetSize(), tm, tn, pattern, symmetric, text);
             if (commGrid->MinWorld(found ? 1 : 0) == 0) {
                 SpParHelper::Print("COMBBLAS: Matrix-market file " + filename + " can not be found\n");
                 MPI_Abort(MPI_COMM_WORLD, NOFILE);
@@ -235,13 +262,29 @@ public:
             gm = tm; gn = tn;
             cb_ctx* ctx = commGrid->GetContext();
             int vd = cb_dtype_of<NT>::value;
-            if (std::is_same<NT, bool>::value) {             // a boolean matrix whose stored entries are all true is a pattern
-                const bool alltrue = std::all_of(vals.begin(), vals.end(), [](ST v) { return v != 0; });
-                if (commGrid->MinWorld(alltrue ? 1 : 0) == 1) vd = CB_PATTERN;
+            bool done = false;
+            if (!hostparse && (!std::is_same<NT, bool>::value || pattern)) {
+                if (std::is_same<NT, bool>::value) vd = CB_PATTERN;
+                const int flags = (onebased ? 1 : 0) | (pattern ? 2 : 0) | (symmetric ? 4 : 0);
+                const int status = cb_tile_from_mm_text(ctx, (int64_t)gm, (int64_t)gn, text.data(), (int64_t)text.size(), flags, vd,
+                                                        dup_rule<BinOp>::value, &dtile);
+                if (status == CB_OK) done = true;
+                else if (status != CB_ERR_UNSUPPORTED) cb_check(status, ctx, "cb_tile_from_mm_text");
+                else SpParHelper::Print("COMBBLAS: " + filename + " holds numbers outside the device parser's exact range, parsing it on the host\n");
             }
-            cb_check(cb_tile_from_distributed_coo(ctx, (int64_t)gm, (int64_t)gn, (int64_t)rows.size(), rows.data(), cols.data(),
-                                                  vd == CB_PATTERN ? nullptr : (const void*)vals.data(), vd, dup_rule<BinOp>::value, &dtile),
-                     ctx, "cb_tile_from_distributed_coo");
+            if (!done) {
+                std::vector<int64_t> rows, cols;
+                std::vector<ST> vals;
+                ReadMMShare(filename, onebased, commGrid->GetRank(), commGrid->GetSize(), tm, tn, rows, cols, vals);
+                vd = cb_dtype_of<NT>::value;
+                if (std::is_same<NT, bool>::value) {             // a boolean matrix whose stored entries are all true is a pattern
+                    const bool alltrue = std::all_of(vals.begin(), vals.end(), [](ST v) { return v != 0; });
+                    if (commGrid->MinWorld(alltrue ? 1 : 0) == 1) vd = CB_PATTERN;
+                }
+                cb_check(cb_tile_from_distributed_coo(ctx, (int64_t)gm, (int64_t)gn, (int64_t)rows.size(), rows.data(), cols.data(),
+                                                      vd == CB_PATTERN ? nullptr : (const void*)vals.data(), vd, dup_rule<BinOp>::value, &dtile),
+                         ctx, "cb_tile_from_distributed_coo");
+            }
             int64_t info[8];
             cb_tile_info(dtile, info);
             dnnz = info[0];

@@ -111,6 +111,18 @@ int cb_tile_from_device_coo(cb_ctx* ctx, int64_t m, int64_t n, int64_t nz, const
  * rank's tile is built on the device.  Collective over the grid. */
 int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz, const int64_t* rows, const int64_t* cols, const void* vals,
                                  int val_dtype, int dup_op, cb_tile** tile);
+/* the same with the PARSING on the device too.  Replaces SpParMat::ParallelReadMM's per-process text handling
+ * (include/CombBLAS/SpParMat.cpp:4010-4095 + SpHelper.h:75-91,147-183): `text` is this rank's share of the data section of a
+ * Matrix Market coordinate file - the bytes of the lines that start inside its byte range, host memory - and is cut into lines
+ * and parsed on the GPU, one thread per line.  flags: 1 = the indices are one-based, 2 = pattern file (no value column, every
+ * entry 1), 4 = symmetric / hermitian (the transpose of every off-diagonal entry is added).  Blank lines and lines that do not
+ * start with two integers are skipped, like the reference's sscanf loop does.  Values are converted to val_dtype with a C cast
+ * (CB_U8: value != 0).  Returns CB_ERR_UNSUPPORTED on every rank, before anything is exchanged, when any share holds a number the
+ * device parser does not convert (more than 19 significant digits, a subnormal or overflowing value, inf / nan, hexadecimal);
+ * everything else is the correctly rounded double strtod gives.  The caller then parses that file on the host and uses
+ * cb_tile_from_distributed_coo.  Collective. */
+int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const char* text, int64_t nbytes, int flags, int val_dtype, int dup_op,
+                         cb_tile** tile);
 int cb_tile_free(cb_tile* tile);
 /* {nnz, m, n, nonempty rows, nonempty columns, work chunks, split rows, bytes resident} */
 int cb_tile_info(const cb_tile* tile, int64_t info[8]);

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <cmath>
 #include <map>
 #include <string>
 #include <thread>
@@ -274,6 +275,58 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
     build_csr(t, trip);
     *tile = t;
     return CB_OK;
+}
+int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const char* text, int64_t nbytes, int flags, int vdt, int dup_op, cb_tile** tile) {
+    // host restatement of the device parser's contract: lines -> triples (strtoll / strtod), numbers with more than 19 significant
+    // digits refused on every rank, then the distributed ingestion above
+    std::vector<int64_t> rows, cols;
+    std::vector<double> vv;
+    int64_t hard = 0;
+    const char* p = text;
+    const char* end = text + nbytes;
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        const std::string line(p, nl ? nl : end);
+        p = nl ? nl + 1 : end;
+        char* q = nullptr;
+        const char* c = line.c_str();
+        const long long ii = std::strtoll(c, &q, 10);
+        if (q == c) continue;
+        const char* c2 = q;
+        const long long jj = std::strtoll(c2, &q, 10);
+        if (q == c2) continue;
+        double v = 1.0;
+        if (!(flags & 2)) {
+            const char* c3 = q;
+            v = std::strtod(c3, &q);
+            if (q == c3) { ++hard; continue; }
+            int sig = 0;
+            bool nz = false;
+            for (const char* d = c3; d < q && *d != 'e' && *d != 'E'; ++d)
+                if (*d >= '0' && *d <= '9' && (nz || *d != '0')) { nz = true; ++sig; }
+            if (sig > 19 || std::isinf(v) || std::isnan(v)) { ++hard; continue; }
+        }
+        const int64_t r = ii - ((flags & 1) ? 1 : 0), cc = jj - ((flags & 1) ? 1 : 0);
+        rows.push_back(r); cols.push_back(cc); vv.push_back(v);
+        if ((flags & 4) && r != cc) { rows.push_back(cc); cols.push_back(r); vv.push_back(v); }
+    }
+    std::vector<unsigned char> mine;
+    put<int64_t>(mine, hard);
+    std::vector<std::vector<unsigned char>> all;
+    mock_allgatherv(ctx, mine, all);
+    for (const auto& b : all) { size_t off = 0; if (take<int64_t>(b, off) != 0) return fail(ctx, CB_ERR_UNSUPPORTED, "mock ABI: numbers outside the device parser's exact range"); }
+    const size_t es = vdt == CB_PATTERN ? 0 : esize(vdt);
+    std::vector<unsigned char> vals(rows.size() * es);
+    for (size_t k = 0; k < rows.size() && es; ++k) {
+        switch (vdt) {
+            case CB_F32: { float x = (float)vv[k]; std::memcpy(&vals[k * es], &x, es); break; }
+            case CB_F64: { double x = vv[k]; std::memcpy(&vals[k * es], &x, es); break; }
+            case CB_I32: { int32_t x = (int32_t)vv[k]; std::memcpy(&vals[k * es], &x, es); break; }
+            case CB_I64: { int64_t x = (int64_t)vv[k]; std::memcpy(&vals[k * es], &x, es); break; }
+            default: { uint8_t x = vv[k] != 0.0; std::memcpy(&vals[k * es], &x, es); break; }
+        }
+    }
+    return cb_tile_from_distributed_coo(ctx, gm, gn, (int64_t)rows.size(), rows.data(), cols.data(), es ? (const void*)vals.data() : nullptr, vdt, dup_op, tile);
 }
 int cb_tile_free(cb_tile* t) { delete t; return CB_OK; }
 int cb_tile_info(const cb_tile* t, int64_t info[8]) {

@@ -107,6 +107,26 @@ def main():
         if rank == 0 and not all(flags):
             print(f"[summa gpu {pr}x{pc}] distributed ingestion (pattern): WRONG", flush=True)
             failures += 1
+        # the same from TEXT (cb_tile_from_mm_text): every rank hands in the lines that start inside its byte range of one Matrix
+        # Market data section; parsed, routed and merged on the GPUs
+        lines = "".join(f"{i_ + 1} {j_ + 1}\t{v_!r}\n" for i_, j_, v_ in zip(allI.tolist(), allJ.tolist(), allV.tolist())).encode()
+        lo_, hi_ = len(lines) * rank // world, len(lines) * (rank + 1) // world
+        lo_ = lo_ if lo_ == 0 or lines[lo_ - 1:lo_] == b"\n" else lines.index(b"\n", lo_) + 1
+        hi_ = hi_ if hi_ == len(lines) or lines[hi_ - 1:hi_] == b"\n" else lines.index(b"\n", hi_) + 1
+        t = ctx.tile_from_mm_text(m, n, lines[lo_:hi_], val_dtype=cb.F64, dup_op=2)
+        rp, cc, vv = t.to_csr(np.float64)
+        t.free()
+        want = {}
+        for i_, j_, v_ in zip(allI.tolist(), allJ.tolist(), allV.tolist()):
+            if r0_ <= i_ < r0_ + rl_ and c0_ <= j_ < c0_ + cl_:
+                k_ = (i_ - r0_, j_ - c0_)
+                want[k_] = v_ if k_ not in want else max(want[k_], v_)
+        got = dict(zip(zip(np.repeat(np.arange(rl_), np.diff(rp)).tolist(), cc.tolist()), vv.tolist()))
+        flags = [None] * world if rank == 0 else None
+        dist.gather_object(got == want, flags, dst=0)
+        if rank == 0:
+            print(f"[summa gpu {pr}x{pc}] Matrix Market text shares parsed on the device: {'every block right' if all(flags) else 'WRONG'}", flush=True)
+            failures += 0 if all(flags) else 1
     for case in a.cases.split(","):
         sr, adt, xdt, kind = CASES[case]
         V = None if adt is None else O.matrix_values(I, J, n, 7, adt)

@@ -94,6 +94,43 @@ def test_matrix_market_round_trip_on_2x2_processes(driver, tmp_path):
     assert len(got) == len(want) and all(a[:2] == b[:2] and abs(a[2] - b[2]) <= 1e-15 * abs(b[2]) for a, b in zip(got, want))
 
 
+def messy_matrix_market(path, hard):
+    """a general real file the way tools in the wild write them: tabs, CRLF, blank and comment lines between the entries, signs,
+    exponents, leading zeros and dots - and, with `hard`, one value with more digits than the device parser reproduces exactly"""
+    rng = np.random.default_rng(5)
+    m, n = 37, 29
+    cells = rng.choice(m * n, 300, replace=False)
+    toks = []
+    for q, c in enumerate(cells):
+        v = rng.standard_normal() * 10.0 ** int(rng.integers(-8, 9))
+        toks.append([f"{v:.17g}", f"{v:.6e}", f"{v:+.3f}", f"{int(v * 100) / 100:g}", f"{abs(v):.0f}.", f"0{abs(v):.2f}", f"{v:.10E}"][q % 7])
+    if hard:
+        toks[11] = "0.1234567890123456789012345"
+    with open(path, "w", newline="") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% a comment\n")
+        f.write(f"{m} {n} {len(cells)}\n")
+        for q, (c, t) in enumerate(zip(cells, toks)):
+            sep, eol = ("\t", "\r\n") if q % 3 == 0 else ("  ", "\n") if q % 3 == 1 else (" ", " \n")
+            f.write(f"{c // n + 1}{sep}{c % n + 1}{sep}{t}{eol}")
+            if q % 50 == 7:
+                f.write("\n% a comment in the data section\n")
+    return m, n, sorted((int(c // n), int(c % n), float(t)) for c, t in zip(cells, toks))
+
+
+@pytest.mark.parametrize("hard", [False, True])
+def test_matrix_market_text_share_parser(driver, tmp_path, hard):
+    # every process hands its byte range of the file to cb_tile_from_mm_text; a number outside the parser's exact range sends
+    # every process to the host parser instead - the same matrix either way, value for value what float() reads
+    mtx = str(tmp_path / "messy.mtx")
+    m, n, want = messy_matrix_market(mtx, hard)
+    so, se = run_grid(driver, 4, tmp_path / "rdv", "mtx", mtx, 8, str(tmp_path / "y.bin"), str(tmp_path / "copy.mtx"))
+    assert "Matrix Market round trip working correctly" in se
+    assert ("parsing it on the host" in so + se) == hard
+    rows = [l.split() for l in open(tmp_path / "copy.mtx").read().splitlines()[2:]]
+    got = sorted((int(r[0]) - 1, int(r[1]) - 1, float(r[2])) for r in rows)
+    assert got == want
+
+
 def test_spmv_fullydistvec_and_dense_epilogues(driver):
     r = run(driver, "spmv", 8)
     assert "SpMV and dense epilogues working correctly" in r.stderr and "rows reached" in r.stdout

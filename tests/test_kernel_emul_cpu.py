@@ -21,3 +21,14 @@ def test_k2_and_fixup_on_the_warp_emulator_under_asan(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "emulation ok" in r.stdout and "mismatches=0" in r.stdout and "runtime error" not in r.stderr
     assert r.stdout.count("mismatches=0") == 60 and "differs from K2" not in r.stdout     # 12 K2 + 6 narrow + 7 K2 with entry prefetch + 14 K2P + 4 K2P with L2 hints + 8 K2H + 9 K2R cases (argument 2 = a second seed)
+
+
+def test_device_number_parser_against_strtod(tmp_path):
+    """csrc/cb_mmparse.cuh (the decimal -> double conversion of the device Matrix Market reader) compiled as plain C++ under UBSan:
+    every string it accepts must give strtod's bits - random doubles in the formats matrix files use, 19-digit mantissas over
+    the whole exponent range, exact round-to-even ties."""
+    exe = str(tmp_path / "mmparse_host")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-o", exe,
+                           f"{ROOT}/tests/emul/mmparse_host.cpp"], timeout=600)
+    r = subprocess.run([exe, "400000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mismatches 0 " in r.stdout and "runtime error" not in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
