@@ -671,7 +671,9 @@ int cb_spmm_summa_host(cb_ctx* ctx, const cb_tile* tile, const void* X_host, int
     const int64_t per16 = 16 / (int64_t)es;
     const int64_t per = pc > 1 ? gk / pc : gk;                       // width of every k-block but the last
     static const int want = getenv("CB_HOST_SLABS") ? atoi(getenv("CB_HOST_SLABS")) : 4;
-    const int64_t min_cols = std::max<int64_t>(per16, 128 / (int64_t)es);
+    // slab width: 256 bytes of every row when the k-block has at least two of them, else 128 (profiles/r02_pcie_probe.jsonl: with
+    // both directions busy 2D copies of 256-byte rows run at 48 / 50 GB/s, of 128-byte rows at 35 / 41, of 64-byte rows at 27 / 18)
+    const int64_t min_cols = std::max<int64_t>(per16, (per * (int64_t)es >= 512 ? 256 : 128) / (int64_t)es);
     int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, CB_MAX_SLABS), per / min_cols));
     const int64_t slab_cols = per > 0 ? ((per + nslab - 1) / nslab + per16 - 1) / per16 * per16 : 0;
     if (slab_cols > 0) nslab = (int)((per + slab_cols - 1) / slab_cols);
