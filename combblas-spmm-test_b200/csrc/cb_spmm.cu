@@ -125,7 +125,7 @@ int cb_spmm_k2_l2(cb_ctx* ctx, int budget_mb) {
 
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth) {
     if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: null ctx");
-    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth)", depth);
+    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8 && depth != 16) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth, 16 bulk-copy ring)", depth);
     ctx->k2_pipe = depth;
     return CB_OK;
 }

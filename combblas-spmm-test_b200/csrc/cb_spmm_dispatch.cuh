@@ -2,6 +2,7 @@
 #pragma once
 #include "cb_hub.cuh"
 #include "cb_spmm_hub_kernel.cuh"
+#include "cb_spmm_tma_kernel.cuh"
 
 #ifndef CB_WIDE_U
 #define CB_WIDE_U 4
@@ -107,6 +108,56 @@ template <class Op, int VW, int R, int U, int MINB>
 static int launch_pf(const LaunchParams& p) {
     if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true, 2>(p);
     return launch_layout_f<Op, VW, R, U, MINB, false, 2>(p);
+}
+
+// K2T: row gathers as bulk asynchronous copies into a per-warp shared-memory ring (cb_spmm_tma_kernel.cuh).  Only for the operand
+// types the benchmark workloads use (every instantiation costs compile time); anything else reports CB_HUB_FALLBACK -> K2.
+template <class Op, int VW>
+static int launch_tma(const LaunchParams& p) {
+    typedef typename Op::T T;
+    constexpr bool built = Op::akind == A_SAME && (std::is_same<T, float>::value || std::is_same<T, int32_t>::value);
+    if constexpr (!built) return CB_HUB_FALLBACK;
+    else {
+        if (p.total_row_bytes != VW * 16) return CB_HUB_FALLBACK;
+        const int stages_env = getenv("CB_TMA_STAGES") ? atoi(getenv("CB_TMA_STAGES")) : 0;
+        const int warps_env = getenv("CB_TMA_WARPS") ? atoi(getenv("CB_TMA_WARPS")) : 0;
+        const cb_tile* t = p.t;
+        SpmmArgs a;
+        a.colflag = t->colflag;
+        a.vals = t->vals;
+        a.nzrows = t->nzrows;
+        a.chunk_start = t->chunk_start;
+        a.chunk_row = t->chunk_row;
+        a.nchunks = t->nchunks;
+        a.X = (const char*)p.X;
+        a.Y = (char*)p.Y;
+        a.ldx_bytes = p.ldx_bytes;
+        a.ldy_bytes = p.ldy_bytes;
+        a.slab_bytes = VW * 16;
+        a.row_bytes = a.slab_bytes;
+        a.total_row_bytes = p.total_row_bytes;
+        a.carry = (char*)t->carry;
+        a.carry_stride = p.total_row_bytes;
+        a.accumulate = p.accumulate;
+        a.hubcls = nullptr;
+        a.cls_max = -1;
+        const int stages = stages_env == 2 || stages_env == 4 ? stages_env : (VW == 32 ? 2 : 4);
+        const size_t per_warp = (size_t)stages * 32 * VW * 16 + (size_t)stages * 8;
+        int warps = warps_env > 0 ? warps_env : (int)std::min<size_t>(12, (200 * 1024) / per_warp);
+        warps = std::max(1, std::min(warps, 12));
+        const size_t smem = per_warp * (size_t)warps;
+        auto kernel = stages == 2 ? cb_spmm_tma_kernel<Op, VW, 2, 8> : cb_spmm_tma_kernel<Op, VW, 4, 8>;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return CB_HUB_FALLBACK; }
+        const int64_t per_block = (int64_t)warps * (32 / VW);
+        dim3 grid((unsigned)((t->nchunks + per_block - 1) / per_block));
+        {
+            cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
+            kernel<<<grid, warps * 32, smem, p.stream>>>(a);
+        }
+        CB_LAUNCHED(p.ctx);
+        CB_CUDA(p.ctx, cudaGetLastError());
+        return CB_OK;
+    }
 }
 
 // K2H / K2R: persistent CTAs (one per SM) in clusters that pool their shared memory for the hub rows; dynamic chunks
@@ -215,7 +266,11 @@ static int launch_op(const LaunchParams& p) {
             const int pipe = p.pipe >= 0 ? p.pipe : (pipe_env >= 0 ? pipe_env : CB_PIPE_DEFAULT);
             constexpr bool W64 = sizeof(typename Op::T) == 8;
             (void)W64;
-            if (pipe == 1 && nvec > 4) {
+            if (pipe == 16 && slab_force < 16 && (nvec == 8 || nvec == 16 || nvec == 32)) {
+                s = nvec == 8 ? launch_tma<Op, 8>(p) : nvec == 16 ? launch_tma<Op, 16>(p) : launch_tma<Op, 32>(p);
+            }
+            if (s != CB_HUB_FALLBACK) {
+            } else if (pipe == 1 && nvec > 4) {
                 if (nvec <= 8) s = wide ? launch_pf<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 8, 1, CB_DEEP_U, DB>(p);
                 else if (nvec <= 16) s = wide ? launch_pf<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 16, 1, CB_DEEP_U, DB>(p);
                 else if (nvec <= 32) s = wide ? launch_pf<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_pf<Op, 32, 1, CB_DEEP_U, DB>(p);

@@ -266,8 +266,10 @@ int cb_spmm_ring_config(cb_ctx* ctx, int depth);
  * as the layout allows; 64, 128, 256, 512); point = 0 deep / 1 wide / -1 chosen from the footprint of the X rows.  Results
  * do not depend on either (columns are independent). */
 int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point);
-/* Ring depth of the pipelined local multiply (K2P, csrc/cb_spmm_kernel.cuh): every lane keeps `depth` row gathers in flight
- * in a register ring; 4 or 8, 0 = the round-1 walk (gathers in groups), -1 = the build's default.  Results are identical. */
+/* Variant of the local multiply, for experiments (results are identical bit for bit): 0 = K2 (gathers in groups, the default),
+ * 1 = K2 with the entry prefetch, 16 = K2T (every row gather one cp.async.bulk copy into a per-warp shared-memory ring with
+ * mbarrier completion, csrc/cb_spmm_tma_kernel.cuh; fp32 / int32 panels of 128-, 256- or 512-byte rows, anything else runs K2),
+ * 4 / 8 = ring depth of K2P (register ring; only in builds with -DCB_BUILD_K2P), -1 = the build's default. */
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth);
 /* L2 residency hints of K2P for tiles whose X rows do not fit in L2: the rows of the tile's most used columns - as many as
  * fit `budget_mb` megabytes at the current row width - are gathered with the evict_last priority, every other row with

@@ -75,6 +75,36 @@ def run(ctx, case, cluster, slab, scale=12, k=64, ring=0):
         assert np.array_equal(b, ref)
 
 
+@pytest.mark.parametrize("case,k,stages,warps", [("pt_f32", 128, 2, 6), ("pt_f32", 128, 2, 3), ("pt_f32", 64, 4, 6), ("pt_f32", 64, 2, 12),
+                                                 ("pt_f32", 32, 4, 12), ("minplus_i32", 32, 2, 5), ("minplus_i32", 64, 4, 6), ("pt_f32", 48, 2, 6)])
+def test_bulk_copy_ring_matches_k2_bitwise(ctx, monkeypatch, case, k, stages, warps):
+    """K2T (csrc/cb_spmm_tma_kernel.cuh): row gathers as cp.async.bulk copies into a per-warp shared-memory ring with mbarrier
+    completion.  Same walk as K2, so the same bits, overwrite and accumulate, split rows included; a width the variant does not
+    cover (k = 48: not a power-of-two row) must quietly run K2.  Opt-in (cb_spmm_k2_pipe(ctx, 16)): measured 1.5-2.4x slower than
+    K2 (profiles/r02_sweep_d_tma.jsonl)."""
+    monkeypatch.setenv("CB_TMA_STAGES", str(stages))
+    monkeypatch.setenv("CB_TMA_WARPS", str(warps))
+    sr, adt, xdt, kind = CASES[case]
+    n, I, J = O.rmat_matrix(13, 16, seed=0)
+    V = O.matrix_values(I, J, n, 1, adt)
+    X = O.dense_operand(n, k, 42, xdt, kind)
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    Xd, Y0, Y1 = ctx.dense_from(X), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt)
+    try:
+        ctx.k2_pipe(0)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y0, sr, accumulate=acc)
+        ctx.k2_pipe(16)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y1, sr, accumulate=acc)
+        a, b = Y0.download(), Y1.download()
+    finally:
+        ctx.k2_pipe(-1)
+        for h in (t, Xd, Y0, Y1):
+            h.free()
+    assert t is not None and a.tobytes() == b.tobytes(), "the bulk-copy ring differs from K2"
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 def test_hub_matches_k2_bitwise_fp32(ctx, cluster):
     run(ctx, "pt_f32", cluster, 0)

@@ -49,6 +49,9 @@ for name in a.workloads:
                 ctx.k2_config(o.get("slab", 0), o.get("point", -1)); ctx.k2_pipe(1)
             elif kind == "pipe":
                 ctx.k2_config(o.get("slab", 0), -1); ctx.k2_pipe(o.get("d", 4)); ctx.k2_l2(o.get("l2", 0))
+            elif kind == "tma":                      # bulk-copy ring (K2T): s = stages (2 / 4), w = warps per CTA
+                os.environ["CB_TMA_STAGES"] = str(o.get("s", 0)); os.environ["CB_TMA_WARPS"] = str(o.get("w", 0))
+                ctx.k2_pipe(16)
             elif kind == "hub":
                 ctx.hub_config(1, o.get("c", 4), o.get("slab", 0)); ctx.ring_config(o.get("ring", 0))
             elif kind == "ring":
