@@ -42,7 +42,10 @@ struct cb_ctx {
     int hub_enable = -1, hub_cluster = 0, hub_slab_bytes = 0;
     int ring_depth = -1;              // K2R ring depth: -1 = follow CB_SPMM_RING, 0 = off (cb_spmm_ring_config)
     int k2_l2_mb = -1;                // K2P L2 residency hints: budget in MB for the rows kept with evict_last; 0 off, -1 default
-    int k2_pipe = -1;                 // K2P ring depth: -1 default, 0 round-1 walk, 4, 8
+    int k2_pipe = -1;                 // variant of the local multiply: -1 default, 0 K2, 1 prefetch, 4 / 8 K2P ring depth, 16 K2T, 32 K2W
+    void* win_panel = nullptr;        // K2W: packed rows of the most used columns, kept in L2 by a persisting access-policy window
+    size_t win_panel_bytes = 0;
+    size_t win_l2_limit = 0;          // persisting L2 set-aside currently configured on the device
     int k2_slab_bytes = 0, k2_point = -1;   // plain K2: column-slab width (0 = automatic) and operating point (cb_spmm_k2_config)
     std::string err;
 };

@@ -114,6 +114,7 @@ int cb_ctx_destroy(cb_ctx* c) {
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->ws_x);
     cudaFree(c->ws_y);
+    cudaFree(c->win_panel);
     if (c->h2d) {
         cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h);
         cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h);

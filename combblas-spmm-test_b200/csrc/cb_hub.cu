@@ -17,6 +17,12 @@ struct cb_hub {
     double last_cover = 0;
     uint8_t* hubcls = nullptr;        // [nnz] device: floor(log2(rank + 1)) of the nonzero's column by descending use, 255 = used once
     bool cls_built = false;
+    // K2W (hub panel under a persisting L2 window): the column stream with the columns of the win_h most used columns replaced
+    // by bit 30 + their rank, and the columns themselves by rank
+    int32_t* win_colflag = nullptr;   // [nnz] device
+    int32_t* win_cols = nullptr;      // [win_h] device
+    int64_t win_h = 0, win_want = -1;
+    double win_cover = 0;
 };
 
 void cb_hub_release(cb_tile* t) {
@@ -25,6 +31,8 @@ void cb_hub_release(cb_tile* t) {
     cudaFree(t->hub->hubcols);
     cudaFree(t->hub->counters);
     cudaFree(t->hub->hubcls);
+    cudaFree(t->hub->win_colflag);
+    cudaFree(t->hub->win_cols);
     delete t->hub;
     t->hub = nullptr;
 }
@@ -94,6 +102,103 @@ int cb_hubcls_get(cb_ctx* ctx, const cb_tile* tile, const uint8_t** cls) {
         h->cls_built = true;
     }
     *cls = h->hubcls;
+    return CB_OK;
+}
+
+// ---- K2W: hub rows in a compact panel that a persisting L2 access-policy window keeps on the chip
+__global__ void __launch_bounds__(256)
+cb_win_rank_kernel(const int32_t* __restrict__ cols_sorted, int64_t h, int32_t* __restrict__ rank_of_col) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < h; r += (int64_t)gridDim.x * blockDim.x) rank_of_col[cols_sorted[r]] = (int32_t)r;
+}
+__global__ void __launch_bounds__(256)
+cb_win_remap_kernel(const int32_t* __restrict__ colflag, int64_t nnz, const int32_t* __restrict__ rank_of_col, int32_t* __restrict__ out,
+                    unsigned long long* __restrict__ covered) {
+    unsigned long long mine = 0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t cf = colflag[p];
+        const int32_t r = rank_of_col[cf & 0x7fffffff];
+        out[p] = r >= 0 ? (int32_t)(((uint32_t)cf & 0x80000000u) | 0x40000000u | (uint32_t)r) : cf;
+        mine += r >= 0;
+    }
+    mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(covered, mine);
+}
+// rows of the hub columns, packed: panel[r] = X[cols[r]] (row_vecs 16-byte vectors each)
+__global__ void __launch_bounds__(256)
+cb_win_gather_kernel(const char* __restrict__ X, int64_t ldx_bytes, const int32_t* __restrict__ cols, int64_t h, int row_vecs, char* __restrict__ panel) {
+    const int64_t total = h * row_vecs;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = v / row_vecs;
+        const int q = (int)(v - r * row_vecs);
+        reinterpret_cast<uint4*>(panel + r * ldx_bytes)[q] = __ldg(reinterpret_cast<const uint4*>(X + (int64_t)cols[r] * ldx_bytes) + q);
+    }
+}
+
+// the remapped column stream for the `want` most used columns (fewer when the tile has fewer columns used twice or more);
+// *h == 0: nothing to keep.  Built lazily, rebuilt when `want` changes; owned tiles with n < 2^30 only.
+int cb_hubwin_get(cb_ctx* ctx, const cb_tile* tile, int64_t want, const int32_t** colflag_w, const int32_t** cols, int64_t* h_out, double* cover) {
+    *colflag_w = nullptr; *cols = nullptr; *h_out = 0;
+    if (cover) *cover = 0;
+    if (!tile->owns_slab || tile->nnz == 0 || tile->n >= (1LL << 30) || want <= 0) return CB_OK;
+    cb_tile* t = const_cast<cb_tile*>(tile);
+    if (!t->hub) t->hub = new cb_hub();
+    cb_hub* h = t->hub;
+    if (h->win_want != want) {
+        cudaFree(h->win_cols); h->win_cols = nullptr;
+        h->win_h = 0; h->win_want = want;
+        cb_scratch sc;
+        int *d_counts = nullptr, *d_counts_sorted = nullptr;
+        int32_t *d_cols = nullptr, *d_cols_sorted = nullptr, *d_rank = nullptr;
+        unsigned long long* d_cov = nullptr;
+        CB_CUDA(ctx, sc.alloc(&d_counts, (size_t)t->n)); CB_CUDA(ctx, sc.alloc(&d_counts_sorted, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_cols, (size_t)t->n)); CB_CUDA(ctx, sc.alloc(&d_cols_sorted, (size_t)t->n));
+        CB_CUDA(ctx, sc.alloc(&d_rank, (size_t)t->n)); CB_CUDA(ctx, sc.alloc(&d_cov, 1));
+        CB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)t->n * sizeof(int), ctx->compute));
+        CB_CUDA(ctx, cudaMemsetAsync(d_rank, 0xff, (size_t)t->n * sizeof(int32_t), ctx->compute));
+        CB_CUDA(ctx, cudaMemsetAsync(d_cov, 0, sizeof(unsigned long long), ctx->compute));
+        const unsigned blocks = (unsigned)std::min<int64_t>((t->nnz + 255) / 256, (int64_t)ctx->sm_count * 16);
+        const unsigned nblocks = (unsigned)std::min<int64_t>((t->n + 255) / 256, (int64_t)ctx->sm_count * 16);
+        cb_hub_count_kernel<<<blocks, 256, 0, ctx->compute>>>(t->colflag, t->nnz, d_counts);
+        cb_iota_kernel<<<nblocks, 256, 0, ctx->compute>>>(d_cols, t->n);
+        CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+        size_t tmp_bytes = 0;
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_counts, d_counts_sorted, d_cols, d_cols_sorted, (int)t->n, 0, 32, ctx->compute));
+        char* tmp = nullptr;
+        CB_CUDA(ctx, sc.alloc(&tmp, tmp_bytes));
+        CB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, d_counts, d_counts_sorted, d_cols, d_cols_sorted, (int)t->n, 0, 32, ctx->compute));
+        // columns used once have nothing to share: cut the list where the counts drop below two
+        int64_t hh = std::min<int64_t>(want, t->n);
+        std::vector<int> top((size_t)hh);
+        CB_CUDA(ctx, cudaMemcpyAsync(top.data(), d_counts_sorted, (size_t)hh * sizeof(int), cudaMemcpyDeviceToHost, ctx->compute));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+        hh = std::partition_point(top.begin(), top.end(), [](int c) { return c >= 2; }) - top.begin();
+        if (hh > 0) {
+            if (!h->win_colflag) {
+                cudaError_t e = cudaMalloc((void**)&h->win_colflag, (size_t)t->nnz * sizeof(int32_t));
+                if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%lld) for the remapped column stream: %s", (long long)t->nnz * 4, cudaGetErrorString(e));
+            }
+            CB_CUDA(ctx, cudaMalloc((void**)&h->win_cols, (size_t)hh * sizeof(int32_t)));
+            CB_CUDA(ctx, cudaMemcpyAsync(h->win_cols, d_cols_sorted, (size_t)hh * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->compute));
+            cb_win_rank_kernel<<<(unsigned)std::min<int64_t>((hh + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->compute>>>(d_cols_sorted, hh, d_rank);
+            cb_win_remap_kernel<<<blocks, 256, 0, ctx->compute>>>(t->colflag, t->nnz, d_rank, h->win_colflag, d_cov);
+            CB_LAUNCHED(ctx); CB_LAUNCHED(ctx);
+            CB_CUDA(ctx, cudaGetLastError());
+            unsigned long long cov = 0;
+            CB_CUDA(ctx, cudaMemcpyAsync(&cov, d_cov, sizeof cov, cudaMemcpyDeviceToHost, ctx->compute));
+            CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+            h->win_cover = (double)cov / (double)t->nnz;
+        }
+        h->win_h = hh;
+    }
+    if (h->win_h > 0) { *colflag_w = h->win_colflag; *cols = h->win_cols; *h_out = h->win_h; if (cover) *cover = h->win_cover; }
+    return CB_OK;
+}
+int cb_hubwin_gather(cb_ctx* ctx, cudaStream_t stream, const void* X, int64_t ldx_bytes, const int32_t* cols, int64_t h, int row_bytes, void* panel) {
+    const int64_t total = h * (row_bytes / 16);
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    cb_win_gather_kernel<<<blocks, 256, 0, stream>>>((const char*)X, ldx_bytes, cols, h, row_bytes / 16, (char*)panel);
+    CB_LAUNCHED(ctx);
+    CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
 }
 

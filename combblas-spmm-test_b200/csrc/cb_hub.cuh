@@ -30,6 +30,9 @@ struct HubPlan {
 // per-nonzero use class of its column, for the L2 residency hints of K2P (built lazily, owned tiles only); *cls == nullptr when
 // the tile cannot have one
 int cb_hubcls_get(cb_ctx* ctx, const cb_tile* tile, const uint8_t** cls);
+// K2W: the column stream with the `want` most used columns replaced by bit 30 + rank, those columns by rank, and the packing of their X rows
+int cb_hubwin_get(cb_ctx* ctx, const cb_tile* tile, int64_t want, const int32_t** colflag_w, const int32_t** cols, int64_t* h, double* cover);
+int cb_hubwin_gather(cb_ctx* ctx, cudaStream_t stream, const void* X, int64_t ldx_bytes, const int32_t* cols, int64_t h, int row_bytes, void* panel);
 int cb_hub_plan(cb_ctx* ctx, const cb_tile* tile, int64_t row_bytes, cudaStream_t stream, cbk::HubPlan* plan);
 void cb_hub_release(cb_tile* tile);
 extern "C" int cb_hub_select_host(const int32_t* counts, int64_t n, int max_hubs, int32_t* hubcols, int64_t* cum);

@@ -101,6 +101,61 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
             if (c < 0) p.hubcls = nullptr;
         }
     }
+    // K2W (opt-in, cb_spmm_k2_pipe(ctx, 32)): the rows of the most used columns - as many as fit the budget (cb_spmm_k2_l2, default
+    // 64 MB) - are packed into one panel that a persisting L2 access-policy window keeps on the chip for the duration of the multiply
+    bool win_on = false;
+    {
+        static const int pipe_env = getenv("CB_K2_PIPE") ? atoi(getenv("CB_K2_PIPE")) : -1;
+        const int pipe = ctx->k2_pipe >= 0 ? ctx->k2_pipe : pipe_env;
+        const int mb = ctx->k2_l2_mb > 0 ? ctx->k2_l2_mb : 64;
+        if (pipe == 32 && stream == ctx->compute && ldx * (int64_t)es == row_bytes && row_bytes >= 256 && (dtype == CB_F32 || dtype == CB_F64) &&
+            semiring == CB_PLUS_TIMES && akind == cbk::A_SAME) {
+            const int32_t* wcols = nullptr;
+            int64_t h = 0;
+            CB_TRY(cb_hubwin_get(ctx, t, (int64_t)mb * (1 << 20) / row_bytes, &p.win_colflag, &wcols, &h, nullptr));
+            if (p.win_colflag) {
+                const size_t need = (size_t)h * (size_t)row_bytes;
+                if (ctx->win_panel_bytes < need) {
+                    if (ctx->win_panel) { CB_CUDA(ctx, cudaStreamSynchronize(stream)); CB_CUDA(ctx, cudaFree(ctx->win_panel)); ctx->win_panel = nullptr; ctx->win_panel_bytes = 0; }
+                    cudaError_t e = cudaMalloc(&ctx->win_panel, need);
+                    if (e != cudaSuccess) return cb_fail(ctx, CB_ERR_ALLOC, "cudaMalloc(%zu) for the hub panel: %s", need, cudaGetErrorString(e));
+                    ctx->win_panel_bytes = need;
+                }
+                cudaDeviceProp prop;
+                static int max_persist = -1, max_window = -1;
+                if (max_persist < 0) {
+                    CB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+                    max_persist = prop.persistingL2CacheMaxSize;
+                    max_window = prop.accessPolicyMaxWindowSize;
+                }
+                const size_t limit = std::min<size_t>(need, (size_t)max_persist);
+                if (ctx->win_l2_limit != limit) { CB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, limit)); ctx->win_l2_limit = limit; }
+                CB_TRY(cb_hubwin_gather(ctx, stream, X, ldx * (int64_t)es, wcols, h, (int)row_bytes, ctx->win_panel));
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof attr);
+                attr.accessPolicyWindow.base_ptr = ctx->win_panel;
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(need, (size_t)max_window);
+                attr.accessPolicyWindow.hitRatio = limit >= need ? 1.0f : (float)((double)limit / (double)need);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                CB_CUDA(ctx, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+                p.win_delta = (const char*)ctx->win_panel - (const char*)X;
+                win_on = true;
+            }
+        }
+    }
+    struct WinOff {                               // the window must not outlive the multiply
+        cudaStream_t s; bool on;
+        ~WinOff() {
+            if (!on) return;
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.num_bytes = 0;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+    } win_off{stream, win_on};
     cbk::HubPlan hub_plan;                        // opt-in persistent variants K2H / K2R (cb_hub.cu); inactive -> plain K2
     CB_TRY(cb_hub_plan(ctx, t, row_bytes, stream, &hub_plan));
     if (hub_plan.active) p.hub = &hub_plan;
@@ -125,7 +180,7 @@ int cb_spmm_k2_l2(cb_ctx* ctx, int budget_mb) {
 
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth) {
     if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: null ctx");
-    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8 && depth != 16) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth, 16 bulk-copy ring)", depth);
+    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8 && depth != 16 && depth != 32) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth, 16 bulk-copy ring, 32 hub panel under an L2 window)", depth);
     ctx->k2_pipe = depth;
     return CB_OK;
 }

@@ -45,11 +45,13 @@ struct LaunchParams {
     const uint8_t* hubcls = nullptr; // non-null: K2P gathers rows of columns of class <= cls_max with evict_last, others evict_first
     int cls_max = -1;
     int pipe = -1;                  // register-ring depth of the pipelined walk K2P: 4 or 8; 0 = the round-1 walk; -1 = default
+    const int32_t* win_colflag = nullptr;   // non-null: K2W - this column stream (hub columns as bit 30 + rank) and the packed hub panel at X + win_delta
+    int64_t win_delta = 0;
 };
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
-template <class Op, int VW, int R, int U, int MINB, bool FULL, int PIPE = 0, bool POL = false>      // PIPE: 0 K2, 1 K2P (ring), 2 K2 with prefetch
+template <class Op, int VW, int R, int U, int MINB, bool FULL, int PIPE = 0, bool POL = false>      // PIPE: 0 K2, 1 K2P (ring), 2 K2 with prefetch, 3 K2W (hub panel)
 static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -71,6 +73,8 @@ static int launch_layout_f(const LaunchParams& p) {
     a.accumulate = p.accumulate;
     a.hubcls = p.hubcls;
     a.cls_max = p.cls_max;
+    a.win_delta = 0;
+    if constexpr (PIPE == 3) { a.colflag = p.win_colflag; a.win_delta = p.win_delta; }
     constexpr int NV = 32 / VW;
     const int64_t vws_per_block = 8 * NV;
     dim3 grid((unsigned)((t->nchunks + vws_per_block - 1) / vws_per_block), (unsigned)((p.total_row_bytes + a.slab_bytes - 1) / a.slab_bytes));
@@ -78,6 +82,7 @@ static int launch_layout_f(const LaunchParams& p) {
         cb_prof_scope prof(p.ctx, p.stream, CB_PROF_SPMM);
         if constexpr (PIPE == 1) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL, POL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
         else if constexpr (PIPE == 2) cb_spmm_kernel<Op, VW, R, U, MINB, FULL, true><<<grid, 256, 0, p.stream>>>(a);
+        else if constexpr (PIPE == 3) cb_spmm_kernel<Op, VW, R, U, MINB, FULL, false, true><<<grid, 256, 0, p.stream>>>(a);
         else cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
@@ -108,6 +113,18 @@ template <class Op, int VW, int R, int U, int MINB>
 static int launch_pf(const LaunchParams& p) {
     if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true, 2>(p);
     return launch_layout_f<Op, VW, R, U, MINB, false, 2>(p);
+}
+
+// K2W: K2 reading the rows of the most used columns from a packed panel under a persisting L2 window (fp32 / fp64 PlusTimes only)
+template <class Op, int VW, int R, int U, int MINB>
+static int launch_win(const LaunchParams& p) {
+    typedef typename Op::T T;
+    constexpr bool built = Op::akind == A_SAME && (std::is_same<T, float>::value || std::is_same<T, double>::value);
+    if constexpr (!built) return CB_HUB_FALLBACK;
+    else {
+        if (p.total_row_bytes % (VW * R * 16) != 0) return CB_HUB_FALLBACK;
+        return launch_layout_f<Op, VW, R, U, MINB, true, 3>(p);
+    }
 }
 
 // K2T: row gathers as bulk asynchronous copies into a per-warp shared-memory ring (cb_spmm_tma_kernel.cuh).  Only for the operand
@@ -266,7 +283,11 @@ static int launch_op(const LaunchParams& p) {
             const int pipe = p.pipe >= 0 ? p.pipe : (pipe_env >= 0 ? pipe_env : CB_PIPE_DEFAULT);
             constexpr bool W64 = sizeof(typename Op::T) == 8;
             (void)W64;
-            if (pipe == 16 && slab_force < 16 && (nvec == 8 || nvec == 16 || nvec == 32)) {
+            if (p.win_colflag && slab_force < 16 && nvec >= 16) {
+                if (nvec == 16) s = launch_win<Op, 16, 1, CB_DEEP_U, DB>(p);
+                else if (nvec == 32) s = launch_win<Op, 32, 1, CB_DEEP_U, DB>(p);
+                else if (nvec == 64) s = launch_win<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
+            } else if (pipe == 16 && slab_force < 16 && (nvec == 8 || nvec == 16 || nvec == 32)) {
                 s = nvec == 8 ? launch_tma<Op, 8>(p) : nvec == 16 ? launch_tma<Op, 16>(p) : launch_tma<Op, 32>(p);
             }
             if (s != CB_HUB_FALLBACK) {

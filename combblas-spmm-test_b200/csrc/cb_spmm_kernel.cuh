@@ -182,6 +182,9 @@ struct SpmmArgs {
     // use (255 = used once); columns of class <= cls_max are gathered with evict_last, all others with evict_first
     const uint8_t* __restrict__ hubcls;
     int cls_max;
+    // K2W: entries with bit 30 set carry the RANK of a much used column instead of the column; their rows sit in a packed panel
+    // (kept in L2 by a persisting access-policy window) at X + win_delta, same row stride
+    int64_t win_delta;
 };
 
 // One lane's share of a panel row: R vectors at byte offsets (vl + r*VW)*16.
@@ -251,7 +254,8 @@ __device__ __forceinline__ Vec16<T> ld_hub16(const HubSrc& hub, uint32_t rank, i
 // PF  : the (column, value) entries of step s+1 are loaded while step s is processed, and the lines of both streams that will
 //       be read PF_AHEAD entries later are pulled into L2 now - the profile of the round-1 kernel showed 27 % of the stall
 //       samples on exactly these two loads (profiles/r02_*): they stream from DRAM once and nothing else hides them.
-template <class Op, int VW, int R, int U, bool FULL, bool HUB, bool PF = false>
+// WIN : K2W - entries flagged with bit 30 are gathered from the packed hub panel at X + win_delta (SpmmArgs).
+template <class Op, int VW, int R, int U, bool FULL, bool HUB, bool PF = false, bool WIN = false>
 __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t chunk, const HubSrc& hub) {
     typedef typename Op::T T;
     typedef typename Op::TA TA;
@@ -381,7 +385,8 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
-                    const char* xr = xbase + (uint64_t)c * ldx;
+                    const char* xr = xbase + (uint64_t)(WIN ? (c & 0x3fffffffu) : c) * ldx;
+                    if (WIN && (c & 0x40000000u)) xr += a.win_delta;
                     const int h = HUB ? __shfl_sync(0xffffffffu, hs, j0 + u, VW) : 0xffff;
 #pragma unroll
                     for (int r = 0; r < R; ++r)
@@ -394,7 +399,8 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t c = __shfl_sync(0xffffffffu, cm, j0 + u, VW);
-                    const char* xr = xbase + (uint64_t)c * ldx;
+                    const char* xr = xbase + (uint64_t)(WIN ? (c & 0x3fffffffu) : c) * ldx;
+                    if (WIN && (c & 0x40000000u)) xr += a.win_delta;
                     const int h = HUB ? __shfl_sync(0xffffffffu, hs, j0 + u, VW) : 0xffff;
 #pragma unroll
                     for (int r = 0; r < R; ++r)
@@ -432,12 +438,12 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
 }
 
 // K2: one chunk per virtual warp, grid sized to the chunk count
-template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PF = false>
+template <class Op, int VW, int R, int U, int MINB, bool FULL, bool PF = false, bool WIN = false>
 __global__ void __launch_bounds__(256, MINB)
 cb_spmm_kernel(const SpmmArgs a) {
     constexpr int NV = 32 / VW;                       // virtual warps per warp
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    cb_spmm_walk<Op, VW, R, U, FULL, false, PF>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
+    cb_spmm_walk<Op, VW, R, U, FULL, false, PF, WIN>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -105,6 +105,44 @@ def test_bulk_copy_ring_matches_k2_bitwise(ctx, monkeypatch, case, k, stages, wa
     assert t is not None and a.tobytes() == b.tobytes(), "the bulk-copy ring differs from K2"
 
 
+@pytest.mark.parametrize("dtype,k,mb", [(np.float32, 128, 1), (np.float32, 64, 1), (np.float64, 128, 2), (np.float64, 64, 1), (np.float32, 128, 64),
+                                        (np.float32, 96, 1)])
+def test_hub_panel_under_l2_window_matches_k2_bitwise(ctx, dtype, k, mb):
+    """K2W (cb_spmm_k2_pipe(ctx, 32) + cb_spmm_k2_l2(ctx, mb)): the rows of the most used columns are packed into a panel that a
+    persisting L2 access-policy window keeps on the chip; the column stream carries bit 30 + rank for them.  Same walk, same
+    bits - overwrite and accumulate, a budget smaller and larger than the columns worth keeping, two panels of different width on
+    the same tile (the remapped stream is rebuilt), and a width the variant does not cover (k = 96) quietly on K2.  Opt-in:
+    DRAM traffic -25 % on R-MAT s24 but no time gained (profiles/r02_ncu_l2window_s24f32.csv)."""
+    n, I, J = O.rmat_matrix(13, 16, seed=0)
+    V = O.matrix_values(I, J, n, 1, dtype)
+    X = O.dense_operand(n, k, 42, dtype, "value")
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    Xd, Y0, Y1 = ctx.dense_from(X), ctx.dense(n, k, dtype), ctx.dense(n, k, dtype)
+    try:
+        ctx.k2_pipe(0)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y0, O.PLUS_TIMES, accumulate=acc)
+        ctx.k2_l2(mb)
+        ctx.k2_pipe(32)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y1, O.PLUS_TIMES, accumulate=acc)
+        a, b = Y0.download(), Y1.download()
+        X2 = O.dense_operand(n, k // 2, 7, dtype, "value")           # another width on the same tile: another number of hub rows
+        X2d, Z0, Z1 = ctx.dense_from(X2), ctx.dense(n, k // 2, dtype), ctx.dense(n, k // 2, dtype)
+        ctx.spmm_local(t, X2d, Z1, O.PLUS_TIMES)
+        ctx.k2_pipe(0)
+        ctx.spmm_local(t, X2d, Z0, O.PLUS_TIMES)
+        c, d = Z0.download(), Z1.download()
+        for h in (X2d, Z0, Z1):
+            h.free()
+    finally:
+        ctx.k2_pipe(-1)
+        ctx.k2_l2(-1)
+        for h in (t, Xd, Y0, Y1):
+            h.free()
+    assert a.tobytes() == b.tobytes() and c.tobytes() == d.tobytes(), "the hub-panel variant differs from K2"
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 def test_hub_matches_k2_bitwise_fp32(ctx, cluster):
     run(ctx, "pt_f32", cluster, 0)
