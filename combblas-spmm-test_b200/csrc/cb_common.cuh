@@ -118,6 +118,8 @@ struct cb_tile {
     // my whole block-row of A regrouped by the X row block it multiplies (one tile per processor row), built from the
     // own + cached parts at the second multiply; entries stay NULL where a single existing part already is that tile
     std::vector<cb_tile*> summa_merged;
+    std::vector<cb_tile*> spgemm_remote;   // sparse x sparse stage loop: A parts of my row neighbours kept after the first product (cb_summa_cache_a)
+    std::vector<char> spgemm_sent;         // ... and, for the parts I root, whether the neighbours already hold them
     // most frequent columns and the per-nonzero hub ranks, built at the first hub multiply (cb_hub.cu); owned tiles only
     cb_hub* hub = nullptr;
 };

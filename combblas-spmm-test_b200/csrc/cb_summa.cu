@@ -431,6 +431,9 @@ int cb_spmm_summa(cb_ctx* ctx, const cb_tile* tile, const cb_dense* X, cb_dense*
         mt->summa_remote.clear();
         for (cb_tile* p : mt->summa_merged) cb_tile_free(p);
         mt->summa_merged.clear();
+        for (cb_tile* p : mt->spgemm_remote) cb_tile_free(p);
+        mt->spgemm_remote.clear();
+        mt->spgemm_sent.clear();
         mt->summa_parts.assign(ns, nullptr);
         for (int s = 0; s < ns; ++s) {
             if (S->a_root[s] != ctx->myproccol) continue;
@@ -789,6 +792,9 @@ int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semirin
         mt->summa_remote.clear();
         for (cb_tile* p : mt->summa_merged) cb_tile_free(p);
         mt->summa_merged.clear();
+        for (cb_tile* p : mt->spgemm_remote) cb_tile_free(p);
+        mt->spgemm_remote.clear();
+        mt->spgemm_sent.clear();
         mt->summa_parts.assign(ns, nullptr);
         for (int s = 0; s < ns; ++s) {
             if (a_root[s] != ctx->myproccol) continue;
@@ -800,6 +806,15 @@ int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semirin
         if (ctx->summa_state) ((SummaState*)ctx->summa_state)->meta_tile = nullptr;
     }
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    // A parts of my row neighbours stay on this GPU after the first product with this tile (tiles are immutable), like in the dense
+    // stage loop; cb_summa_cache_a(ctx, 0) re-sends them every call, which is what the reference's broadcasts do.  Every rank of a
+    // processor row has the same call history, so root and receivers agree on which parts have travelled.
+    const bool cache = ctx->summa_cache_a && pc > 1;
+    if (!cache || (int)mt->spgemm_remote.size() != ns) {
+        for (cb_tile* p : mt->spgemm_remote) cb_tile_free(p);
+        mt->spgemm_remote.assign(cache ? ns : 0, nullptr);
+        mt->spgemm_sent.assign(cache ? ns : 0, 0);
+    }
     cb_spgemm_acc acc;
     int status = CB_OK;
     for (int r = 0; r < pr && status == CB_OK; ++r) {
@@ -816,8 +831,27 @@ int cb_spgemm_summa(cb_ctx* ctx, const cb_tile* A, const cb_tile* B, int semirin
             char* arecv = nullptr;
             const bool a_mine = a_root[s] == ctx->myproccol;
             const cb_tile* mypart = a_mine ? (mt->summa_parts[s] ? mt->summa_parts[s] : A) : nullptr;
-            if (pc > 1) status = bcast_tile(ctx, (ncclComm_t)ctx->nccl_row, a_root[s], a_mine, mypart, &aview, &arecv);
-            if (status == CB_OK) status = cb_spgemm_expand(ctx, a_mine ? mypart : &aview, bt, seg[s] - b0, semiring, dtype, &acc);
+            const cb_tile* apart = a_mine ? mypart : &aview;
+            const bool have = cache && (a_mine ? mt->spgemm_sent[s] != 0 : mt->spgemm_remote[s] != nullptr);
+            if (have) {
+                if (!a_mine) apart = mt->spgemm_remote[s];
+            } else if (pc > 1) {
+                status = bcast_tile(ctx, (ncclComm_t)ctx->nccl_row, a_root[s], a_mine, mypart, &aview, &arecv);
+                if (status == CB_OK && cache) {
+                    if (a_mine) mt->spgemm_sent[s] = 1;
+                    else {                                      // keep the received part: the buffer changes owner
+                        cb_tile* v = new cb_tile();
+                        const cb_tile_meta meta = cb_tile_get_meta(&aview);
+                        v->ctx = ctx;
+                        v->slab = arecv; v->slab_bytes = cb_layout(meta).total; v->owns_slab = true;
+                        cb_tile_bind(v, meta, v->slab);
+                        mt->spgemm_remote[s] = v;
+                        arecv = nullptr;
+                        apart = v;
+                    }
+                }
+            }
+            if (status == CB_OK) status = cb_spgemm_expand(ctx, apart, bt, seg[s] - b0, semiring, dtype, &acc);
             cudaFree(arecv);
         }
         cudaFree(brecv);

@@ -382,6 +382,7 @@ int cb_tile_free(cb_tile* t) {
     for (cb_tile* sub : t->summa_parts) cb_tile_free(sub);
     for (cb_tile* sub : t->summa_remote) cb_tile_free(sub);
     for (cb_tile* sub : t->summa_merged) cb_tile_free(sub);
+    for (cb_tile* sub : t->spgemm_remote) cb_tile_free(sub);
     delete t;
     return CB_OK;
 }

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--densities", type=int, nargs="*", default=[1, 10, 100, 1000])
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--grid", default="")
+    ap.add_argument("--no-cache-a", action="store_true", help="re-send A's parts on every call, as the reference's broadcasts do")
     ap.add_argument("--directed", action="store_true", help="do not symmetrise A (the generator takes < 2^31 candidate edges: scale 26 needs this)")
     a = ap.parse_args()
     cb = cbb200_loader.load_package()
@@ -56,6 +57,8 @@ def main():
         uid = holder[0]
     pr, pc = grid_shape(world) if not a.grid else tuple(int(v) for v in a.grid.lower().split("x"))
     ctx = cb.Context(local, rank, world, pr, pc, uid)
+    if a.no_cache_a:
+        ctx.summa_cache_a(False)
     n, k = 1 << a.scale, a.cols
     r0, rl = block_range(n, pr, ctx.myprocrow)
     c0, cl = block_range(n, pc, ctx.myproccol)
@@ -111,7 +114,7 @@ def main():
         B.free()
         if rank == 0:
             print(json.dumps(dict(workload=f"R-MAT scale {a.scale} x sparse 2^{a.scale} x {k}, {d} nonzeros per column, fp64 PlusTimes", n_gpus=world,
-                                  grid=f"{pr}x{pc}", seconds_per_multiply=round(float(np.mean(secs)), 5), runs=[round(s, 5) for s in secs],
+                                  grid=f"{pr}x{pc}", a_parts_cached=not a.no_cache_a and pc > 1, seconds_per_multiply=round(float(np.mean(secs)), 5), runs=[round(s, 5) for s in secs],
                                   nnz_A=nnzA, nnz_B=info[1], nnz_C=info[0],
                                   reference_published_seconds_scale26_4096_tasks=PUBLISHED.get(d) if a.scale == 26 else None)), flush=True)
     A.free()
