@@ -260,7 +260,13 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
     typedef typename Op::T T;
     typedef typename Op::TA TA;
     constexpr int EPL = 16 / sizeof(T);
+    // CB_EXP_* (tools/gpu_r02_m.sh): timing-only builds that take one piece of the walk away at a time, to see what separates K2
+    // from the arithmetic-free gather probe on L2-resident panels.  Their results are wrong by construction; never shipped.
+#ifdef CB_EXP_NOVAL
+    constexpr bool HASVAL = false;
+#else
     constexpr bool HASVAL = Op::akind != A_PATTERN;
+#endif
     const int lane = threadIdx.x & 31;
     const int vl = lane & (VW - 1);
     const int vshift = lane & ~(VW - 1);              // first lane of this virtual warp
@@ -303,6 +309,11 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < EPL; ++q) {
+#ifdef CB_EXP_NOFP
+                if (sizeof(T) == 4) { uint32_t u = *reinterpret_cast<const uint32_t*>(&x.v[r].v[q]) ^ *reinterpret_cast<uint32_t*>(&acc.v[r].v[q]); acc.v[r].v[q] = *reinterpret_cast<T*>(&u); }
+                (void)av;
+                continue;
+#endif
 #ifdef CB_FMA
                 acc.v[r].v[q] = (Op::first_touch && first) ? Op::mul(av, x.v[r].v[q]) : Op::madd(av, x.v[r].v[q], acc.v[r].v[q]);
 #else
@@ -330,14 +341,18 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
 #pragma unroll
                     for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::add(y.v[q], acc.v[r].v[q]);
                 }
+#ifndef CB_EXP_NOFLUSH
                 st16_stream<T>(d, acc.v[r]);
+#endif
 #pragma unroll
                 for (int q = 0; q < EPL; ++q) acc.v[r].v[q] = Op::id();
             }
         }
         first = true;
         ++ridx;
-        if (more) row = a.nzrows[ridx];
+#ifndef CB_EXP_NOFLUSH
+        if (more) row = a.nzrows[ridx];       // (reading the ids two rows ahead was measured: slower, profiles/r02_k2_rowid_lookahead.jsonl)
+#endif
     };
 
     constexpr int PF_AHEAD = 512;                        // entries: 2 KB of the column stream
@@ -372,7 +387,11 @@ __device__ __forceinline__ void cb_spmm_walk(const SpmmArgs& a, const int64_t ch
             if (HUB) hs = (int)__ldcs(hub.hubslot + s + base + vl);
         }
         // end-of-row flags of this virtual warp's VW entries, one bit each
+#ifdef CB_EXP_NOROWEND
+        const uint32_t fm = 0;
+#else
         const uint32_t fm = (__ballot_sync(0xffffffffu, cf < 0) >> vshift) & (VW == 32 ? 0xffffffffu : ((1u << VW) - 1u));
+#endif
         const uint32_t cm = (uint32_t)cf & 0x7fffffffu;
         // warp-uniform (every lane takes the same side of the branches below, so the shuffles inside them stay convergent):
         // all virtual warps of this warp still own a full block, hence no bounds predicates on the entries
