@@ -466,7 +466,7 @@ cb_spmm_kernel(const SpmmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K2P: the same walk with the row gathers PIPELINED THROUGH A REGISTER RING (the default kernel since round 2).
+// K2P: the same walk with the row gathers PIPELINED THROUGH A REGISTER RING (opt-in, built only with -DCB_BUILD_K2P: measured slower than K2).
 //
 // What the profile of K2 said (profiles/r02_*): on L2-resident panels a warp spends only ~45 % of its time with gathers in
 // flight - per step of VW nonzeros it waits once for the (column, value) entries and once per group of U gathers, and folds
