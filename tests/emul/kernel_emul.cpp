@@ -116,8 +116,29 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         a.Y = (char*)Y.data();
         std::fill(carry.begin(), carry.end(), (char)0x77);
         std::vector<uint8_t> hubcls;
+        std::vector<int32_t> wcolflag;
+        std::vector<T> wpanel;
         if (pipe == 3) {     // the round-1 walk with the entry prefetch
             syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL, true>(a); });
+        } else if (pipe == 5) {     // K2W: the nhub most used columns as bit 30 + rank in the column stream, their X rows packed into a panel
+            std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
+            for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
+            for (int64_t c = 0; c < n; ++c) order[c] = (int32_t)c;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cnt[x] > cnt[y]; });
+            int h = 0;
+            while (h < nhub && h < n && cnt[order[h]] >= 2) ++h;
+            std::vector<int32_t> rank_of((size_t)n, -1);
+            for (int r = 0; r < h; ++r) rank_of[order[r]] = r;
+            wcolflag.resize((size_t)t.nnz);
+            for (int64_t p = 0; p < t.nnz; ++p) {
+                const int32_t cf = t.colflag[p], r = rank_of[cf & 0x7fffffff];
+                wcolflag[p] = r >= 0 ? (int32_t)(((uint32_t)cf & 0x80000000u) | 0x40000000u | (uint32_t)r) : cf;
+            }
+            wpanel.resize((size_t)std::max(h, 1) * ld_elems);                          // exactly h rows: a rank >= h read is an ASan report
+            for (int r = 0; r < h; ++r) std::memcpy(&wpanel[(size_t)r * ld_elems], &X[(size_t)order[r] * ld_elems], row_bytes);
+            a.colflag = wcolflag.data();
+            a.win_delta = (const char*)wpanel.data() - (const char*)X.data();
+            syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL, false, true>(a); });
         } else if (pipe == 2) {     // with L2 residency hints: per-nonzero use class of its column (cb_hub.cu), classes <= 2 marked
             std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
             for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
@@ -248,6 +269,11 @@ int main(int argc, char** argv) {
     bad += run_case<SelectMax<int64_t>, 8, 1, 4, false>("prefetch selectmax_i64 k=13", 45, 50, 13, 32, 45, 75 + sd, false, 0, 0, 0, 3);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, true>("prefetch pt_f32 VW32 L=1200", 300, 3000, 128, 1200, 2900, 76 + sd, false, 0, 0, 0, 3);
     bad += run_case<OrAnd<A_PATTERN>, 8, 1, 4, false>("prefetch or_and VW8 L=700", 200, 2000, 24, 700, 1800, 77 + sd, false, 0, 0, 0, 3);
+    // K2W, the hub panel behind a window: hub entries flagged in the column stream and gathered from the packed panel
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, true>("window pt_f32 VW32 20 hubs", 300, 700, 128, 200, 900, 81 + sd, false, 0, 20, 0, 5);
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("window pt_f32 VW16 all hubs acc", 61, 97, 64, 32, 150, 82 + sd, true, 0, 1000, 0, 5);
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, true>("window pt_f64 R2 7 hubs", 30, 80, 128, 32, 70, 83 + sd, false, 0, 7, 0, 5);
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 1, 4, true>("window pt_f64 VW32 no hubs", 45, 50, 64, 32, 45, 84 + sd, false, 0, 0, 0, 5);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 8, true>("pipe+l2 pt_f32 VW32 L=200 D8", 300, 700, 128, 200, 900, 65 + sd, false, 0, 0, 0, 2);
     bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, false>("pipe+l2 pt_f64 R2 ragged acc", 30, 80, 100, 32, 70, 66 + sd, true, 0, 0, 0, 2);
     bad += run_case<MinPlus<int32_t>, 8, 1, 8, true>("pipe+l2 minplus_i32 VW8 D8", 70, 64, 32, 32, 60, 67 + sd, false, 0, 0, 0, 2);
