@@ -1,4 +1,4 @@
-"""Memory safety and warp convergence of the hot kernels without a GPU: csrc/cb_spmm_kernel.cuh and cb_spmm_hub_kernel.cuh are
+"""Memory safety and warp convergence of the hot kernels without a GPU (K2, its prefetch / register-ring / hub-window forms, K2H, K2R): csrc/cb_spmm_kernel.cuh and cb_spmm_hub_kernel.cuh are
 compiled UNMODIFIED for the host against a lock-step warp emulator (tests/emul/cuda_emul.h: 32 lanes = 32 threads, *_sync
 intrinsics are rendezvous points; CTAs, clusters, shared memory and reads of a neighbour CTA's shared memory for the hub
 variant) and run under AddressSanitizer + UBSan on small tiles with hub rows, empty rows, ragged widths, column slabs and the
