@@ -80,3 +80,14 @@ def test_host_evaluation_of_sampled_rows_matches_the_oracle():
                 assert np.allclose(got[i], ref[r].astype(np.float64), rtol=bench.TOL[w["xdt"]], atol=0)
             else:
                 assert np.array_equal(got[i], ref[r])
+
+
+def test_every_tool_script_compiles_and_shell_scripts_parse():
+    # the scripts under tools/ are how the files under profiles/ were made; they only run on a GPU box, so at least keep them loadable
+    import glob
+    import py_compile
+    import subprocess
+    for f in sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
+        py_compile.compile(f, doraise=True)
+    for f in sorted(glob.glob(os.path.join(ROOT, "tools", "*.sh"))):
+        assert subprocess.run(["bash", "-n", f]).returncode == 0, f
