@@ -87,7 +87,9 @@ extern "C" int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const c
     *out = nullptr;
     const size_t vs = val_dtype == CB_PATTERN ? 0 : cb_dtype_size(val_dtype);
     if (val_dtype != CB_PATTERN && !vs) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_tile_from_mm_text: value dtype %d", val_dtype);
-    if (nbytes >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_mm_text: %lld bytes of text on one rank", (long long)nbytes);
+    // a share too large for the 32-bit positions used here is not an error of this rank alone: like a number the parser refuses, it
+    // sends EVERY rank to the host parser (the decision is agreed on below, before anybody enters the exchange)
+    const bool too_large = nbytes >= (int64_t(1) << 30);
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute;
     const int sm = ctx->sm_count;
@@ -96,7 +98,7 @@ extern "C" int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const c
     unsigned int hard = 0;
     int64_t *d_rows = nullptr, *d_cols = nullptr;
     char* d_vals = nullptr;
-    if (nbytes > 0) {
+    if (nbytes > 0 && !too_large) {
         char* d_text = nullptr;
         uint8_t* d_flag = nullptr;
         int64_t *d_ls = nullptr, *d_count = nullptr;
@@ -138,7 +140,6 @@ extern "C" int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const c
         CB_CUDA(ctx, cudaGetLastError());
         mm_flags_kernel<<<grid_for(cap, sm), 256, 0, st>>>(d_r2, cap, d_used);
         CB_LAUNCHED(ctx);
-        if (cap >= (int64_t(1) << 31)) return cb_fail(ctx, CB_ERR_TOO_LARGE, "cb_tile_from_mm_text: %lld lines on one rank", (long long)nlines);
         CB_TRY(compact<int64_t>(ctx, sc, d_r2, d_used, cap, d_rows, d_count));
         CB_TRY(compact<int64_t>(ctx, sc, d_c2, d_used, cap, d_cols, d_count));
         switch (vs) {
@@ -153,8 +154,8 @@ extern "C" int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const c
         CB_CUDA(ctx, cudaStreamSynchronize(st));
     }
     // every rank must know whether any share held a number the device parser cannot reproduce before anyone enters the exchange
-    int64_t anyhard = hard;
+    int64_t anyhard = (int64_t)hard + (too_large ? 1 : 0);
     CB_TRY(cb_comm_allreduce_i64(ctx, 0, 1, &anyhard, 1));
-    if (anyhard) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_tile_from_mm_text: the file holds numbers outside the device parser's exact range (parse it on the host)");
+    if (anyhard) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "cb_tile_from_mm_text: the file holds numbers outside the device parser's exact range, or a share of 1 GiB or more (parse it on the host)");
     return cb_ingest_device_coo(ctx, gm, gn, nz, d_rows, d_cols, d_vals, val_dtype, dup_op, out);
 }

@@ -270,7 +270,7 @@ public:
                                                         dup_rule<BinOp>::value, &dtile);
                 if (status == CB_OK) done = true;
                 else if (status != CB_ERR_UNSUPPORTED) cb_check(status, ctx, "cb_tile_from_mm_text");
-                else SpParHelper::Print("COMBBLAS: " + filename + " holds numbers outside the device parser's exact range, parsing it on the host\n");
+                else SpParHelper::Print("COMBBLAS: " + filename + " is not for the device parser (numbers outside its exact range, or a share of 1 GiB or more), parsing it on the host\n");
             }
             if (!done) {
                 std::vector<int64_t> rows, cols;

@@ -118,7 +118,8 @@ int cb_tile_from_distributed_coo(cb_ctx* ctx, int64_t gm, int64_t gn, int64_t nz
  * entry 1), 4 = symmetric / hermitian (the transpose of every off-diagonal entry is added).  Blank lines and lines that do not
  * start with two integers are skipped, like the reference's sscanf loop does.  Values are converted to val_dtype with a C cast
  * (CB_U8: value != 0).  Returns CB_ERR_UNSUPPORTED on every rank, before anything is exchanged, when any share holds a number the
- * device parser does not convert (more than 19 significant digits, a subnormal or overflowing value, inf / nan, hexadecimal);
+ * device parser does not convert (more than 19 significant digits, a subnormal or overflowing value, inf / nan, hexadecimal) or
+ * is 1 GiB or larger (32-bit positions);
  * everything else is the correctly rounded double strtod gives.  The caller then parses that file on the host and uses
  * cb_tile_from_distributed_coo.  Collective. */
 int cb_tile_from_mm_text(cb_ctx* ctx, int64_t gm, int64_t gn, const char* text, int64_t nbytes, int flags, int val_dtype, int dup_op,
