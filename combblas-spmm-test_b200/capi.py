@@ -381,7 +381,7 @@ class Context:
         _check(lib().cb_spmm_k2_l2(self.h, int(budget_mb)), self.h)
 
     def k2_pipe(self, depth=-1):
-        """Variant of the local multiply: 0 K2, 1 K2 + entry prefetch, 16 K2T (bulk-copy ring), 32 K2W (hub panel under a persisting L2 window, budget k2_l2), 4 / 8 K2P ring depth, -1 default."""
+        """Variant of the local multiply: 0 K2, 1 K2 + entry prefetch, 16 K2T (bulk-copy ring), 32 K2W (hub panel under a persisting L2 window, budget k2_l2), 64 K2 with persistent warps, 4 / 8 K2P ring depth, -1 default."""
         _check(lib().cb_spmm_k2_pipe(self.h, int(depth)), self.h)
 
     def summa_cache_a(self, on=True):

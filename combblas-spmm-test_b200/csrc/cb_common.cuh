@@ -43,6 +43,7 @@ struct cb_ctx {
     int ring_depth = -1;              // K2R ring depth: -1 = follow CB_SPMM_RING, 0 = off (cb_spmm_ring_config)
     int k2_l2_mb = -1;                // K2P L2 residency hints: budget in MB for the rows kept with evict_last; 0 off, -1 default
     int k2_pipe = -1;                 // variant of the local multiply: -1 default, 0 K2, 1 prefetch, 4 / 8 K2P ring depth, 16 K2T, 32 K2W
+    unsigned* k2_counter = nullptr;   // chunk counter of the persistent-warp form of K2 (cb_spmm_k2_pipe 64)
     void* win_panel = nullptr;        // K2W: packed rows of the most used columns, kept in L2 by a persisting access-policy window
     size_t win_panel_bytes = 0;
     size_t win_l2_limit = 0;          // persisting L2 set-aside currently configured on the device

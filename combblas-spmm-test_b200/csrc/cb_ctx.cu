@@ -115,6 +115,7 @@ int cb_ctx_destroy(cb_ctx* c) {
     cudaFree(c->ws_x);
     cudaFree(c->ws_y);
     cudaFree(c->win_panel);
+    cudaFree(c->k2_counter);
     if (c->h2d) {
         cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h);
         cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h);

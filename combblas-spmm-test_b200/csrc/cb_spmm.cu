@@ -144,6 +144,15 @@ int cb_spmm_launch(cb_ctx* ctx, cudaStream_t stream, const cb_tile* t, const voi
             }
         }
     }
+    {
+        static const int pipe_env2 = getenv("CB_K2_PIPE") ? atoi(getenv("CB_K2_PIPE")) : -1;
+        const int pipe = ctx->k2_pipe >= 0 ? ctx->k2_pipe : pipe_env2;
+        if (pipe == 64) {                         // K2 with persistent warps: the chunk counter starts at zero on this stream
+            if (!ctx->k2_counter) CB_CUDA(ctx, cudaMalloc((void**)&ctx->k2_counter, sizeof(unsigned)));
+            CB_CUDA(ctx, cudaMemsetAsync(ctx->k2_counter, 0, sizeof(unsigned), stream));
+            p.persist_counter = ctx->k2_counter;
+        }
+    }
     struct WinOff {                               // the window must not outlive the multiply
         cudaStream_t s; bool on;
         ~WinOff() {
@@ -180,7 +189,7 @@ int cb_spmm_k2_l2(cb_ctx* ctx, int budget_mb) {
 
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth) {
     if (!ctx) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: null ctx");
-    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8 && depth != 16 && depth != 32) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth, 16 bulk-copy ring, 32 hub panel under an L2 window)", depth);
+    if (depth != -1 && depth != 0 && depth != 1 && depth != 4 && depth != 8 && depth != 16 && depth != 32 && depth != 64) return cb_fail(ctx, CB_ERR_INVALIDPARAMS, "cb_spmm_k2_pipe: mode %d (-1 default, 0 round-1 walk, 1 round-1 walk with entry prefetch, 4 / 8 ring depth, 16 bulk-copy ring, 32 hub panel under an L2 window, 64 persistent warps)", depth);
     ctx->k2_pipe = depth;
     return CB_OK;
 }

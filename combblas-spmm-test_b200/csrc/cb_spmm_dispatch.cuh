@@ -45,13 +45,14 @@ struct LaunchParams {
     const uint8_t* hubcls = nullptr; // non-null: K2P gathers rows of columns of class <= cls_max with evict_last, others evict_first
     int cls_max = -1;
     int pipe = -1;                  // register-ring depth of the pipelined walk K2P: 4 or 8; 0 = the round-1 walk; -1 = default
+    unsigned* persist_counter = nullptr;    // non-null: K2 with persistent warps (chunk counter, zeroed on the stream before the launch)
     const int32_t* win_colflag = nullptr;   // non-null: K2W - this column stream (hub columns as bit 30 + rank) and the packed hub panel at X + win_delta
     int64_t win_delta = 0;
 };
 
 enum { CB_HUB_FALLBACK = -77 };     // internal: the hub launch is not possible here, run plain K2
 
-template <class Op, int VW, int R, int U, int MINB, bool FULL, int PIPE = 0, bool POL = false>      // PIPE: 0 K2, 1 K2P (ring), 2 K2 with prefetch, 3 K2W (hub panel)
+template <class Op, int VW, int R, int U, int MINB, bool FULL, int PIPE = 0, bool POL = false>      // PIPE: 0 K2, 1 K2P (ring), 2 K2 with prefetch, 3 K2W (hub panel), 4 K2 with persistent warps
 static int launch_layout_f(const LaunchParams& p) {
     const cb_tile* t = p.t;
     SpmmArgs a;
@@ -83,6 +84,11 @@ static int launch_layout_f(const LaunchParams& p) {
         if constexpr (PIPE == 1) cb_spmm_pipe_kernel<Op, VW, R, U, MINB, FULL, POL><<<grid, 256, 0, p.stream>>>(a);      // U = ring depth
         else if constexpr (PIPE == 2) cb_spmm_kernel<Op, VW, R, U, MINB, FULL, true><<<grid, 256, 0, p.stream>>>(a);
         else if constexpr (PIPE == 3) cb_spmm_kernel<Op, VW, R, U, MINB, FULL, false, true><<<grid, 256, 0, p.stream>>>(a);
+        else if constexpr (PIPE == 4) {
+            // one launch fills the chip: MINB CTAs per SM (the kernel's own occupancy bound), never more CTAs than there are chunk groups
+            const unsigned full_chip = (unsigned)p.ctx->sm_count * (unsigned)MINB;
+            cb_spmm_persist_kernel<Op, VW, R, U, MINB, FULL><<<dim3(grid.x < full_chip ? grid.x : full_chip, 1), 256, 0, p.stream>>>(a, p.persist_counter);
+        }
         else cb_spmm_kernel<Op, VW, R, U, MINB, FULL><<<grid, 256, 0, p.stream>>>(a);
     }
     CB_LAUNCHED(p.ctx);
@@ -124,6 +130,19 @@ static int launch_win(const LaunchParams& p) {
     else {
         if (p.total_row_bytes % (VW * R * 16) != 0) return CB_HUB_FALLBACK;
         return launch_layout_f<Op, VW, R, U, MINB, true, 3>(p);
+    }
+}
+
+// K2 with persistent warps (single column slab only; the operand types of the benchmark workloads)
+template <class Op, int VW, int R, int U, int MINB>
+static int launch_persist(const LaunchParams& p) {
+    typedef typename Op::T T;
+    constexpr bool built = Op::akind == A_SAME && (std::is_same<T, float>::value || std::is_same<T, double>::value || std::is_same<T, int32_t>::value);
+    if constexpr (!built) return CB_HUB_FALLBACK;
+    else {
+        if (p.total_row_bytes > VW * R * 16) return CB_HUB_FALLBACK;          // more than one column slab: plain K2
+        if (p.total_row_bytes % (VW * R * 16) == 0) return launch_layout_f<Op, VW, R, U, MINB, true, 4>(p);
+        return launch_layout_f<Op, VW, R, U, MINB, false, 4>(p);
     }
 }
 
@@ -289,6 +308,12 @@ static int launch_op(const LaunchParams& p) {
                 else if (nvec == 64) s = launch_win<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
             } else if (pipe == 16 && slab_force < 16 && (nvec == 8 || nvec == 16 || nvec == 32)) {
                 s = nvec == 8 ? launch_tma<Op, 8>(p) : nvec == 16 ? launch_tma<Op, 16>(p) : launch_tma<Op, 32>(p);
+            }
+            if (s == CB_HUB_FALLBACK && p.persist_counter && slab_force < 16 && nvec > 4) {
+                if (nvec <= 8) s = wide ? launch_persist<Op, 8, 1, CB_WIDE_U, WB>(p) : launch_persist<Op, 8, 1, CB_DEEP_U, DB>(p);
+                else if (nvec <= 16) s = wide ? launch_persist<Op, 16, 1, CB_WIDE_U, WB>(p) : launch_persist<Op, 16, 1, CB_DEEP_U, DB>(p);
+                else if (nvec <= 32) s = wide ? launch_persist<Op, 32, 1, CB_WIDE_U, WB>(p) : launch_persist<Op, 32, 1, CB_DEEP_U, DB>(p);
+                else if (nvec <= 64) s = launch_persist<Op, 32, 2, CB_DEEP_U / 2, DB>(p);
             }
             if (s != CB_HUB_FALLBACK) {
             } else if (pipe == 1 && nvec > 4) {

@@ -465,6 +465,23 @@ cb_spmm_kernel(const SpmmArgs a) {
     cb_spmm_walk<Op, VW, R, U, FULL, false, PF, WIN>(a, warp * NV + ((threadIdx.x & 31) / VW), HubSrc());
 }
 
+// K2 with PERSISTENT warps (opt-in, cb_spmm_k2_pipe(ctx, 64)): as many CTAs as fit the chip at once; every warp takes the next group
+// of 32/VW chunks from a counter until none is left.  The plain kernel retires a CTA when its slowest warp is done and pays the
+// launch of 15 000 - 130 000 CTAs of ~16 steps each: ncu shows 37 - 42 % of the warp slots occupied where the register limit allows
+// 50 - 62 % (profiles/r02_k2w_s24f32_full.md, r01_c2_spmm_kernel_full.md).  Same walk, same bits.
+template <class Op, int VW, int R, int U, int MINB, bool FULL>
+__global__ void __launch_bounds__(256, MINB)
+cb_spmm_persist_kernel(const SpmmArgs a, unsigned* __restrict__ counter) {
+    constexpr int NV = 32 / VW;
+    for (;;) {
+        unsigned base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, (unsigned)NV);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int64_t)base >= a.nchunks) break;                                 // warp-uniform
+        cb_spmm_walk<Op, VW, R, U, FULL, false>(a, (int64_t)base + (threadIdx.x & 31) / VW, HubSrc());
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // K2P: the same walk with the row gathers PIPELINED THROUGH A REGISTER RING (opt-in, built only with -DCB_BUILD_K2P: measured slower than K2).
 //

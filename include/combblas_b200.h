@@ -272,7 +272,8 @@ int cb_spmm_k2_config(cb_ctx* ctx, int slab_bytes, int point);
  * mbarrier completion, csrc/cb_spmm_tma_kernel.cuh; fp32 / int32 panels of 128-, 256- or 512-byte rows, anything else runs K2),
  * 32 = K2W (the rows of the most used columns - cb_spmm_k2_l2's budget, default 64 MB - packed into a panel that a persisting L2
  * access-policy window keeps on the chip; fp32 / fp64 PlusTimes panels of 256-byte rows and wider, anything else runs K2),
- * 4 / 8 = ring depth of K2P (register ring; only in builds with -DCB_BUILD_K2P), -1 = the build's default. */
+ * 64 = K2 with persistent warps (one launch fills the chip, warps take chunk groups from a counter; fp32 / fp64 / int32 panels of one
+ * column slab, anything else runs K2), 4 / 8 = ring depth of K2P (register ring; only in builds with -DCB_BUILD_K2P), -1 = the build's default. */
 int cb_spmm_k2_pipe(cb_ctx* ctx, int depth);
 /* L2 residency hints of K2P for tiles whose X rows do not fit in L2: the rows of the tile's most used columns - as many as
  * fit `budget_mb` megabytes at the current row width - are gathered with the evict_last priority, every other row with

@@ -120,6 +120,10 @@ static long run_case(const char* name, int64_t m, int64_t n, int k_elems /* elem
         std::vector<T> wpanel;
         if (pipe == 3) {     // the round-1 walk with the entry prefetch
             syncs = emul::launch(grid, dim3(256), [&] { cb_spmm_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL, true>(a); });
+        } else if (pipe == 6) {     // K2 with persistent warps: two CTAs take chunk groups from a counter until none is left
+            unsigned counter = 0;
+            syncs = emul::launch(dim3(2, 1), dim3(256), [&] { cb_spmm_persist_kernel<Op, VW, R, (U < 4 ? U : 4), 3, FULL>(a, &counter); });
+            if ((int64_t)counter < t.nchunks) { std::printf("%-28s persistent warps left chunks behind\n", name); ++syncs; Y[0] = T(); }
         } else if (pipe == 5) {     // K2W: the nhub most used columns as bit 30 + rank in the column stream, their X rows packed into a panel
             std::vector<int32_t> cnt((size_t)n, 0), order((size_t)n);
             for (int32_t cf : t.colflag) ++cnt[cf & 0x7fffffff];
@@ -269,6 +273,11 @@ int main(int argc, char** argv) {
     bad += run_case<SelectMax<int64_t>, 8, 1, 4, false>("prefetch selectmax_i64 k=13", 45, 50, 13, 32, 45, 75 + sd, false, 0, 0, 0, 3);
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, true>("prefetch pt_f32 VW32 L=1200", 300, 3000, 128, 1200, 2900, 76 + sd, false, 0, 0, 0, 3);
     bad += run_case<OrAnd<A_PATTERN>, 8, 1, 4, false>("prefetch or_and VW8 L=700", 200, 2000, 24, 700, 1800, 77 + sd, false, 0, 0, 0, 3);
+    // K2 with persistent warps (single column slab)
+    bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("persist pt_f32 VW16", 61, 97, 64, 32, 150, 91 + sd, false, 0, 0, 0, 6);
+    bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, false>("persist pt_f32 VW32 k=100 acc", 40, 200, 100, 32, 90, 92 + sd, true, 0, 0, 0, 6);
+    bad += run_case<PlusTimes<double, A_SAME>, 32, 2, 4, true>("persist pt_f64 R2 larger", 300, 700, 128, 64, 900, 93 + sd, false, 0, 0, 0, 6);
+    bad += run_case<MinPlus<int32_t>, 8, 1, 4, true>("persist minplus_i32 VW8 larger", 400, 900, 32, 64, 700, 94 + sd, false, 0, 0, 0, 6);
     // K2W, the hub panel behind a window: hub entries flagged in the column stream and gathered from the packed panel
     bad += run_case<PlusTimes<float, A_SAME>, 32, 1, 4, true>("window pt_f32 VW32 20 hubs", 300, 700, 128, 200, 900, 81 + sd, false, 0, 20, 0, 5);
     bad += run_case<PlusTimes<float, A_SAME>, 16, 1, 4, true>("window pt_f32 VW16 all hubs acc", 61, 97, 64, 32, 150, 82 + sd, true, 0, 1000, 0, 5);

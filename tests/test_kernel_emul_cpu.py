@@ -20,7 +20,7 @@ def test_k2_and_fixup_on_the_warp_emulator_under_asan(tmp_path):
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)      # a dead-locked warp = diverged *_sync = timeout
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "emulation ok" in r.stdout and "mismatches=0" in r.stdout and "runtime error" not in r.stderr
-    assert r.stdout.count("mismatches=0") == 64 and "differs from K2" not in r.stdout     # 12 K2 + 6 narrow + 7 K2 with entry prefetch + 14 K2P + 4 K2P with L2 hints + 4 K2W + 8 K2H + 9 K2R cases (argument 2 = a second seed)
+    assert r.stdout.count("mismatches=0") == 68 and "differs from K2" not in r.stdout     # 12 K2 + 6 narrow + 7 K2 with entry prefetch + 14 K2P + 4 K2P with L2 hints + 4 K2W + 4 persistent-warp K2 + 8 K2H + 9 K2R cases (argument 2 = a second seed)
 
 
 def test_device_number_parser_against_strtod(tmp_path):

@@ -105,6 +105,34 @@ def test_bulk_copy_ring_matches_k2_bitwise(ctx, monkeypatch, case, k, stages, wa
     assert t is not None and a.tobytes() == b.tobytes(), "the bulk-copy ring differs from K2"
 
 
+@pytest.mark.parametrize("case,k", [("pt_f32", 128), ("pt_f32", 64), ("pt_f32", 100), ("pt_f64", 128), ("pt_f64", 32), ("minplus_i32", 32),
+                                    ("pt_f32", 300), ("selmax_i32", 16)])
+def test_persistent_warps_match_k2_bitwise(ctx, case, k):
+    """K2 with persistent warps (cb_spmm_k2_pipe(ctx, 64)): one launch fills the chip and every warp takes chunk groups from a
+    counter.  Same walk, so the same bits - overwrite and accumulate, split rows included; panels of more than one column slab
+    (k = 300) and operand types the variant is not built for (SelectMax) quietly run K2.  Opt-in; the one variant of round 2 that
+    beats K2: C2 0.733 -> 0.661 ms, C5 2.25 -> 2.05 ms, equal on the DRAM-bound inputs (profiles/r02_sweep_h_persistent.jsonl)."""
+    sr, adt, xdt, kind = CASES[case]
+    n, I, J = O.rmat_matrix(13, 16, seed=0)
+    V = None if adt is None else O.matrix_values(I, J, n, 1, adt)
+    X = O.dense_operand(n, k, 42, xdt, kind)
+    t = ctx.tile_from_coo(n, n, I, J, V)
+    Xd, Y0, Y1 = ctx.dense_from(X), ctx.dense(n, k, xdt), ctx.dense(n, k, xdt)
+    try:
+        ctx.k2_pipe(0)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y0, sr, accumulate=acc)
+        ctx.k2_pipe(64)
+        for acc in (False, True):
+            ctx.spmm_local(t, Xd, Y1, sr, accumulate=acc)
+        a, b = Y0.download(), Y1.download()
+    finally:
+        ctx.k2_pipe(-1)
+        for h in (t, Xd, Y0, Y1):
+            h.free()
+    assert a.tobytes() == b.tobytes(), "persistent warps differ from K2"
+
+
 @pytest.mark.parametrize("dtype,k,mb", [(np.float32, 128, 1), (np.float32, 64, 1), (np.float64, 128, 2), (np.float64, 64, 1), (np.float32, 128, 64),
                                         (np.float32, 96, 1)])
 def test_hub_panel_under_l2_window_matches_k2_bitwise(ctx, dtype, k, mb):

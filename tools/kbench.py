@@ -52,6 +52,8 @@ for name in a.workloads:
             elif kind == "tma":                      # bulk-copy ring (K2T): s = stages (2 / 4), w = warps per CTA
                 os.environ["CB_TMA_STAGES"] = str(o.get("s", 0)); os.environ["CB_TMA_WARPS"] = str(o.get("w", 0))
                 ctx.k2_pipe(16)
+            elif kind == "persist":                  # K2 with persistent warps (chunk groups from a counter)
+                ctx.k2_config(0, o.get("point", -1)); ctx.k2_pipe(64)
             elif kind == "win":                      # K2W: hub panel of mb megabytes under a persisting L2 window
                 ctx.k2_l2(o.get("mb", 64)); ctx.k2_pipe(32)
             elif kind == "hub":
